@@ -1,0 +1,382 @@
+"""ctypes binding of ``libica_b200.so`` (C-ABI in ``include/ica_b200.h``).
+
+This is the only door from Python to the arithmetic: there is NO CPU fallback.  If the shared
+library is missing it is built in-tree with nvcc (``build.py``); if that is impossible, or a
+compute entry point is called without a visible GPU, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import build as _build
+
+MAX_PARAMS = 8
+MAX_SCALES = 12
+TRAJ_STRIDE = 12
+
+FLAG_RECORD_TRAJECTORY = 1
+FLAG_WRITE_DI_IW = 2
+
+DTYPE_F32, DTYPE_U8, DTYPE_F64 = 0, 1, 2
+
+ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_ALLOC = -1, -2, -3, -4
+
+
+class Config(C.Structure):
+    """Mirror of ``struct ica_config``."""
+    _fields_ = [
+        ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("channels", C.c_int32),
+        ("gray_as_rgb", C.c_int32), ("nscales", C.c_int32), ("nu", C.c_double),
+        ("transform_type", C.c_int32), ("robust_type", C.c_int32), ("robust_loop", C.c_int32),
+        ("lambda_", C.c_double), ("tol", C.c_double), ("max_iter", C.c_int32), ("delta", C.c_int32),
+        ("nanifoutside", C.c_int32), ("flags", C.c_uint32), ("blocks_per_pair", C.c_int32),
+    ]
+
+
+# every symbol include/ica_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+_PD = C.POINTER(C.c_double)
+_PI = C.POINTER(C.c_int32)
+_PF = C.POINTER(C.c_float)
+SIGNATURES = {
+    "ica_last_error": (C.c_char_p, []),
+    "ica_version": (C.c_int, []),
+    "ica_device_count": (C.c_int, []),
+    "ica_set_device": (C.c_int, [C.c_int]),
+    "ica_get_constants": (C.c_int, [_PD]),
+    "ica_plan_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
+    "ica_plan_destroy": (C.c_int, [_P]),
+    "ica_plan_set_transform_types": (C.c_int, [_P, _PI, C.c_int32]),
+    "ica_plan_level_shapes": (C.c_int, [_P, _PI, _PI]),
+    "ica_plan_device_bytes": (C.c_size_t, [_P]),
+    "ica_plan_run_device": (C.c_int, [_P, _P, _P, _P, _P]),
+    "ica_plan_run_host": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),
+    "ica_plan_last_host_run_ms": (C.c_int, [_P, _PF]),
+    "ica_plan_get_results": (C.c_int, [_P, _P, _P, _P]),
+    "ica_plan_get_trajectory": (C.c_int, [_P, _P, _P]),
+    "ica_plan_get_di_iw_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
+    "ica_plan_get_level_device": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P), _PI]),
+    "ica_plan_last_launch_count": (C.c_int64, [_P]),
+    "ica_plan_enable_timing": (C.c_int, [_P, C.c_int32]),
+    "ica_plan_get_timing": (C.c_int, [_P, _PF, _PI, _PF, _PI]),
+    "ica_warp_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "ica_rescale_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _PI, _PI]),
+    "ica_zoom_size": (C.c_int, [C.c_int32, C.c_int32, C.c_double, _PI, _PI]),
+    "ica_gradient_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "ica_hessian_b_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P,
+                                     C.c_int32, C.c_double, C.c_int32, C.c_int32, _P, _P]),
+    "ica_nparams": (C.c_int, [C.c_int32]),
+    "ica_params2matrix": (C.c_int, [_P, C.c_int32, _P]),
+    "ica_update_transform": (C.c_int, [_P, _P, C.c_int32]),
+    "ica_zoom_in_parameters": (C.c_int, [_P, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, _P]),
+    "ica_inverse_hessian": (C.c_int, [_P, C.c_int32, _P]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """Loads (building first if needed) the native library; raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            try:
+                path = _build.build()
+            except Exception as exc:  # noqa: BLE001
+                raise RuntimeError(
+                    "libica_b200.so is missing and could not be built; the B200 path has no CPU "
+                    f"fallback ({exc})") from exc
+        handle = C.CDLL(path)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the library lacks a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    return lib().ica_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc == ERR_INVALID:
+        raise ValueError(msg)
+    raise RuntimeError(f"libica_b200 error {rc}: {msg}")
+
+
+def device_count() -> int:
+    return int(lib().ica_device_count())
+
+
+def set_device(index: int) -> None:
+    check(lib().ica_set_device(int(index)))
+
+
+def require_gpu() -> None:
+    if device_count() < 1:
+        raise RuntimeError("no CUDA device visible: inverse_compositional_algorithm_b200 has no "
+                           "CPU fallback")
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_P)
+
+
+# ------------------------------------------------------------------ scalar algebra (host side)
+def nparams(ttype: int) -> int:
+    n = lib().ica_nparams(int(ttype))
+    if n < 0:
+        raise ValueError("Unknown transform type")
+    return n
+
+
+def params2matrix(p: np.ndarray, ttype: int) -> np.ndarray:
+    pp = np.zeros(MAX_PARAMS)
+    pp[:min(len(p), MAX_PARAMS)] = p[:MAX_PARAMS]
+    m = np.empty(9)
+    check(lib().ica_params2matrix(_ptr(pp), int(ttype), _ptr(m)))
+    return m.reshape(3, 3)
+
+
+def update_transform(p: np.ndarray, dp: np.ndarray, ttype: int) -> np.ndarray:
+    n = nparams(ttype)
+    pp = np.zeros(MAX_PARAMS)
+    dd = np.zeros(MAX_PARAMS)
+    pp[:n] = p[:n]
+    dd[:n] = dp[:n]
+    check(lib().ica_update_transform(_ptr(pp), _ptr(dd), int(ttype)))
+    return pp[:n].copy()
+
+
+def zoom_in_parameters(p: np.ndarray, ttype: int, nx, ny, nxx, nyy) -> np.ndarray:
+    n = nparams(ttype)
+    pp = np.zeros(MAX_PARAMS)
+    pp[:n] = p[:n]
+    out = np.zeros(MAX_PARAMS)
+    check(lib().ica_zoom_in_parameters(_ptr(pp), int(ttype), float(nx), float(ny), float(nxx),
+                                       float(nyy), _ptr(out)))
+    return out[:n].copy()
+
+
+def zoom_size(nx: int, ny: int, factor: float):
+    a, b = C.c_int32(), C.c_int32()
+    check(lib().ica_zoom_size(int(nx), int(ny), float(factor), C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def inverse_hessian(H: np.ndarray) -> np.ndarray:
+    H = np.ascontiguousarray(H, dtype=np.float64)
+    n = H.shape[0]
+    out = np.empty((n, n))
+    check(lib().ica_inverse_hessian(_ptr(H), n, _ptr(out)))
+    return out
+
+
+def constants() -> np.ndarray:
+    out = np.empty(5)
+    check(lib().ica_get_constants(out.ctypes.data_as(_PD)))
+    return out
+
+
+# ------------------------------------------------------------------ stateless GPU helpers
+def _as_image_f32(image) -> np.ndarray:
+    img = np.ascontiguousarray(image, dtype=np.float32)
+    if img.ndim == 2:
+        img = img[:, :, None]
+    if img.ndim != 3 or img.shape[2] not in (1, 3):
+        raise ValueError("image must be (H, W), (H, W, 1) or (H, W, 3)")
+    return img
+
+
+def warp(image, matrix) -> np.ndarray:
+    require_gpu()
+    img = _as_image_f32(image)
+    m = np.ascontiguousarray(matrix, dtype=np.float64).reshape(9)
+    out = np.empty_like(img)
+    check(lib().ica_warp_host(_ptr(img), img.shape[0], img.shape[1], img.shape[2], _ptr(m), _ptr(out)))
+    return out
+
+
+def rescale(image, nu: float) -> np.ndarray:
+    require_gpu()
+    img = _as_image_f32(image)
+    nxx, nyy = zoom_size(img.shape[1], img.shape[0], nu)
+    out = np.empty((max(nyy, 1), max(nxx, 1), img.shape[2]), dtype=np.float32)
+    oh, ow = C.c_int32(), C.c_int32()
+    check(lib().ica_rescale_host(_ptr(img), img.shape[0], img.shape[1], img.shape[2], float(nu),
+                                 _ptr(out), C.byref(oh), C.byref(ow)))
+    assert (oh.value, ow.value) == out.shape[:2]
+    return out
+
+
+def gradient(image, delta: int, nanifoutside: bool):
+    require_gpu()
+    img = _as_image_f32(image)
+    ix = np.empty_like(img)
+    iy = np.empty_like(img)
+    check(lib().ica_gradient_host(_ptr(img), img.shape[0], img.shape[1], img.shape[2], int(delta),
+                                  1 if nanifoutside else 0, _ptr(ix), _ptr(iy)))
+    return ix, iy
+
+
+def hessian_b(I1, I2, ttype: int, p, robust_type: int, lambda_: float, delta: int,
+              nanifoutside: bool, gray_as_rgb: bool = False):
+    require_gpu()
+    a = _as_image_f32(I1)
+    b = _as_image_f32(I2)
+    if a.shape != b.shape:
+        raise ValueError("I1 and I2 must have the same dimensions")
+    n = nparams(ttype)
+    pp = np.zeros(MAX_PARAMS)
+    pp[:n] = np.asarray(p, dtype=np.float64)[:n]
+    H = np.zeros((n, n))
+    bv = np.zeros(n)
+    check(lib().ica_hessian_b_host(_ptr(a), _ptr(b), a.shape[0], a.shape[1], a.shape[2],
+                                   1 if gray_as_rgb else 0, int(ttype), _ptr(pp), int(robust_type),
+                                   float(lambda_), int(delta), 1 if nanifoutside else 0, _ptr(H),
+                                   _ptr(bv)))
+    return H, bv
+
+
+# ------------------------------------------------------------------ plan
+class Plan:
+    """Owner of one ``ica_plan`` (pyramids, per-pair state and partial buffers for B pairs)."""
+
+    def __init__(self, *, batch, height, width, channels, nscales, nu, transform_type, robust_type,
+                 robust_loop, lambda_, tol, max_iter, delta, nanifoutside, gray_as_rgb=False,
+                 record_trajectory=False, write_di_iw=False, blocks_per_pair=0):
+        require_gpu()
+        flags = (FLAG_RECORD_TRAJECTORY if record_trajectory else 0) | (
+            FLAG_WRITE_DI_IW if write_di_iw else 0)
+        self.cfg = Config(batch=batch, height=height, width=width, channels=channels,
+                          gray_as_rgb=1 if gray_as_rgb else 0, nscales=nscales, nu=nu,
+                          transform_type=int(transform_type), robust_type=int(robust_type),
+                          robust_loop=1 if robust_loop else 0, lambda_=lambda_, tol=tol,
+                          max_iter=max_iter, delta=delta, nanifoutside=1 if nanifoutside else 0,
+                          flags=flags, blocks_per_pair=blocks_per_pair)
+        self._h = _P()
+        check(lib().ica_plan_create(C.byref(self.cfg), C.byref(self._h)))
+        self.batch, self.height, self.width, self.channels = batch, height, width, channels
+        self.nscales, self.max_iter = nscales, max_iter
+        self.record_trajectory, self.write_di_iw = record_trajectory, write_di_iw
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ica_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_transform_types(self, types):
+        t = np.ascontiguousarray(types, dtype=np.int32)
+        check(lib().ica_plan_set_transform_types(self._h, t.ctypes.data_as(_PI), t.size))
+
+    def level_shapes(self):
+        nx = np.zeros(self.nscales, dtype=np.int32)
+        ny = np.zeros(self.nscales, dtype=np.int32)
+        check(lib().ica_plan_level_shapes(self._h, nx.ctypes.data_as(_PI), ny.ctypes.data_as(_PI)))
+        return nx, ny
+
+    def device_bytes(self) -> int:
+        return int(lib().ica_plan_device_bytes(self._h))
+
+    def last_launch_count(self) -> int:
+        return int(lib().ica_plan_last_launch_count(self._h))
+
+    def enable_timing(self, enable=True):
+        check(lib().ica_plan_enable_timing(self._h, 1 if enable else 0))
+
+    def timing(self):
+        a, b = C.c_float(), C.c_float()
+        na, nb = C.c_int32(), C.c_int32()
+        check(lib().ica_plan_get_timing(self._h, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
+        return {"iterate_ms": a.value, "iterate_launches": na.value, "pyramid_ms": b.value,
+                "pyramid_launches": nb.value}
+
+    def run_device(self, I1_ptr: int, I2_ptr: int, p_ptr: int, stream: int = 0):
+        """Device pointers (ints): float32 [B][H][W][C] x2, double [B][8]."""
+        check(lib().ica_plan_run_device(self._h, _P(I1_ptr), _P(I2_ptr), _P(p_ptr), _P(stream)))
+
+    def results(self):
+        p = np.zeros((self.batch, MAX_PARAMS))
+        err = np.zeros(self.batch)
+        iters = np.zeros((self.batch, self.nscales), dtype=np.int32)
+        check(lib().ica_plan_get_results(self._h, _ptr(p), _ptr(err), _ptr(iters)))
+        return p, err, iters
+
+    def run_host(self, I1: np.ndarray, I2: np.ndarray, p0=None, want_images=False):
+        """``I1``/``I2``: arrays [B][H][W][C] of dtype float32, uint8 or float64 (C-contiguous)."""
+        shape = (self.batch, self.height, self.width, self.channels)
+        if I1.shape != shape or I2.shape != shape:
+            raise ValueError(f"expected image batches of shape {shape}, got {I1.shape} / {I2.shape}")
+        if I1.dtype != I2.dtype:
+            raise ValueError("I1 and I2 must share a dtype")
+        code = {np.dtype(np.float32): DTYPE_F32, np.dtype(np.uint8): DTYPE_U8,
+                np.dtype(np.float64): DTYPE_F64}.get(I1.dtype)
+        if code is None:
+            I1 = I1.astype(np.float32)
+            I2 = I2.astype(np.float32)
+            code = DTYPE_F32
+        I1 = np.ascontiguousarray(I1)
+        I2 = np.ascontiguousarray(I2)
+        p = np.zeros((self.batch, MAX_PARAMS))
+        if p0 is not None:
+            p0 = np.asarray(p0, dtype=np.float64).reshape(self.batch, -1)
+            p[:, :p0.shape[1]] = p0
+        err = np.zeros(self.batch)
+        iters = np.zeros((self.batch, self.nscales), dtype=np.int32)
+        DI = Iw = None
+        di_ptr = iw_ptr = None
+        if want_images:
+            DI = np.empty(shape, dtype=np.float32)
+            Iw = np.empty(shape, dtype=np.float32)
+            di_ptr, iw_ptr = _ptr(DI), _ptr(Iw)
+        check(lib().ica_plan_run_host(self._h, _ptr(I1), _ptr(I2), code, _ptr(p), _ptr(err),
+                                      _ptr(iters), di_ptr, iw_ptr))
+        return p, err, iters, DI, Iw
+
+    def run_host_ptrs(self, I1_ptr: int, I2_ptr: int, dtype_code: int, p: np.ndarray,
+                      err: np.ndarray, iters: np.ndarray):
+        """Raw host pointers (e.g. pinned torch tensors) -- used by bench.py's e2e leg."""
+        check(lib().ica_plan_run_host(self._h, _P(I1_ptr), _P(I2_ptr), int(dtype_code), _ptr(p),
+                                      _ptr(err), _ptr(iters), None, None))
+
+    def last_host_run_ms(self) -> float:
+        ms = C.c_float()
+        check(lib().ica_plan_last_host_run_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def trajectory(self):
+        """List (per pair) of arrays [count][12]: scale, iter, |dp|, lambda, p[8]."""
+        cap = self.nscales * self.max_iter
+        traj = np.zeros((self.batch, cap, TRAJ_STRIDE))
+        cnt = np.zeros(self.batch, dtype=np.int32)
+        check(lib().ica_plan_get_trajectory(self._h, _ptr(traj), _ptr(cnt)))
+        return [traj[b, :cnt[b]].copy() for b in range(self.batch)]
+
+    def level_device(self, which: int, pair: int, scale: int):
+        ptr, pitch = _P(), C.c_int32()
+        check(lib().ica_plan_get_level_device(self._h, which, pair, scale, C.byref(ptr), C.byref(pitch)))
+        return ptr.value, pitch.value

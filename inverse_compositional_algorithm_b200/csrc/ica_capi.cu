@@ -1,0 +1,654 @@
+// C-ABI of libica_b200.so (see include/ica_b200.h): plan management and entry points.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <algorithm>
+#include <vector>
+#include "ica_common.cuh"
+#include "ica_transform.cuh"
+#include "ica_device.cuh"
+#include "ica_iterate.cuh"
+#include "ica_pyramid.cuh"
+
+namespace ica {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace ica
+
+using namespace ica;
+
+#define ICA_LAUNCH_CHECK(expr)                                                      \
+  do {                                                                              \
+    cudaError_t e__ = (expr);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      ica::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),       \
+                     __FILE__, __LINE__);                                           \
+      return ICA_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+struct ica_plan {
+  ica_config cfg;
+  int B, H, W, C, nscales, dh, G;
+  LevelDesc lv[ICA_MAX_SCALES];
+  long long in_stride = 0, pyr_stride = 0;
+  float *pyr1 = nullptr, *pyr2 = nullptr;
+  float* tmp = nullptr;
+  long long tmp_stride = 0;
+  int tmp_images = 0;
+  DeviceResample ry[ICA_MAX_SCALES], rx[ICA_MAX_SCALES];
+  PairState* state = nullptr;
+  MinMaxKeys* mm = nullptr;
+  double* partials = nullptr;
+  double* traj = nullptr;
+  int traj_cap = 0;
+  int* n_active = nullptr;
+  int* h_n_active = nullptr;  // pinned
+  int* ttypes_dev = nullptr;
+  std::vector<int> ttypes;
+  double* p_dev = nullptr;
+  double* err_dev = nullptr;
+  int* iters_dev = nullptr;
+  // host-entry staging
+  float *in1_dev = nullptr, *in2_dev = nullptr;
+  void* raw_dev = nullptr;
+  size_t raw_bytes = 0;
+  float *DI_dev = nullptr, *Iw_dev = nullptr;
+  const float *last_I1 = nullptr, *last_I2 = nullptr;
+  cudaStream_t stream = nullptr;  // own stream of the host entry
+  size_t device_bytes = 0;
+  long long launches = 0;
+  // optional timing
+  int timing = 0;
+  cudaEvent_t ev_host0 = nullptr, ev_host1 = nullptr;  // bracket ica_plan_run_host on its stream
+  std::vector<cudaEvent_t> ev_iter, ev_pyr;
+  int n_ev_iter = 0, n_ev_pyr = 0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(ica_plan* pl, T** ptr, size_t count) {
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  cudaError_t e = cudaMalloc((void**)ptr, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    return ICA_ERR_ALLOC;
+  }
+  if (pl) pl->device_bytes += bytes;
+  return ICA_OK;
+}
+
+int upload_resample(ica_plan* pl, const Resample1D& r, DeviceResample* d) {
+  d->n_in = r.n_in; d->n_out = r.n_out; d->taps = r.taps;
+  int rc;
+  if ((rc = dev_alloc(pl, &d->start, r.start.size()))) return rc;
+  if ((rc = dev_alloc(pl, &d->weights, r.weights.size()))) return rc;
+  if ((rc = dev_alloc(pl, &d->weights_t, r.weights.size()))) return rc;
+  std::vector<float> wt(r.weights.size());
+  for (int o = 0; o < r.n_out; ++o)
+    for (int k = 0; k < r.taps; ++k) wt[(size_t)k * r.n_out + o] = r.weights[(size_t)o * r.taps + k];
+  ICA_CUDA_CHECK(cudaMemcpy(d->start, r.start.data(), r.start.size() * sizeof(int), cudaMemcpyHostToDevice));
+  ICA_CUDA_CHECK(cudaMemcpy(d->weights, r.weights.data(), r.weights.size() * sizeof(float), cudaMemcpyHostToDevice));
+  ICA_CUDA_CHECK(cudaMemcpy(d->weights_t, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return ICA_OK;
+}
+
+void free_resample(DeviceResample* d) {
+  cudaFree(d->start); cudaFree(d->weights); cudaFree(d->weights_t);
+  d->start = nullptr; d->weights = nullptr; d->weights_t = nullptr;
+}
+
+int validate_config(const ica_config* c) {
+  if (!c) { set_error("config is NULL"); return ICA_ERR_INVALID; }
+  if (c->batch < 1) { set_error("batch must be >= 1"); return ICA_ERR_INVALID; }
+  if (c->height < 1 || c->width < 1) { set_error("image shape must be positive"); return ICA_ERR_INVALID; }
+  if (c->channels != 1 && c->channels != 3) { set_error("channels must be 1 or 3"); return ICA_ERR_INVALID; }
+  if (c->nscales < 1 || c->nscales > ICA_MAX_SCALES) { set_error("nscales must be in [1, %d]", ICA_MAX_SCALES); return ICA_ERR_INVALID; }
+  if (c->nscales > 1 && !(c->nu > 0.0 && c->nu < 1.0)) { set_error("nu must be in (0, 1)"); return ICA_ERR_INVALID; }
+  if (nparams_of(c->transform_type) < 0) { set_error("Unknown transform type"); return ICA_ERR_INVALID; }
+  if (c->robust_type < 0 || c->robust_type > 4) { set_error("Unknown type for robust error function"); return ICA_ERR_INVALID; }
+  if (!(c->tol < 0.01)) { set_error("TOL must be positive and very small (less than 0.01)"); return ICA_ERR_INVALID; }
+  if (c->max_iter < 1) { set_error("max_iter must be >= 1"); return ICA_ERR_INVALID; }
+  if (c->delta < 0) { set_error("delta must be >= 0"); return ICA_ERR_INVALID; }
+  return ICA_OK;
+}
+
+int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n < 1) {
+    set_error("no CUDA device is visible (%s); libica_b200 has no CPU fallback",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return ICA_ERR_NO_DEVICE;
+  }
+  return ICA_OK;
+}
+
+void fill_iter_params(const ica_plan* pl, const float* I1, const float* I2, IterParams* P) {
+  memset(P, 0, sizeof(*P));
+  P->I1_0 = I1; P->I2_0 = I2; P->in_stride = pl->in_stride;
+  P->pyr1 = pl->pyr1; P->pyr2 = pl->pyr2; P->pyr_stride = pl->pyr_stride;
+  for (int s = 0; s < pl->nscales; ++s) P->lv[s] = pl->lv[s];
+  P->nscales = pl->nscales;
+  P->state = pl->state; P->mm = pl->mm; P->partials = pl->partials;
+  P->traj = (pl->cfg.flags & ICA_FLAG_RECORD_TRAJECTORY) ? pl->traj : nullptr;
+  P->dbg_Hb = nullptr;
+  P->n_active = pl->n_active;
+  P->traj_cap = pl->traj_cap;
+  P->G = pl->G;
+  P->robust_type = pl->cfg.robust_type;
+  P->robust_loop = pl->cfg.robust_loop;
+  P->lambda_cfg = pl->cfg.lambda_;
+  P->tol = pl->cfg.tol;
+  P->max_iter = pl->cfg.max_iter;
+  P->delta = pl->cfg.delta;
+  P->frame = (pl->cfg.nanifoutside != 0 && pl->cfg.delta > 0) ? 1 : 0;
+  P->ch_mult = (pl->C == 1 && pl->cfg.gray_as_rgb) ? 3.0f : 1.0f;
+}
+
+// minmax of level 0 and all pyramid levels of both images
+int build_pyramids(ica_plan* pl, const float* I1, const float* I2, cudaStream_t stream) {
+  const int B = pl->B, ns = pl->nscales;
+  ICA_LAUNCH_CHECK(launch_minmax_reset(pl->mm, B * ns * 2, stream));
+  pl->launches += 1;
+  const long long n0 = (long long)pl->H * pl->W * pl->C;
+  const float* src[2] = {I1, I2};
+  float* pyr[2] = {pl->pyr1, pl->pyr2};
+  for (int which = 0; which < 2; ++which) {
+    ICA_LAUNCH_CHECK(launch_minmax(src[which], pl->in_stride, n0, B, pl->mm + which, ns * 2, stream));
+    pl->launches += 1;
+  }
+  for (int s = 0; s + 1 < ns; ++s) {
+    const LevelDesc& Li = pl->lv[s];
+    const LevelDesc& Lo = pl->lv[s + 1];
+    for (int which = 0; which < 2; ++which) {
+      for (int b0 = 0; b0 < B; b0 += pl->tmp_images) {
+        const int nimg = std::min(pl->tmp_images, B - b0);
+        const float* in0 = s == 0 ? src[which] + (long long)b0 * pl->in_stride
+                                  : pyr[which] + (long long)b0 * pl->pyr_stride + Li.offset;
+        const long long istr = s == 0 ? pl->in_stride : pl->pyr_stride;
+        float* out0 = pyr[which] + (long long)b0 * pl->pyr_stride + Lo.offset;
+        if (pl->timing && pl->n_ev_pyr + 2 <= (int)pl->ev_pyr.size()) cudaEventRecord(pl->ev_pyr[pl->n_ev_pyr++], stream);
+        ICA_LAUNCH_CHECK(launch_pyr_down(in0, istr, Li.pitch, Li.nx, Li.ny, pl->C, pl->ry[s], pl->rx[s], pl->tmp,
+                                         pl->tmp_stride, out0, pl->pyr_stride, Lo.pitch, nimg,
+                                         pl->mm + ((long long)b0 * ns + s) * 2 + which, ns * 2,
+                                         pl->mm + ((long long)b0 * ns + s + 1) * 2 + which, ns * 2, stream));
+        if (pl->timing && pl->n_ev_pyr + 1 <= (int)pl->ev_pyr.size()) cudaEventRecord(pl->ev_pyr[pl->n_ev_pyr++], stream);
+        pl->launches += 2;
+      }
+    }
+  }
+  return ICA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ica_last_error(void) { return g_err; }
+int ica_version(void) { return 100; }
+
+int ica_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int ica_set_device(int device) {
+  if (int rc = require_device()) return rc;
+  ICA_CUDA_CHECK(cudaSetDevice(device));
+  return ICA_OK;
+}
+
+int ica_get_constants(double* out5) {
+  if (!out5) return ICA_ERR_INVALID;
+  out5[0] = kMaxIter; out5[1] = kLambda0; out5[2] = kLambdaN; out5[3] = kLambdaRatio; out5[4] = kSplinePad;
+  return ICA_OK;
+}
+
+int ica_plan_destroy(ica_plan* pl) {
+  if (!pl) return ICA_OK;
+  cudaFree(pl->pyr1); cudaFree(pl->pyr2); cudaFree(pl->tmp);
+  for (int s = 0; s < ICA_MAX_SCALES; ++s) { free_resample(&pl->ry[s]); free_resample(&pl->rx[s]); }
+  cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->traj); cudaFree(pl->n_active);
+  if (pl->h_n_active) cudaFreeHost(pl->h_n_active);
+  cudaFree(pl->ttypes_dev); cudaFree(pl->p_dev); cudaFree(pl->err_dev); cudaFree(pl->iters_dev);
+  cudaFree(pl->in1_dev); cudaFree(pl->in2_dev); cudaFree(pl->raw_dev); cudaFree(pl->DI_dev); cudaFree(pl->Iw_dev);
+  for (auto e : pl->ev_iter) cudaEventDestroy(e);
+  for (auto e : pl->ev_pyr) cudaEventDestroy(e);
+  if (pl->ev_host0) cudaEventDestroy(pl->ev_host0);
+  if (pl->ev_host1) cudaEventDestroy(pl->ev_host1);
+  if (pl->stream) cudaStreamDestroy(pl->stream);
+  delete pl;
+  return ICA_OK;
+}
+
+int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
+  if (!plan_out) { set_error("plan_out is NULL"); return ICA_ERR_INVALID; }
+  *plan_out = nullptr;
+  if (int rc = validate_config(cfg)) return rc;
+  if (int rc = require_device()) return rc;
+  ica_plan* pl = new ica_plan();
+  pl->cfg = *cfg;
+  if (pl->cfg.robust_type != QUADRATIC) pl->cfg.robust_loop = 1;
+  pl->B = cfg->batch; pl->H = cfg->height; pl->W = cfg->width; pl->C = cfg->channels; pl->nscales = cfg->nscales;
+  pl->ttypes.assign(pl->B, cfg->transform_type);
+  pl->dh = moment_degree_of(cfg->transform_type);
+  const int TWv = iterate_tile_w(), THv = iterate_tile_h();
+  // level shapes (zoom.zoom_size, src/zoom.py:8-22; skimage uses the same rounding)
+  long long off = 0;
+  int nx = pl->W, ny = pl->H;
+  for (int s = 0; s < pl->nscales; ++s) {
+    if (s > 0) { nx = std::max(zoomed_size(nx, cfg->nu), 1); ny = std::max(zoomed_size(ny, cfg->nu), 1); }
+    LevelDesc& L = pl->lv[s];
+    L.nx = nx; L.ny = ny; L.pitch = nx * pl->C;
+    L.offset = s == 0 ? 0 : off;
+    L.tiles_x = (nx + TWv - 1) / TWv; L.tiles_y = (ny + THv - 1) / THv;
+    if (s > 0) off += ((long long)nx * ny * pl->C + 31) / 32 * 32;
+  }
+  pl->in_stride = (long long)pl->H * pl->W * pl->C;
+  pl->pyr_stride = off;
+  const int nt0 = pl->lv[0].tiles_x * pl->lv[0].tiles_y;
+  int G = cfg->blocks_per_pair > 0 ? cfg->blocks_per_pair : std::max(8, (592 + pl->B - 1) / pl->B);
+  pl->G = std::max(1, std::min(G, nt0));
+  int rc = ICA_OK;
+#define TRY(expr) do { if ((rc = (expr)) != ICA_OK) { ica_plan_destroy(pl); return rc; } } while (0)
+#define TRY_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { set_error("%s failed: %s", #expr, cudaGetErrorString(e__)); ica_plan_destroy(pl); return ICA_ERR_CUDA; } } while (0)
+  if (pl->nscales > 1) {
+    TRY(dev_alloc(pl, &pl->pyr1, (size_t)pl->B * pl->pyr_stride));
+    TRY(dev_alloc(pl, &pl->pyr2, (size_t)pl->B * pl->pyr_stride));
+    pl->tmp_stride = (long long)pl->lv[1].ny * pl->lv[0].nx * pl->C;
+    const long long budget = 64ll << 20;
+    pl->tmp_images = (int)std::max<long long>(1, std::min<long long>(pl->B, budget / std::max<long long>(1, pl->tmp_stride * 4)));
+    TRY(dev_alloc(pl, &pl->tmp, (size_t)pl->tmp_images * pl->tmp_stride));
+    for (int s = 0; s + 1 < pl->nscales; ++s) {
+      Resample1D r;
+      build_resample_1d(pl->lv[s].ny, pl->lv[s + 1].ny, &r);
+      if (r.taps > max_taps()) { set_error("resampling operator too wide (%d taps)", r.taps); ica_plan_destroy(pl); return ICA_ERR_INVALID; }
+      TRY(upload_resample(pl, r, &pl->ry[s]));
+      build_resample_1d(pl->lv[s].nx, pl->lv[s + 1].nx, &r);
+      if (r.taps > max_taps()) { set_error("resampling operator too wide (%d taps)", r.taps); ica_plan_destroy(pl); return ICA_ERR_INVALID; }
+      TRY(upload_resample(pl, r, &pl->rx[s]));
+    }
+  }
+  TRY(dev_alloc(pl, &pl->state, (size_t)pl->B));
+  TRY(dev_alloc(pl, &pl->mm, (size_t)pl->B * pl->nscales * 2));
+  TRY(dev_alloc(pl, &pl->partials, (size_t)pl->B * pl->G * kAccStride));
+  pl->traj_cap = pl->nscales * cfg->max_iter;
+  if (cfg->flags & ICA_FLAG_RECORD_TRAJECTORY) TRY(dev_alloc(pl, &pl->traj, (size_t)pl->B * pl->traj_cap * ICA_TRAJ_STRIDE));
+  TRY(dev_alloc(pl, &pl->n_active, 1));
+  TRY_CUDA(cudaMallocHost((void**)&pl->h_n_active, sizeof(int)));
+  TRY(dev_alloc(pl, &pl->ttypes_dev, (size_t)pl->B));
+  TRY_CUDA(cudaMemcpy(pl->ttypes_dev, pl->ttypes.data(), pl->B * sizeof(int), cudaMemcpyHostToDevice));
+  TRY(dev_alloc(pl, &pl->p_dev, (size_t)pl->B * ICA_MAX_PARAMS));
+  TRY(dev_alloc(pl, &pl->err_dev, (size_t)pl->B));
+  TRY(dev_alloc(pl, &pl->iters_dev, (size_t)pl->B * pl->nscales));
+  if (cfg->flags & ICA_FLAG_WRITE_DI_IW) {
+    TRY(dev_alloc(pl, &pl->DI_dev, (size_t)pl->B * pl->in_stride));
+    TRY(dev_alloc(pl, &pl->Iw_dev, (size_t)pl->B * pl->in_stride));
+  }
+  TRY_CUDA(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+  TRY_CUDA(cudaEventCreate(&pl->ev_host0));
+  TRY_CUDA(cudaEventCreate(&pl->ev_host1));
+  TRY_CUDA(cudaMemset(pl->state, 0, pl->B * sizeof(PairState)));
+#undef TRY
+#undef TRY_CUDA
+  *plan_out = pl;
+  return ICA_OK;
+}
+
+int ica_plan_set_transform_types(ica_plan* pl, const int32_t* types, int32_t count) {
+  if (!pl || !types || count != pl->B) { set_error("transform type array must have one entry per pair"); return ICA_ERR_INVALID; }
+  int dh = 0;
+  for (int i = 0; i < count; ++i) {
+    if (nparams_of(types[i]) < 0) { set_error("Unknown transform type"); return ICA_ERR_INVALID; }
+    dh = std::max(dh, moment_degree_of(types[i]));
+  }
+  pl->ttypes.assign(types, types + count);
+  pl->dh = dh;
+  ICA_CUDA_CHECK(cudaMemcpy(pl->ttypes_dev, pl->ttypes.data(), count * sizeof(int), cudaMemcpyHostToDevice));
+  return ICA_OK;
+}
+
+int ica_plan_level_shapes(const ica_plan* pl, int32_t* nx_out, int32_t* ny_out) {
+  if (!pl) return ICA_ERR_INVALID;
+  for (int s = 0; s < pl->nscales; ++s) { if (nx_out) nx_out[s] = pl->lv[s].nx; if (ny_out) ny_out[s] = pl->lv[s].ny; }
+  return ICA_OK;
+}
+
+size_t ica_plan_device_bytes(const ica_plan* pl) { return pl ? pl->device_bytes : 0; }
+int64_t ica_plan_last_launch_count(const ica_plan* pl) { return pl ? pl->launches : 0; }
+
+int ica_plan_enable_timing(ica_plan* pl, int32_t enable) {
+  if (!pl) return ICA_ERR_INVALID;
+  pl->timing = enable ? 1 : 0;
+  if (enable && pl->ev_iter.empty()) {
+    const int n_it = 2 * (pl->nscales * pl->cfg.max_iter + 8);
+    const int n_py = 4 * pl->nscales * ((pl->B + std::max(1, pl->tmp_images) - 1) / std::max(1, pl->tmp_images)) + 8;
+    pl->ev_iter.resize(n_it); pl->ev_pyr.resize(n_py);
+    for (auto& e : pl->ev_iter) ICA_CUDA_CHECK(cudaEventCreate(&e));
+    for (auto& e : pl->ev_pyr) ICA_CUDA_CHECK(cudaEventCreate(&e));
+  }
+  return ICA_OK;
+}
+
+int ica_plan_get_timing(ica_plan* pl, float* iterate_ms, int32_t* iterate_launches, float* pyramid_ms,
+                        int32_t* pyramid_launches) {
+  if (!pl) return ICA_ERR_INVALID;
+  float it = 0.f, py = 0.f;
+  for (int i = 0; i + 1 < pl->n_ev_iter; i += 2) {
+    float ms = 0.f;
+    ICA_CUDA_CHECK(cudaEventSynchronize(pl->ev_iter[i + 1]));
+    ICA_CUDA_CHECK(cudaEventElapsedTime(&ms, pl->ev_iter[i], pl->ev_iter[i + 1]));
+    it += ms;
+  }
+  for (int i = 0; i + 1 < pl->n_ev_pyr; i += 2) {
+    float ms = 0.f;
+    ICA_CUDA_CHECK(cudaEventSynchronize(pl->ev_pyr[i + 1]));
+    ICA_CUDA_CHECK(cudaEventElapsedTime(&ms, pl->ev_pyr[i], pl->ev_pyr[i + 1]));
+    py += ms;
+  }
+  if (iterate_ms) *iterate_ms = it;
+  if (iterate_launches) *iterate_launches = pl->n_ev_iter / 2;
+  if (pyramid_ms) *pyramid_ms = py;
+  if (pyramid_launches) *pyramid_launches = pl->n_ev_pyr;  // two kernels per recorded pair
+  return ICA_OK;
+}
+
+int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* p_inout, void* stream_) {
+  if (!pl || !I1 || !I2 || !p_inout) { set_error("NULL argument"); return ICA_ERR_INVALID; }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  pl->launches = 0;
+  pl->n_ev_iter = 0; pl->n_ev_pyr = 0;
+  pl->last_I1 = I1; pl->last_I2 = I2;
+  if (int rc = build_pyramids(pl, I1, I2, stream)) return rc;
+  ICA_LAUNCH_CHECK(launch_init_state(pl->state, p_inout, pl->ttypes_dev, pl->B, pl->nscales, pl->cfg.lambda_,
+                                     pl->n_active, stream));
+  pl->launches += 1;
+  IterParams P;
+  fill_iter_params(pl, I1, I2, &P);
+  const int max_launches = pl->nscales * pl->cfg.max_iter;
+  const int poll_every = 4;
+  int done = 0;
+  // a pair needs at least one launch per scale, so the first poll can wait that long
+  int next_poll = std::max(pl->nscales, poll_every);
+  for (int it = 0; it < max_launches && !done; ++it) {
+    const bool timed = pl->timing && pl->n_ev_iter + 2 <= (int)pl->ev_iter.size();
+    if (timed) cudaEventRecord(pl->ev_iter[pl->n_ev_iter++], stream);
+    ICA_LAUNCH_CHECK(launch_iterate(P, pl->B, pl->C, pl->dh, stream));
+    if (timed) cudaEventRecord(pl->ev_iter[pl->n_ev_iter++], stream);
+    pl->launches += 1;
+    if (it + 1 >= next_poll && it + 1 < max_launches) {
+      ICA_CUDA_CHECK(cudaMemcpyAsync(pl->h_n_active, pl->n_active, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      ICA_CUDA_CHECK(cudaStreamSynchronize(stream));
+      if (*pl->h_n_active <= 0) done = 1;
+      next_poll = it + 1 + poll_every;
+    }
+  }
+  ICA_LAUNCH_CHECK(launch_export_results(pl->state, pl->B, p_inout, pl->err_dev, pl->iters_dev, pl->nscales, stream));
+  pl->launches += 1;
+  if (pl->cfg.flags & ICA_FLAG_WRITE_DI_IW) {
+    ICA_LAUNCH_CHECK(launch_warp_out(I1, I2, pl->in_stride, pl->W, pl->H, pl->C, pl->state, pl->mm, pl->nscales, pl->B,
+                                     pl->Iw_dev, pl->DI_dev, stream));
+    pl->launches += 1;
+  }
+  return ICA_OK;
+}
+
+static int upload_images(ica_plan* pl, const void* host, int dtype, float* dst, cudaStream_t stream) {
+  const long long n = (long long)pl->B * pl->in_stride;
+  if (dtype == 0) {
+    ICA_CUDA_CHECK(cudaMemcpyAsync(dst, host, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    return ICA_OK;
+  }
+  const size_t esz = dtype == 1 ? 1 : 8;
+  if (pl->raw_bytes < (size_t)n * esz) {
+    cudaFree(pl->raw_dev); pl->raw_dev = nullptr; pl->raw_bytes = 0;
+    cudaError_t e = cudaMalloc(&pl->raw_dev, (size_t)n * esz);
+    if (e != cudaSuccess) { set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return ICA_ERR_ALLOC; }
+    pl->raw_bytes = (size_t)n * esz; pl->device_bytes += pl->raw_bytes;
+  }
+  ICA_CUDA_CHECK(cudaMemcpyAsync(pl->raw_dev, host, (size_t)n * esz, cudaMemcpyHostToDevice, stream));
+  if (dtype == 1) ICA_LAUNCH_CHECK(launch_convert_u8((const unsigned char*)pl->raw_dev, dst, n, stream));
+  else ICA_LAUNCH_CHECK(launch_convert_f64((const double*)pl->raw_dev, dst, n, stream));
+  pl->launches += 1;
+  return ICA_OK;
+}
+
+int ica_plan_run_host(ica_plan* pl, const void* I1_host, const void* I2_host, int32_t dtype, double* p_inout_host,
+                      double* err_out, int32_t* iters_out, float* DI_out, float* Iw_out) {
+  if (!pl || !I1_host || !I2_host || !p_inout_host) { set_error("NULL argument"); return ICA_ERR_INVALID; }
+  if (dtype < 0 || dtype > 2) { set_error("dtype must be 0 (f32), 1 (u8) or 2 (f64)"); return ICA_ERR_INVALID; }
+  if ((DI_out || Iw_out) && !(pl->cfg.flags & ICA_FLAG_WRITE_DI_IW)) {
+    set_error("DI/Iw requested but the plan was created without ICA_FLAG_WRITE_DI_IW"); return ICA_ERR_INVALID;
+  }
+  cudaStream_t stream = pl->stream;
+  const size_t nimg = (size_t)pl->B * pl->in_stride;
+  if (!pl->in1_dev) {
+    if (int rc = dev_alloc(pl, &pl->in1_dev, nimg)) return rc;
+    if (int rc = dev_alloc(pl, &pl->in2_dev, nimg)) return rc;
+  }
+  ICA_CUDA_CHECK(cudaEventRecord(pl->ev_host0, stream));
+  // the dtype staging buffer is reused for the second image only after the first conversion was enqueued
+  if (int rc = upload_images(pl, I1_host, dtype, pl->in1_dev, stream)) return rc;
+  if (int rc = upload_images(pl, I2_host, dtype, pl->in2_dev, stream)) return rc;
+  ICA_CUDA_CHECK(cudaMemcpyAsync(pl->p_dev, p_inout_host, (size_t)pl->B * ICA_MAX_PARAMS * sizeof(double),
+                                 cudaMemcpyHostToDevice, stream));
+  const long long conv_launches = pl->launches;
+  if (int rc = ica_plan_run_device(pl, pl->in1_dev, pl->in2_dev, pl->p_dev, stream)) return rc;
+  pl->launches += (dtype == 0 ? 0 : 2);
+  (void)conv_launches;
+  ICA_CUDA_CHECK(cudaMemcpyAsync(p_inout_host, pl->p_dev, (size_t)pl->B * ICA_MAX_PARAMS * sizeof(double),
+                                 cudaMemcpyDeviceToHost, stream));
+  if (err_out) ICA_CUDA_CHECK(cudaMemcpyAsync(err_out, pl->err_dev, pl->B * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  if (iters_out) ICA_CUDA_CHECK(cudaMemcpyAsync(iters_out, pl->iters_dev, (size_t)pl->B * pl->nscales * sizeof(int),
+                                                cudaMemcpyDeviceToHost, stream));
+  if (DI_out) ICA_CUDA_CHECK(cudaMemcpyAsync(DI_out, pl->DI_dev, nimg * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  if (Iw_out) ICA_CUDA_CHECK(cudaMemcpyAsync(Iw_out, pl->Iw_dev, nimg * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  ICA_CUDA_CHECK(cudaEventRecord(pl->ev_host1, stream));
+  ICA_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return ICA_OK;
+}
+
+int ica_plan_last_host_run_ms(ica_plan* pl, float* ms_out) {
+  if (!pl || !ms_out) return ICA_ERR_INVALID;
+  ICA_CUDA_CHECK(cudaEventElapsedTime(ms_out, pl->ev_host0, pl->ev_host1));
+  return ICA_OK;
+}
+
+int ica_plan_get_results(ica_plan* pl, double* p_out, double* err_out, int32_t* iters_out) {
+  if (!pl) return ICA_ERR_INVALID;
+  ICA_CUDA_CHECK(cudaDeviceSynchronize());
+  ICA_LAUNCH_CHECK(launch_export_results(pl->state, pl->B, pl->p_dev, pl->err_dev, pl->iters_dev, pl->nscales, 0));
+  if (p_out) ICA_CUDA_CHECK(cudaMemcpy(p_out, pl->p_dev, (size_t)pl->B * ICA_MAX_PARAMS * sizeof(double), cudaMemcpyDeviceToHost));
+  if (err_out) ICA_CUDA_CHECK(cudaMemcpy(err_out, pl->err_dev, pl->B * sizeof(double), cudaMemcpyDeviceToHost));
+  if (iters_out) ICA_CUDA_CHECK(cudaMemcpy(iters_out, pl->iters_dev, (size_t)pl->B * pl->nscales * sizeof(int), cudaMemcpyDeviceToHost));
+  return ICA_OK;
+}
+
+int ica_plan_get_trajectory(ica_plan* pl, double* traj_out, int32_t* count_out) {
+  if (!pl || !pl->traj) { set_error("plan was created without ICA_FLAG_RECORD_TRAJECTORY"); return ICA_ERR_INVALID; }
+  ICA_CUDA_CHECK(cudaDeviceSynchronize());
+  if (traj_out) ICA_CUDA_CHECK(cudaMemcpy(traj_out, pl->traj, (size_t)pl->B * pl->traj_cap * ICA_TRAJ_STRIDE * sizeof(double), cudaMemcpyDeviceToHost));
+  if (count_out) {
+    std::vector<PairState> h(pl->B);
+    ICA_CUDA_CHECK(cudaMemcpy(h.data(), pl->state, pl->B * sizeof(PairState), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < pl->B; ++b) count_out[b] = h[b].traj_count;
+  }
+  return ICA_OK;
+}
+
+int ica_plan_get_di_iw_device(ica_plan* pl, const float** DI_dev, const float** Iw_dev) {
+  if (!pl || !pl->DI_dev) { set_error("plan was created without ICA_FLAG_WRITE_DI_IW"); return ICA_ERR_INVALID; }
+  if (DI_dev) *DI_dev = pl->DI_dev;
+  if (Iw_dev) *Iw_dev = pl->Iw_dev;
+  return ICA_OK;
+}
+
+int ica_plan_get_level_device(ica_plan* pl, int32_t which, int32_t pair, int32_t scale, const float** ptr_out,
+                              int32_t* pitch_out) {
+  if (!pl || which < 0 || which > 1 || pair < 0 || pair >= pl->B || scale < 0 || scale >= pl->nscales || !pl->last_I1) {
+    set_error("bad level query"); return ICA_ERR_INVALID;
+  }
+  const float* base0 = which == 0 ? pl->last_I1 : pl->last_I2;
+  const float* pyr = which == 0 ? pl->pyr1 : pl->pyr2;
+  if (ptr_out) *ptr_out = scale == 0 ? base0 + (long long)pair * pl->in_stride
+                                     : pyr + (long long)pair * pl->pyr_stride + pl->lv[scale].offset;
+  if (pitch_out) *pitch_out = pl->lv[scale].pitch;
+  return ICA_OK;
+}
+
+// ------------------------------------------------------------------ stateless entry points
+int ica_zoom_size(int32_t nx, int32_t ny, double factor, int32_t* nxx, int32_t* nyy) {
+  if (nxx) *nxx = zoomed_size(nx, factor);
+  if (nyy) *nyy = zoomed_size(ny, factor);
+  return ICA_OK;
+}
+
+int ica_nparams(int32_t t) { int n = nparams_of(t); if (n < 0) set_error("Unknown transform type"); return n < 0 ? ICA_ERR_INVALID : n; }
+
+int ica_params2matrix(const double* p, int32_t t, double* m9) {
+  if (!p || !m9 || nparams_of(t) < 0) { set_error("Unknown transform type"); return ICA_ERR_INVALID; }
+  params2matrix(p, t, m9);
+  return ICA_OK;
+}
+
+int ica_update_transform(double* p, const double* dp, int32_t t) {
+  if (!p || !dp || nparams_of(t) < 0) { set_error("Unknown transform type"); return ICA_ERR_INVALID; }
+  update_transform(p, dp, t);
+  return ICA_OK;
+}
+
+int ica_zoom_in_parameters(const double* p, int32_t t, double nx, double ny, double nxx, double nyy, double* out) {
+  if (!p || !out || nparams_of(t) < 0) { set_error("Unsupported transformation type"); return ICA_ERR_INVALID; }
+  zoom_in_parameters(p, t, nx, ny, nxx, nyy, out);
+  return ICA_OK;
+}
+
+int ica_inverse_hessian(const double* H, int32_t n, double* Hinv) {
+  if (!H || !Hinv || n < 1 || n > ICA_MAX_PARAMS) { set_error("n must be in [1, 8]"); return ICA_ERR_INVALID; }
+  inverse_hessian(H, n, Hinv);
+  return ICA_OK;
+}
+
+int ica_warp_host(const float* image, int32_t height, int32_t width, int32_t channels, const double* m9, float* out) {
+  if (!image || !m9 || !out || height < 1 || width < 1 || (channels != 1 && channels != 3)) { set_error("bad argument"); return ICA_ERR_INVALID; }
+  if (int rc = require_device()) return rc;
+  const size_t n = (size_t)height * width * channels;
+  float *d_in = nullptr, *d_out = nullptr; MinMaxKeys* d_mm = nullptr;
+  int rc = ICA_OK;
+  if ((rc = dev_alloc<float>(nullptr, &d_in, n)) || (rc = dev_alloc<float>(nullptr, &d_out, n)) || (rc = dev_alloc<MinMaxKeys>(nullptr, &d_mm, 1))) {
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_mm); return rc;
+  }
+  cudaError_t e = cudaMemcpy(d_in, image, n * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_minmax_reset(d_mm, 1, 0);
+  if (e == cudaSuccess) e = launch_minmax(d_in, 0, (long long)n, 1, d_mm, 1, 0);
+  if (e == cudaSuccess) e = launch_warp_matrix(d_in, width, height, channels, m9, d_mm, d_out, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(d_in); cudaFree(d_out); cudaFree(d_mm);
+  if (e != cudaSuccess) { set_error("ica_warp_host: %s", cudaGetErrorString(e)); return ICA_ERR_CUDA; }
+  return ICA_OK;
+}
+
+int ica_gradient_host(const float* image, int32_t height, int32_t width, int32_t channels, int32_t delta,
+                      int32_t nanifoutside, float* Ix, float* Iy) {
+  if (!image || !Ix || !Iy || height < 1 || width < 1 || (channels != 1 && channels != 3)) { set_error("bad argument"); return ICA_ERR_INVALID; }
+  if (int rc = require_device()) return rc;
+  const size_t n = (size_t)height * width * channels;
+  float *d_in = nullptr, *d_x = nullptr, *d_y = nullptr;
+  int rc = ICA_OK;
+  if ((rc = dev_alloc<float>(nullptr, &d_in, n)) || (rc = dev_alloc<float>(nullptr, &d_x, n)) || (rc = dev_alloc<float>(nullptr, &d_y, n))) {
+    cudaFree(d_in); cudaFree(d_x); cudaFree(d_y); return rc;
+  }
+  cudaError_t e = cudaMemcpy(d_in, image, n * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_gradient(d_in, width, height, channels, delta, (nanifoutside && delta > 0) ? 1 : 0, d_x, d_y, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(Ix, d_x, n * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(Iy, d_y, n * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(d_in); cudaFree(d_x); cudaFree(d_y);
+  if (e != cudaSuccess) { set_error("ica_gradient_host: %s", cudaGetErrorString(e)); return ICA_ERR_CUDA; }
+  return ICA_OK;
+}
+
+int ica_rescale_host(const float* image, int32_t height, int32_t width, int32_t channels, double nu, float* out,
+                     int32_t* out_h, int32_t* out_w) {
+  if (!image || !out || height < 1 || width < 1 || (channels != 1 && channels != 3) || !(nu > 0.0 && nu < 1.0)) {
+    set_error("bad argument"); return ICA_ERR_INVALID;
+  }
+  ica_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.batch = 1; cfg.height = height; cfg.width = width; cfg.channels = channels; cfg.nscales = 2; cfg.nu = nu;
+  cfg.transform_type = TRANSLATION; cfg.robust_type = QUADRATIC; cfg.tol = 1e-3; cfg.max_iter = 1;
+  ica_plan* pl = nullptr;
+  if (int rc = ica_plan_create(&cfg, &pl)) return rc;
+  const size_t n = (size_t)height * width * channels;
+  int rc = dev_alloc(pl, &pl->in1_dev, n);
+  if (!rc) rc = dev_alloc(pl, &pl->in2_dev, n);
+  if (!rc) {
+    cudaError_t e = cudaMemcpy(pl->in1_dev, image, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pl->in2_dev, image, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error("ica_rescale_host: %s", cudaGetErrorString(e)); rc = ICA_ERR_CUDA; }
+  }
+  if (!rc) rc = build_pyramids(pl, pl->in1_dev, pl->in2_dev, 0);
+  if (!rc) {
+    const LevelDesc& L = pl->lv[1];
+    cudaError_t e = cudaMemcpy(out, pl->pyr1 + L.offset, (size_t)L.nx * L.ny * channels * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_error("ica_rescale_host: %s", cudaGetErrorString(e)); rc = ICA_ERR_CUDA; }
+    if (out_h) *out_h = L.ny;
+    if (out_w) *out_w = L.nx;
+  }
+  ica_plan_destroy(pl);
+  return rc;
+}
+
+int ica_hessian_b_host(const float* I1, const float* I2, int32_t height, int32_t width, int32_t channels,
+                       int32_t gray_as_rgb, int32_t transform_type, const double* p, int32_t robust_type,
+                       double lambda_, int32_t delta, int32_t nanifoutside, double* H_out, double* b_out) {
+  if (!I1 || !I2 || !p || !H_out || !b_out) { set_error("NULL argument"); return ICA_ERR_INVALID; }
+  ica_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.batch = 1; cfg.height = height; cfg.width = width; cfg.channels = channels; cfg.gray_as_rgb = gray_as_rgb;
+  cfg.nscales = 1; cfg.nu = 0.5; cfg.transform_type = transform_type; cfg.robust_type = robust_type;
+  cfg.robust_loop = 1; cfg.lambda_ = lambda_ > 0 ? lambda_ : kLambda0; cfg.tol = 1e-3; cfg.max_iter = 1;
+  cfg.delta = delta; cfg.nanifoutside = nanifoutside;
+  ica_plan* pl = nullptr;
+  if (int rc = ica_plan_create(&cfg, &pl)) return rc;
+  const size_t n = (size_t)height * width * channels;
+  const int np = nparams_of(transform_type);
+  double ph[ICA_MAX_PARAMS] = {0};
+  for (int i = 0; i < np; ++i) ph[i] = p[i];
+  double* d_dbg = nullptr;
+  int rc = dev_alloc(pl, &pl->in1_dev, n);
+  if (!rc) rc = dev_alloc(pl, &pl->in2_dev, n);
+  if (!rc) rc = dev_alloc(pl, &d_dbg, 72);
+  cudaError_t e = cudaSuccess;
+  if (!rc) {
+    e = cudaMemcpy(pl->in1_dev, I1, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pl->in2_dev, I2, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pl->p_dev, ph, sizeof(ph), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error("ica_hessian_b_host: %s", cudaGetErrorString(e)); rc = ICA_ERR_CUDA; }
+  }
+  if (!rc) rc = build_pyramids(pl, pl->in1_dev, pl->in2_dev, 0);
+  if (!rc) {
+    e = launch_init_state(pl->state, pl->p_dev, pl->ttypes_dev, 1, 1, cfg.lambda_, pl->n_active, 0);
+    IterParams P;
+    fill_iter_params(pl, pl->in1_dev, pl->in2_dev, &P);
+    P.dbg_Hb = d_dbg;
+    if (e == cudaSuccess) e = launch_iterate(P, 1, channels, pl->dh, 0);
+    double hb[72];
+    if (e == cudaSuccess) e = cudaMemcpy(hb, d_dbg, sizeof(hb), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_error("ica_hessian_b_host: %s", cudaGetErrorString(e)); rc = ICA_ERR_CUDA; }
+    else { memcpy(H_out, hb, sizeof(double) * np * np); memcpy(b_out, hb + 64, sizeof(double) * np); }
+  }
+  cudaFree(d_dbg);
+  ica_plan_destroy(pl);
+  return rc;
+}
+
+}  // extern "C"

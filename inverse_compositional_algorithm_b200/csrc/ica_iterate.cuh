@@ -1,0 +1,49 @@
+// Host-visible interface of ica_iterate.cu
+#pragma once
+#include "ica_common.cuh"
+
+namespace ica {
+
+struct IterParams {
+  const float* I1_0;      // level-0 inputs [B][H][W][C]
+  const float* I2_0;
+  long long in_stride;    // floats per pair at level 0
+  const float* pyr1;      // levels >= 1: [B][pyr_stride]
+  const float* pyr2;
+  long long pyr_stride;
+  LevelDesc lv[ICA_MAX_SCALES];
+  int nscales;
+  PairState* state;       // [B]
+  const MinMaxKeys* mm;   // [B][nscales][2]  (0 = I1, 1 = I2)
+  double* partials;       // [B][G][kAccStride]
+  double* traj;           // [B][traj_cap][ICA_TRAJ_STRIDE] or nullptr
+  double* dbg_Hb;         // nullptr, or 72 doubles: H (<=64) then b (8); state left untouched
+  int* n_active;
+  int traj_cap;
+  int G;                  // blocks per pair
+  int robust_type;
+  int robust_loop;        // 1: rho' and H every iteration; 0: quadratic loop (H at iter 0 of a scale)
+  double lambda_cfg;
+  double tol;
+  int max_iter;
+  int delta;
+  int frame;              // nanifoutside && delta > 0
+  float ch_mult;          // 3 for a gray image standing for its RGB replication, else 1
+};
+
+int iterate_tile_w();
+int iterate_tile_h();
+cudaError_t launch_iterate(const IterParams& P, int B, int channels, int dh, cudaStream_t stream);
+cudaError_t launch_init_state(PairState* state, const double* p_in, const int* ttypes, int B, int nscales,
+                              double lambda_cfg, int* n_active, cudaStream_t stream);
+cudaError_t launch_export_results(const PairState* state, int B, double* p_out, double* err_out, int* iters_out,
+                                  int nscales, cudaStream_t stream);
+cudaError_t launch_warp_out(const float* I1_0, const float* I2_0, long long in_stride, int nx, int ny, int channels,
+                            const PairState* state, const MinMaxKeys* mm, int nscales, int B, float* Iw, float* DI,
+                            cudaStream_t stream);
+cudaError_t launch_warp_matrix(const float* img, int nx, int ny, int channels, const double* m9, const MinMaxKeys* mm,
+                               float* out, cudaStream_t stream);
+cudaError_t launch_gradient(const float* img, int nx, int ny, int channels, int delta, int frame, float* Ix,
+                            float* Iy, cudaStream_t stream);
+
+}  // namespace ica

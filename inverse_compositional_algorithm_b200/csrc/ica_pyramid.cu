@@ -1,0 +1,306 @@
+// K0: one pyramid level with the semantics of
+//   skimage.transform.rescale(img, nu, mode='constant', cval=0, order=3, anti_aliasing=True,
+//                             channel_axis=2, preserve_range=True)
+// as called at src/inverse_compositional_algorithm.py:333-336 (third-party arithmetic:
+// scikit-image 0.24 -> scipy.ndimage.gaussian_filter + scipy.ndimage.zoom).
+//
+// Per axis the chain  Gaussian(sigma=(f-1)/2, zero extension) -> pad 12 zeros -> cubic B-spline
+// prefilter (IIR, pole sqrt(3)-2, mirror initialisation on the padded line) -> B-spline
+// evaluation at (o+1/2) f - 1/2  is LINEAR, so it is one banded matrix A (n_out x n_in).  The
+// host builds A exactly in fp64 by pushing unit impulses through that chain (build_resample_1d),
+// keeps the band above 1e-9 of the largest weight (about 30 taps for nu = 1/2) and the device
+// applies  out = clip(A_y * in * A_x^T)  as two FIR passes with per-output-row weights.
+// The channel axis is prefiltered by scipy too but evaluated at integer positions, which returns
+// the samples unchanged, so it is skipped.  Bound: HBM (read level s, write level s+1).
+#include <math.h>
+#include <vector>
+#include <algorithm>
+#include "ica_pyramid.cuh"
+
+namespace ica {
+
+// round-half-to-even like np.round (src/zoom.py:20-21 and skimage's output shape)
+int round_half_even(double v) { return (int)nearbyint(v); }
+
+int zoomed_size(int n, double factor) { return round_half_even((double)n * factor); }
+
+void build_resample_1d(int n_in, int n_out, Resample1D* out, double rel_threshold) {
+  const double f = (double)n_in / (double)n_out;
+  const double sigma = f > 1.0 ? (f - 1.0) / 2.0 : 0.0;
+  // scipy.ndimage._gaussian_kernel1d, truncate = 4
+  std::vector<double> gk;
+  int radius = 0;
+  if (sigma > 1e-15) {
+    radius = (int)(4.0 * sigma + 0.5);
+    gk.resize(2 * radius + 1);
+    double sum = 0.0;
+    for (int i = -radius; i <= radius; ++i) { gk[i + radius] = exp(-0.5 / (sigma * sigma) * i * i); sum += gk[i + radius]; }
+    for (auto& w : gk) w /= sum;
+  }
+  const int N = n_in + 2 * kSplinePad;
+  const double z = sqrt(3.0) - 2.0;
+  // evaluation taps and weights per output sample
+  std::vector<int> efirst(n_out);
+  std::vector<double> ew(4 * (size_t)n_out);
+  for (int o = 0; o < n_out; ++o) {
+    const double cc = (o + 0.5) * f - 0.5 + kSplinePad;
+    const double fl = floor(cc);
+    const double t = cc - fl;
+    efirst[o] = (int)fl - 1;
+    ew[4 * o + 0] = (1 - t) * (1 - t) * (1 - t) / 6.0;
+    ew[4 * o + 1] = (3 * t * t * t - 6 * t * t + 4) / 6.0;
+    ew[4 * o + 2] = (-3 * t * t * t + 3 * t * t + 3 * t + 1) / 6.0;
+    ew[4 * o + 3] = t * t * t / 6.0;
+  }
+  // banded storage around the centre of each output row
+  const int RB = 48;
+  const int BWD = 2 * RB + 1;
+  std::vector<double> band((size_t)n_out * BWD, 0.0);
+  std::vector<int> bstart(n_out);
+  for (int o = 0; o < n_out; ++o) bstart[o] = (int)floor((o + 0.5) * f - 0.5) - RB;
+  std::vector<double> c(N);
+  for (int j = 0; j < n_in; ++j) {
+    std::fill(c.begin(), c.end(), 0.0);
+    // Gaussian response of the impulse at j (correlate, zero extension, output domain [0,n_in))
+    if (radius > 0) {
+      for (int i = std::max(0, j - radius); i <= std::min(n_in - 1, j + radius); ++i) c[kSplinePad + i] = gk[j - i + radius];
+    } else {
+      c[kSplinePad + j] = 1.0;
+    }
+    // scipy ni_splines.c apply_filter (order 3: one pole, gain (1-z)(1-1/z) = 6), mirror init
+    for (int i = 0; i < N; ++i) c[i] *= 6.0;
+    {
+      double zi = z;
+      const double zn1 = pow(z, (double)(N - 1));
+      double c0 = c[0] + zn1 * c[N - 1];
+      for (int i = 1; i < N - 1; ++i) { c0 += zi * (c[i] + zn1 * c[N - 1 - i]); zi *= z; }
+      c[0] = c0 / (1.0 - zn1 * zn1);
+    }
+    for (int i = 1; i < N; ++i) c[i] += z * c[i - 1];
+    c[N - 1] = (z * c[N - 2] + c[N - 1]) * z / (z * z - 1.0);
+    for (int i = N - 2; i >= 0; --i) c[i] = z * (c[i + 1] - c[i]);
+    // evaluate the outputs whose band can contain j
+    const int olo = std::max(0, (int)floor((j - RB - 2) / f) - 1);
+    const int ohi = std::min(n_out - 1, (int)ceil((j + RB + 2) / f) + 1);
+    for (int o = olo; o <= ohi; ++o) {
+      const int col = j - bstart[o];
+      if (col < 0 || col >= BWD) continue;
+      double s = 0.0;
+      for (int k = 0; k < 4; ++k) {
+        const int idx = efirst[o] + k;
+        if (idx >= 0 && idx < N) s += ew[4 * o + k] * c[idx];
+      }
+      band[(size_t)o * BWD + col] = s;
+    }
+  }
+  // keep the significant band
+  double mx = 0.0;
+  for (double v : band) mx = std::max(mx, fabs(v));
+  const double thr = rel_threshold * mx;
+  std::vector<int> first(n_out), last(n_out);
+  int taps = 1;
+  for (int o = 0; o < n_out; ++o) {
+    int fi = BWD, la = -1;
+    for (int k = 0; k < BWD; ++k) if (fabs(band[(size_t)o * BWD + k]) > thr) { fi = std::min(fi, k); la = std::max(la, k); }
+    if (la < 0) { fi = RB; la = RB; }
+    first[o] = bstart[o] + fi; last[o] = bstart[o] + la;
+    taps = std::max(taps, la - fi + 1);
+  }
+  taps = std::min(taps, n_in);
+  out->n_in = n_in; out->n_out = n_out; out->taps = taps;
+  out->start.resize(n_out);
+  out->weights.assign((size_t)n_out * taps, 0.f);
+  for (int o = 0; o < n_out; ++o) {
+    int st = first[o] - (taps - (last[o] - first[o] + 1)) / 2;   // centre the kept band
+    st = std::max(0, std::min(st, n_in - taps));
+    out->start[o] = st;
+    for (int k = 0; k < taps; ++k) {
+      const int col = st + k - bstart[o];
+      out->weights[(size_t)o * taps + k] = (col >= 0 && col < BWD) ? (float)band[(size_t)o * BWD + col] : 0.f;
+    }
+  }
+}
+
+namespace {
+
+constexpr int kVR = 4;        // output rows per thread in the vertical pass
+constexpr int kMaxTaps = 64;
+
+// ---- vertical pass: tmp[oy][j] = sum_k Wy[oy][k] * in[sy[oy]+k][j],  j over nx*C floats
+__global__ void __launch_bounds__(256) pyr_vertical_kernel(
+    const float* __restrict__ in0, long long in_stride, int in_pitch, int ncols, int ny_out,
+    const float* __restrict__ W, const int* __restrict__ start, int taps,
+    float* __restrict__ tmp, long long tmp_stride) {
+  __shared__ float sw[kVR][kMaxTaps];
+  __shared__ int sst[kVR];
+  const int img = blockIdx.z;
+  const int oy0 = blockIdx.y * kVR;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = threadIdx.x; i < kVR * taps; i += blockDim.x) {
+    const int r = i / taps, k = i % taps;
+    sw[r][k] = (oy0 + r < ny_out) ? W[(long long)(oy0 + r) * taps + k] : 0.f;
+  }
+  if (threadIdx.x < kVR) sst[threadIdx.x] = start[min(oy0 + threadIdx.x, ny_out - 1)];
+  __syncthreads();
+  if (j >= ncols) return;
+  int row_lo = sst[0], row_hi = sst[0] + taps;
+#pragma unroll
+  for (int r = 1; r < kVR; ++r) { row_lo = min(row_lo, sst[r]); row_hi = max(row_hi, sst[r] + taps); }
+  const float* in = in0 + (long long)img * in_stride + j;
+  float acc[kVR];
+#pragma unroll
+  for (int r = 0; r < kVR; ++r) acc[r] = 0.f;
+  for (int row = row_lo; row < row_hi; ++row) {
+    const float v = __ldg(in + (long long)row * in_pitch);
+#pragma unroll
+    for (int r = 0; r < kVR; ++r) {
+      const int k = row - sst[r];
+      if (k >= 0 && k < taps) acc[r] = fmaf(sw[r][k], v, acc[r]);
+    }
+  }
+  float* o = tmp + (long long)img * tmp_stride + j;
+#pragma unroll
+  for (int r = 0; r < kVR; ++r) if (oy0 + r < ny_out) o[(long long)(oy0 + r) * ncols] = acc[r];
+}
+
+// ---- horizontal pass + clip to the parent's range + min/max of the new level
+template <int C>
+__global__ void __launch_bounds__(256) pyr_horizontal_kernel(
+    const float* __restrict__ tmp, long long tmp_stride, int ncols_in, int nx_out, int ny_out,
+    const float* __restrict__ Wt /* [taps][nx_out] */, const int* __restrict__ start, int taps,
+    float* __restrict__ out0, long long out_stride, int out_pitch,
+    const MinMaxKeys* __restrict__ mm_parent, int mm_parent_stride,
+    MinMaxKeys* __restrict__ mm_child, int mm_child_stride) {
+  const int img = blockIdx.z;
+  const int oy = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;   // flat ox*C + c
+  const MinMaxKeys pk = mm_parent[(long long)img * mm_parent_stride];
+  const float lo = key_float(pk.lo), hi = key_float(pk.hi);
+  float val = 0.f;
+  const bool active = e < nx_out * C;
+  if (active) {
+    const int ox = e / C, c = e - ox * C;
+    const float* row = tmp + (long long)img * tmp_stride + (long long)oy * ncols_in + c;
+    const int st = __ldg(start + ox);
+    float acc = 0.f;
+    for (int k = 0; k < taps; ++k) acc = fmaf(__ldg(Wt + (long long)k * nx_out + ox), __ldg(row + (st + k) * C), acc);
+    val = fminf(fmaxf(acc, lo), hi);
+    out0[(long long)img * out_stride + (long long)oy * out_pitch + e] = val;
+  }
+  // block min/max -> order-preserving keys -> one atomic pair per block
+  unsigned kmin = active ? float_key(val) : 0xffffffffu;
+  unsigned kmax = active ? float_key(val) : 0u;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  }
+  __shared__ unsigned smin[8], smax[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { smin[warp] = kmin; smax[warp] = kmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { kmin = min(kmin, smin[w]); kmax = max(kmax, smax[w]); }
+    MinMaxKeys* ck = mm_child + (long long)img * mm_child_stride;
+    atomicMin(&ck->lo, kmin);
+    atomicMax(&ck->hi, kmax);
+  }
+}
+
+__global__ void minmax_reset_kernel(MinMaxKeys* mm, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) { mm[i].lo = 0xffffffffu; mm[i].hi = 0u; }
+}
+
+// min/max of a whole image (level 0): grid (blocks, images)
+__global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ img0, long long stride, long long count,
+                                                      MinMaxKeys* __restrict__ mm, int mm_stride) {
+  const float* img = img0 + (long long)blockIdx.y * stride;
+  unsigned kmin = 0xffffffffu, kmax = 0u;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const float v = __ldg(img + i);
+    if (v == v) { const unsigned k = float_key(v); kmin = min(kmin, k); kmax = max(kmax, k); }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  }
+  __shared__ unsigned smin[8], smax[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { smin[warp] = kmin; smax[warp] = kmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { kmin = min(kmin, smin[w]); kmax = max(kmax, smax[w]); }
+    MinMaxKeys* k = mm + (long long)blockIdx.y * mm_stride;
+    atomicMin(&k->lo, kmin);
+    atomicMax(&k->hi, kmax);
+  }
+}
+
+// dtype conversion of host-format inputs (uint8 / float64 -> float32), vectorised by 4
+template <typename T>
+__global__ void convert_to_float_kernel(const T* __restrict__ in, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (float)in[i];
+}
+
+}  // namespace
+
+cudaError_t launch_minmax_reset(MinMaxKeys* mm, int count, cudaStream_t stream) {
+  minmax_reset_kernel<<<(count + 255) / 256, 256, 0, stream>>>(mm, count);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_minmax(const float* img0, long long stride, long long count, int nimg, MinMaxKeys* mm,
+                          int mm_stride, cudaStream_t stream) {
+  int blocks = (int)std::min<long long>((count + 256 * 8 - 1) / (256 * 8), 64);
+  if (blocks < 1) blocks = 1;
+  minmax_kernel<<<dim3(blocks, nimg), 256, 0, stream>>>(img0, stride, count, mm, mm_stride);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pyr_down(const float* in0, long long in_stride, int in_pitch, int nx_in, int ny_in, int channels,
+                            const DeviceResample& ry, const DeviceResample& rx, float* tmp, long long tmp_stride,
+                            float* out0, long long out_stride, int out_pitch, int nimg,
+                            const MinMaxKeys* mm_parent, int mm_parent_stride, MinMaxKeys* mm_child,
+                            int mm_child_stride, cudaStream_t stream) {
+  const int ncols = nx_in * channels;
+  const int ny_out = ry.n_out, nx_out = rx.n_out;
+  {
+    dim3 grid((ncols + 255) / 256, (ny_out + kVR - 1) / kVR, nimg);
+    pyr_vertical_kernel<<<grid, 256, 0, stream>>>(in0, in_stride, in_pitch, ncols, ny_out, ry.weights, ry.start,
+                                                   ry.taps, tmp, tmp_stride);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  {
+    const int ne = nx_out * channels;
+    const int threads = ne >= 256 ? 256 : ((ne + 31) / 32) * 32;
+    dim3 grid((ne + threads - 1) / threads, ny_out, nimg);
+    if (channels == 3)
+      pyr_horizontal_kernel<3><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, ny_out, rx.weights_t,
+                                                              rx.start, rx.taps, out0, out_stride, out_pitch, mm_parent,
+                                                              mm_parent_stride, mm_child, mm_child_stride);
+    else
+      pyr_horizontal_kernel<1><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, ny_out, rx.weights_t,
+                                                              rx.start, rx.taps, out0, out_stride, out_pitch, mm_parent,
+                                                              mm_parent_stride, mm_child, mm_child_stride);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_convert_u8(const unsigned char* in, float* out, long long n, cudaStream_t stream) {
+  int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+  convert_to_float_kernel<unsigned char><<<blocks, 256, 0, stream>>>(in, out, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_convert_f64(const double* in, float* out, long long n, cudaStream_t stream) {
+  int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+  convert_to_float_kernel<double><<<blocks, 256, 0, stream>>>(in, out, n);
+  return cudaGetLastError();
+}
+
+int max_taps() { return kMaxTaps; }
+
+}  // namespace ica

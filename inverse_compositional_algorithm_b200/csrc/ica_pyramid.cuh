@@ -1,0 +1,40 @@
+// Host-visible interface of ica_pyramid.cu
+#pragma once
+#include <vector>
+#include "ica_common.cuh"
+
+namespace ica {
+
+// Banded 1-D resampling operator (host): out[o] = sum_k weights[o*taps+k] * in[start[o]+k]
+struct Resample1D {
+  int n_in = 0, n_out = 0, taps = 0;
+  std::vector<int> start;
+  std::vector<float> weights;
+};
+
+// The same operator on the device; weights_t is the [taps][n_out] transpose for the horizontal pass
+struct DeviceResample {
+  int n_in = 0, n_out = 0, taps = 0;
+  int* start = nullptr;
+  float* weights = nullptr;
+  float* weights_t = nullptr;
+};
+
+int round_half_even(double v);
+int zoomed_size(int n, double factor);   // src/zoom.py:8-22
+void build_resample_1d(int n_in, int n_out, Resample1D* out, double rel_threshold = 1e-9);
+int max_taps();
+
+cudaError_t launch_minmax_reset(MinMaxKeys* mm, int count, cudaStream_t stream);
+cudaError_t launch_minmax(const float* img0, long long stride, long long count, int nimg, MinMaxKeys* mm,
+                          int mm_stride, cudaStream_t stream);
+// one level for `nimg` images laid out with the given strides; tmp holds ny_out x (nx_in*C) floats per image
+cudaError_t launch_pyr_down(const float* in0, long long in_stride, int in_pitch, int nx_in, int ny_in, int channels,
+                            const DeviceResample& ry, const DeviceResample& rx, float* tmp, long long tmp_stride,
+                            float* out0, long long out_stride, int out_pitch, int nimg,
+                            const MinMaxKeys* mm_parent, int mm_parent_stride, MinMaxKeys* mm_child,
+                            int mm_child_stride, cudaStream_t stream);
+cudaError_t launch_convert_u8(const unsigned char* in, float* out, long long n, cudaStream_t stream);
+cudaError_t launch_convert_f64(const double* in, float* out, long long n, cudaStream_t stream);
+
+}  // namespace ica

@@ -1,0 +1,174 @@
+"""Drivers: host-side mirror of the reference's ``src/inverse_compositional_algorithm.py``.
+
+Same three entry points, same argument names, same return tuple ``(p, error, DI, Iw)`` and
+the same ``ValueError``s.  All arithmetic runs in ``libica_b200.so`` (sm_100a CUDA): one
+``ica_plan_run_host`` call per registration builds both pyramids, iterates every scale on the
+device (fused warp / residual / rho' / b / H kernel with the solve-and-compose epilogue) and
+returns the parameters; nothing is computed on the CPU and there is no fallback.
+
+Beyond the reference: :func:`register_batch` runs B independent pairs in one call (the batched
+shape of the reference's Keras twin, ``src/keras-tf/tf_inverse_compositional_algorithm.py:467-583``,
+but with per-pair convergence).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _native
+from . import constants as cts
+from .image_optimisation import RobustErrorFunctionType, _as_robust
+from .transformation import TransformType, _as_type
+
+_PLAN_CACHE: dict = {}
+_PLAN_CACHE_MAX = 8
+
+
+def _get_plan(**key):
+    k = tuple(sorted(key.items()))
+    plan = _PLAN_CACHE.get(k)
+    if plan is None:
+        if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE))).close()
+        plan = _native.Plan(**key)
+        _PLAN_CACHE[k] = plan
+    return plan
+
+
+def clear_plan_cache():
+    while _PLAN_CACHE:
+        _PLAN_CACHE.popitem()[1].close()
+
+
+def _check_rgb(I1, I2):
+    # ica.py:48-49, 300-301
+    if len(I1.shape) != 3 or len(I2.shape) != 3 or I1.shape[2] != 3 or I2.shape[2] != 3:
+        raise ValueError("I1 and I2 must be RGB images with channels in the last dimension")
+
+
+def _check_common(I1, I2, TOL):
+    # ica.py:55-60, 172-177, 304-311
+    if I1.shape != I2.shape:
+        raise ValueError("I1 and I2 must have the same dimensions")
+    if TOL >= 0.01:
+        raise ValueError("TOL must be positive and very small (less than 0.01)")
+
+
+def _as_batch(I):
+    I = np.asarray(I)
+    if I.dtype not in (np.float32, np.uint8, np.float64):
+        I = I.astype(np.float64)  # ica.py:63-65 casts everything to float64
+    return np.ascontiguousarray(I)[None]
+
+
+def _print_trace(traj, n, quadratic, with_scale):
+    """The reference's verbose lines (ica.py:125-129, 253-257, 341-345, 357-358)."""
+    last_scale = None
+    for row in traj:
+        s, it, err, lam = int(row[0]), int(row[1]), row[2], row[3]
+        if with_scale and s != last_scale:
+            print(f"Scale: {s}")
+            print("(L2 norm)" if quadratic else "(Robust error function)")
+            last_scale = s
+        ptxt = " ".join(str(v) for v in row[4:4 + n])
+        if quadratic:
+            print(f"Iteration {it}: |Dp|={err}: p=({ptxt})")
+        else:
+            print(f"|Dp|={err}: p=({ptxt}), lambda_={lam}")
+
+
+def _run_single(I1, I2, p, transform_type, nscales, nu, TOL, robust_type, robust_loop, lambda_,
+                nanifoutside, delta, verbose):
+    t = _as_type(transform_type)
+    r = _as_robust(robust_type)
+    n = t.nparams()
+    ny, nx, nz = I1.shape
+    plan = _get_plan(batch=1, height=ny, width=nx, channels=nz, nscales=int(nscales), nu=float(nu),
+                     transform_type=t.value, robust_type=r.value, robust_loop=bool(robust_loop),
+                     lambda_=float(lambda_), tol=float(TOL), max_iter=cts.MAX_ITER, delta=int(delta),
+                     nanifoutside=(nanifoutside is True), gray_as_rgb=False,
+                     record_trajectory=bool(verbose), write_di_iw=True)
+    p0 = np.zeros(_native.MAX_PARAMS)
+    p0[:n] = np.asarray(p, dtype=np.float64)[:n]
+    pout, err, iters, DI, Iw = plan.run_host(_as_batch(I1), _as_batch(I2), p0[None], want_images=True)
+    if verbose:
+        _print_trace(plan.trajectory()[0], n, quadratic=not robust_loop, with_scale=nscales > 1)
+    return pout[0, :n].copy(), float(err[0]), DI[0].astype(np.float64), Iw[0].astype(np.float64)
+
+
+def inverse_compositional_algorithm(I1, I2, p, transform_type, TOL, nanifoutside, delta, verbose):
+    """Quadratic (L2) inverse compositional algorithm, one scale.
+    Drop-in for ``src/inverse_compositional_algorithm.py:17-133``; ``p`` is updated in place when
+    it is a float64 array (the reference mutates it) and also returned."""
+    _check_rgb(I1, I2)
+    _check_common(I1, I2, TOL)
+    pout, err, DI, Iw = _run_single(I1, I2, p, transform_type, 1, 0.5, TOL,
+                                    RobustErrorFunctionType.QUADRATIC, False, 0.0, nanifoutside,
+                                    delta, verbose)
+    return _writeback(p, pout), err, DI, Iw
+
+
+def robust_inverse_compositional_algorithm(I1, I2, p, transform_type, TOL, robust_type, lambda_,
+                                           nanifoutside, delta, verbose):
+    """Robust inverse compositional algorithm, one scale.
+    Drop-in for ``src/inverse_compositional_algorithm.py:135-261`` (rho' and the weighted Hessian
+    are re-evaluated every iteration, also for QUADRATIC)."""
+    _check_common(I1, I2, TOL)
+    if len(I1.shape) != 3 or I1.shape[2] not in (1, 3):
+        raise ValueError("I1 and I2 must be (H, W, 3) or (H, W, 1) images")
+    pout, err, DI, Iw = _run_single(I1, I2, p, transform_type, 1, 0.5, TOL, robust_type, True,
+                                    lambda_, nanifoutside, delta, verbose)
+    return _writeback(p, pout), err, DI, Iw
+
+
+def pyramidal_inverse_compositional_algorithm(I1, I2, p, transform_type, nscales, nu, TOL,
+                                              robust_type, lambda_, nanifoutside, delta, verbose):
+    """Coarse-to-fine driver.  Drop-in for ``src/inverse_compositional_algorithm.py:264-374``:
+    skimage-``rescale`` pyramid, QUADRATIC -> quadratic loop, anything else -> robust loop,
+    ``zoom_in_parameters`` between scales; like the reference the input ``p`` is copied and only
+    used when ``nscales == 1`` (ica.py:327, 372)."""
+    _check_rgb(I1, I2)
+    _check_common(I1, I2, TOL)
+    r = _as_robust(robust_type)
+    robust_loop = r != RobustErrorFunctionType.QUADRATIC
+    return _run_single(I1, I2, np.copy(p), transform_type, nscales, nu, TOL, r, robust_loop, lambda_,
+                       nanifoutside, delta, verbose)
+
+
+def _writeback(p, pout):
+    if isinstance(p, np.ndarray) and p.dtype == np.float64 and p.shape == pout.shape:
+        p[...] = pout
+        return p
+    return pout
+
+
+def register_batch(I1, I2, transform_type, nscales=1, nu=0.5, TOL=1e-3,
+                   robust_type=RobustErrorFunctionType.QUADRATIC, lambda_=0.0, nanifoutside=True,
+                   delta=10, p0=None, gray_as_rgb=True, return_images=False, plan=None):
+    """B independent registrations in one call: ``I1``/``I2`` are ``[B, H, W, C]`` (C = 1 or 3,
+    float32 / uint8 / float64); ``transform_type`` is one type or a length-B sequence (mixed
+    batches).  Returns ``(p [B, 8] zero-padded, error [B], iters [B, nscales])`` and, with
+    ``return_images``, ``DI`` and ``Iw``.  A gray batch behaves as the reference would on the
+    image replicated to three channels unless ``gray_as_rgb=False``."""
+    I1 = np.asarray(I1)
+    I2 = np.asarray(I2)
+    if I1.ndim != 4 or I1.shape[3] not in (1, 3):
+        raise ValueError("I1 and I2 must be [B, H, W, C] with C in (1, 3)")
+    _check_common(I1, I2, TOL)
+    B, ny, nx, nz = I1.shape
+    types = ([_as_type(transform_type)] * B if not isinstance(transform_type, (list, tuple, np.ndarray))
+             else [_as_type(t) for t in transform_type])
+    if len(types) != B:
+        raise ValueError("one transform type per pair is required")
+    r = _as_robust(robust_type)
+    if plan is None:
+        plan = _get_plan(batch=B, height=ny, width=nx, channels=nz, nscales=int(nscales),
+                         nu=float(nu), transform_type=types[0].value, robust_type=r.value,
+                         robust_loop=r != RobustErrorFunctionType.QUADRATIC, lambda_=float(lambda_),
+                         tol=float(TOL), max_iter=cts.MAX_ITER, delta=int(delta),
+                         nanifoutside=(nanifoutside is True), gray_as_rgb=bool(gray_as_rgb) and nz == 1,
+                         record_trajectory=False, write_di_iw=bool(return_images))
+    plan.set_transform_types([t.value for t in types])
+    pout, err, iters, DI, Iw = plan.run_host(I1, I2, p0, want_images=return_images)
+    if return_images:
+        return pout, err, iters, DI, Iw
+    return pout, err, iters
