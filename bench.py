@@ -244,15 +244,17 @@ def run_ours(args, wl):
     torch.cuda.synchronize()
     p_h = np.zeros((B, 8)); err_h = np.zeros(B); it_h = np.zeros((B, ns), dtype=np.int32)
     e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(0 if args.no_e2e else max(1, min(args.warmup, 2))):
         p_h[:] = 0
         plan.run_host_ptrs(h1.data_ptr(), h2.data_ptr(), _native.DTYPE_F32, p_h, err_h, it_h)
     barrier()
     e2e_ms = 0.0
-    for _ in range(e2e_steps):
+    for _ in range(0 if args.no_e2e else e2e_steps):
         p_h[:] = 0
         plan.run_host_ptrs(h1.data_ptr(), h2.data_ptr(), _native.DTYPE_F32, p_h, err_h, it_h)
         e2e_ms += plan.last_host_run_ms()
+    if args.no_e2e:
+        e2e_ms = float("inf")
     if world > 1:
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -318,6 +320,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=32, help="image pairs per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

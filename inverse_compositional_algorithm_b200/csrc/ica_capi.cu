@@ -35,7 +35,9 @@ using namespace ica;
 
 struct ica_plan {
   ica_config cfg;
-  int B, H, W, C, nscales, dh, G;
+  int B, H, W, C, nscales, dh;
+  int max_chunks = 0, grid = 0;
+  int* chunk_start = nullptr;
   LevelDesc lv[ICA_MAX_SCALES];
   long long in_stride = 0, pyr_stride = 0;
   float *pyr1 = nullptr, *pyr2 = nullptr;
@@ -142,7 +144,9 @@ void fill_iter_params(const ica_plan* pl, const float* I1, const float* I2, Iter
   P->dbg_Hb = nullptr;
   P->n_active = pl->n_active;
   P->traj_cap = pl->traj_cap;
-  P->G = pl->G;
+  P->chunk_start = pl->chunk_start;
+  P->B = pl->B;
+  P->max_chunks = pl->max_chunks;
   P->robust_type = pl->cfg.robust_type;
   P->robust_loop = pl->cfg.robust_loop;
   P->lambda_cfg = pl->cfg.lambda_;
@@ -217,7 +221,7 @@ int ica_plan_destroy(ica_plan* pl) {
   if (!pl) return ICA_OK;
   cudaFree(pl->pyr1); cudaFree(pl->pyr2); cudaFree(pl->tmp);
   for (int s = 0; s < ICA_MAX_SCALES; ++s) { free_resample(&pl->ry[s]); free_resample(&pl->rx[s]); }
-  cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->traj); cudaFree(pl->n_active);
+  cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->traj); cudaFree(pl->n_active);
   if (pl->h_n_active) cudaFreeHost(pl->h_n_active);
   cudaFree(pl->ttypes_dev); cudaFree(pl->p_dev); cudaFree(pl->err_dev); cudaFree(pl->iters_dev);
   cudaFree(pl->in1_dev); cudaFree(pl->in2_dev); cudaFree(pl->raw_dev); cudaFree(pl->DI_dev); cudaFree(pl->Iw_dev);
@@ -248,16 +252,25 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   for (int s = 0; s < pl->nscales; ++s) {
     if (s > 0) { nx = std::max(zoomed_size(nx, cfg->nu), 1); ny = std::max(zoomed_size(ny, cfg->nu), 1); }
     LevelDesc& L = pl->lv[s];
-    L.nx = nx; L.ny = ny; L.pitch = nx * pl->C;
+    L.nx = nx; L.ny = ny;
+    // levels >= 1 live in plan-owned slabs: pad rows to 16 bytes so the TMA bulk copies apply
+    L.pitch = s == 0 ? nx * pl->C : ((nx * pl->C + 3) / 4) * 4;
     L.offset = s == 0 ? 0 : off;
     L.tiles_x = (nx + TWv - 1) / TWv; L.tiles_y = (ny + THv - 1) / THv;
-    if (s > 0) off += ((long long)nx * ny * pl->C + 31) / 32 * 32;
+    if (s > 0) off += ((long long)L.pitch * ny + 31) / 32 * 32;
   }
   pl->in_stride = (long long)pl->H * pl->W * pl->C;
   pl->pyr_stride = off;
   const int nt0 = pl->lv[0].tiles_x * pl->lv[0].tiles_y;
-  int G = cfg->blocks_per_pair > 0 ? cfg->blocks_per_pair : std::max(8, (592 + pl->B - 1) / pl->B);
-  pl->G = std::max(1, std::min(G, nt0));
+  // chunks (= partial slots) per pair: enough for one straggler pair to cover the whole chip
+  int mc = cfg->blocks_per_pair > 0 ? cfg->blocks_per_pair : (pl->B <= 4 ? 1024 : 256);
+  pl->max_chunks = std::max(1, std::min(mc, nt0));
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    pl->grid = 2 * sms;   // persistent: 2 CTAs per SM (register- and shared-memory-limited)
+  }
   int rc = ICA_OK;
 #define TRY(expr) do { if ((rc = (expr)) != ICA_OK) { ica_plan_destroy(pl); return rc; } } while (0)
 #define TRY_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { set_error("%s failed: %s", #expr, cudaGetErrorString(e__)); ica_plan_destroy(pl); return ICA_ERR_CUDA; } } while (0)
@@ -280,7 +293,8 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   }
   TRY(dev_alloc(pl, &pl->state, (size_t)pl->B));
   TRY(dev_alloc(pl, &pl->mm, (size_t)pl->B * pl->nscales * 2));
-  TRY(dev_alloc(pl, &pl->partials, (size_t)pl->B * pl->G * kAccStride));
+  TRY(dev_alloc(pl, &pl->partials, (size_t)pl->B * pl->max_chunks * kAccStride));
+  TRY(dev_alloc(pl, &pl->chunk_start, (size_t)pl->B + 1));
   pl->traj_cap = pl->nscales * cfg->max_iter;
   if (cfg->flags & ICA_FLAG_RECORD_TRAJECTORY) TRY(dev_alloc(pl, &pl->traj, (size_t)pl->B * pl->traj_cap * ICA_TRAJ_STRIDE));
   TRY(dev_alloc(pl, &pl->n_active, 1));
@@ -375,17 +389,19 @@ int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* 
   IterParams P;
   fill_iter_params(pl, I1, I2, &P);
   const int max_launches = pl->nscales * pl->cfg.max_iter;
-  const int poll_every = 4;
+  const int poll_every = 8;
   int done = 0;
   // a pair needs at least one launch per scale, so the first poll can wait that long
   int next_poll = std::max(pl->nscales, poll_every);
   for (int it = 0; it < max_launches && !done; ++it) {
     const bool timed = pl->timing && pl->n_ev_iter + 2 <= (int)pl->ev_iter.size();
+    ICA_LAUNCH_CHECK(launch_schedule(P, stream));   // work list + number of unfinished pairs
     if (timed) cudaEventRecord(pl->ev_iter[pl->n_ev_iter++], stream);
-    ICA_LAUNCH_CHECK(launch_iterate(P, pl->B, pl->C, pl->dh, stream));
+    ICA_LAUNCH_CHECK(launch_iterate(P, pl->C, pl->dh, pl->grid, stream));
     if (timed) cudaEventRecord(pl->ev_iter[pl->n_ev_iter++], stream);
-    pl->launches += 1;
+    pl->launches += 2;
     if (it + 1 >= next_poll && it + 1 < max_launches) {
+      // n_active was written by the schedule kernel of THIS iteration: 0 means the launch above was empty
       ICA_CUDA_CHECK(cudaMemcpyAsync(pl->h_n_active, pl->n_active, sizeof(int), cudaMemcpyDeviceToHost, stream));
       ICA_CUDA_CHECK(cudaStreamSynchronize(stream));
       if (*pl->h_n_active <= 0) done = 1;
@@ -598,7 +614,9 @@ int ica_rescale_host(const float* image, int32_t height, int32_t width, int32_t 
   if (!rc) rc = build_pyramids(pl, pl->in1_dev, pl->in2_dev, 0);
   if (!rc) {
     const LevelDesc& L = pl->lv[1];
-    cudaError_t e = cudaMemcpy(out, pl->pyr1 + L.offset, (size_t)L.nx * L.ny * channels * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy2D(out, (size_t)L.nx * channels * sizeof(float), pl->pyr1 + L.offset,
+                                 (size_t)L.pitch * sizeof(float), (size_t)L.nx * channels * sizeof(float), L.ny,
+                                 cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { set_error("ica_rescale_host: %s", cudaGetErrorString(e)); rc = ICA_ERR_CUDA; }
     if (out_h) *out_h = L.ny;
     if (out_w) *out_w = L.nx;
@@ -640,7 +658,8 @@ int ica_hessian_b_host(const float* I1, const float* I2, int32_t height, int32_t
     IterParams P;
     fill_iter_params(pl, pl->in1_dev, pl->in2_dev, &P);
     P.dbg_Hb = d_dbg;
-    if (e == cudaSuccess) e = launch_iterate(P, 1, channels, pl->dh, 0);
+    if (e == cudaSuccess) e = launch_schedule(P, 0);
+    if (e == cudaSuccess) e = launch_iterate(P, channels, pl->dh, pl->grid, 0);
     double hb[72];
     if (e == cudaSuccess) e = cudaMemcpy(hb, d_dbg, sizeof(hb), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { set_error("ica_hessian_b_host: %s", cudaGetErrorString(e)); rc = ICA_ERR_CUDA; }

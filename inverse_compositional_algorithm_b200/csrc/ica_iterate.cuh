@@ -15,12 +15,14 @@ struct IterParams {
   int nscales;
   PairState* state;       // [B]
   const MinMaxKeys* mm;   // [B][nscales][2]  (0 = I1, 1 = I2)
-  double* partials;       // [B][G][kAccStride]
+  double* partials;       // [B][max_chunks][kAccStride]
   double* traj;           // [B][traj_cap][ICA_TRAJ_STRIDE] or nullptr
   double* dbg_Hb;         // nullptr, or 72 doubles: H (<=64) then b (8); state left untouched
   int* n_active;
+  int* chunk_start;       // [B+1] work list of the current launch (ica_schedule_kernel)
+  int B;
+  int max_chunks;         // partial slots per pair
   int traj_cap;
-  int G;                  // blocks per pair
   int robust_type;
   int robust_loop;        // 1: rho' and H every iteration; 0: quadratic loop (H at iter 0 of a scale)
   double lambda_cfg;
@@ -33,7 +35,8 @@ struct IterParams {
 
 int iterate_tile_w();
 int iterate_tile_h();
-cudaError_t launch_iterate(const IterParams& P, int B, int channels, int dh, cudaStream_t stream);
+cudaError_t launch_schedule(const IterParams& P, cudaStream_t stream);
+cudaError_t launch_iterate(const IterParams& P, int channels, int dh, int grid, cudaStream_t stream);
 cudaError_t launch_init_state(PairState* state, const double* p_in, const int* ttypes, int B, int nscales,
                               double lambda_cfg, int* n_active, cudaStream_t stream);
 cudaError_t launch_export_results(const PairState* state, int B, double* p_out, double* err_out, int* iters_out,
