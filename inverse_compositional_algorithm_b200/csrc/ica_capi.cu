@@ -38,6 +38,7 @@ struct ica_plan {
   int B, H, W, C, nscales, dh;
   int max_chunks = 0, grid = 0;
   int* chunk_start = nullptr;
+  int* item_pair = nullptr;
   LevelDesc lv[ICA_MAX_SCALES];
   long long in_stride = 0, pyr_stride = 0;
   float *pyr1 = nullptr, *pyr2 = nullptr;
@@ -145,6 +146,7 @@ void fill_iter_params(const ica_plan* pl, const float* I1, const float* I2, Iter
   P->n_active = pl->n_active;
   P->traj_cap = pl->traj_cap;
   P->chunk_start = pl->chunk_start;
+  P->item_pair = pl->item_pair;
   P->B = pl->B;
   P->max_chunks = pl->max_chunks;
   P->robust_type = pl->cfg.robust_type;
@@ -221,7 +223,7 @@ int ica_plan_destroy(ica_plan* pl) {
   if (!pl) return ICA_OK;
   cudaFree(pl->pyr1); cudaFree(pl->pyr2); cudaFree(pl->tmp);
   for (int s = 0; s < ICA_MAX_SCALES; ++s) { free_resample(&pl->ry[s]); free_resample(&pl->rx[s]); }
-  cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->traj); cudaFree(pl->n_active);
+  cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->item_pair); cudaFree(pl->traj); cudaFree(pl->n_active);
   if (pl->h_n_active) cudaFreeHost(pl->h_n_active);
   cudaFree(pl->ttypes_dev); cudaFree(pl->p_dev); cudaFree(pl->err_dev); cudaFree(pl->iters_dev);
   cudaFree(pl->in1_dev); cudaFree(pl->in2_dev); cudaFree(pl->raw_dev); cudaFree(pl->DI_dev); cudaFree(pl->Iw_dev);
@@ -295,6 +297,7 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   TRY(dev_alloc(pl, &pl->mm, (size_t)pl->B * pl->nscales * 2));
   TRY(dev_alloc(pl, &pl->partials, (size_t)pl->B * pl->max_chunks * kAccStride));
   TRY(dev_alloc(pl, &pl->chunk_start, (size_t)pl->B + 1));
+  TRY(dev_alloc(pl, &pl->item_pair, (size_t)pl->B * pl->max_chunks));
   pl->traj_cap = pl->nscales * cfg->max_iter;
   if (cfg->flags & ICA_FLAG_RECORD_TRAJECTORY) TRY(dev_alloc(pl, &pl->traj, (size_t)pl->B * pl->traj_cap * ICA_TRAJ_STRIDE));
   TRY(dev_alloc(pl, &pl->n_active, 1));

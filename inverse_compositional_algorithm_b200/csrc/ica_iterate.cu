@@ -14,20 +14,19 @@
 //
 // Execution model
 //   * ica_schedule_kernel (1 block) turns the per-pair scales into a work list: pair b at a
-//     level with T tiles contributes min(T, max_chunks) chunks of consecutive 64x16 tiles.
-//   * ica_iterate_kernel is PERSISTENT: 2 CTAs per SM, each CTA walks the chunk list with a
-//     fixed stride, so a ragged batch (pairs at different scales, different iteration counts)
-//     still fills all 148 SMs and a single straggler at the finest scale is spread over the
-//     whole chip.
-//   * per tile the I1 patch (+halo) and the window of I2 the warp can touch are staged into
-//     shared memory with 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) completing on an
-//     mbarrier; two stages, so the copy of tile t+1 overlaps the arithmetic of tile t.  Rows or
-//     columns of the window that fall outside the image are filled by ordinary stores (NaN for
-//     I2 = skimage's cval, so the NaN footprint falls out of the arithmetic).
-//   * a warp owns one image row at a time; x-moments are accumulated per lane in fp32, a
-//     transposing shuffle reduction leaves moment k on lane k, which folds in y^b in fp64.
-//     Chunk partials go to fixed slots, the last chunk of a pair sums them in a fixed order
-//     (deterministic) and runs the n x n solve / compose epilogue.
+//     level with T tiles contributes min(T, max_chunks) chunks of consecutive 64x14 tiles.
+//   * ica_iterate_kernel is PERSISTENT (2 CTAs per SM) and WARP-SPECIALISED: warp 7 of each CTA
+//     is a producer that walks the CTA's chunks, and per tile stages the I1 patch (+halo) and
+//     the window of I2 the warp can reach into shared memory with 1-D TMA bulk copies
+//     (cp.async.bulk -> UBLKCP) completing on a "full" mbarrier; warps 0-6 consume the stage and
+//     release it through an "empty" mbarrier.  Two stages, so copies of tile t+1 (even of the
+//     next chunk) overlap the arithmetic of tile t, and there is no block-wide barrier in the
+//     tile loop.  Pixels of the window that fall outside the image are filled by ordinary
+//     stores (NaN for I2 = skimage's cval, so the NaN footprint falls out of the arithmetic).
+//   * a consumer warp owns one image row at a time; x-moments are accumulated per lane in fp32,
+//     transposed through shared memory so that moment k lands on lane k, which folds in y^b in
+//     fp64.  Chunk partials go to fixed slots; the last chunk of a pair sums them in a fixed
+//     order (deterministic) and runs the n x n solve / compose epilogue.
 // Bound: HBM (read I1 once + I2 once per pixel-iteration = 2*C*4 bytes); no tensor cores.
 #include "ica_device.cuh"
 #include "ica_transform.cuh"
@@ -37,19 +36,20 @@ namespace ica {
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
+constexpr int kConsumerWarps = 7;    // + 1 producer warp = 8 warps: warps are allocated in groups of 4
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kThreads = kConsumerThreads + 32;   // + one producer warp
 constexpr int TW = 64;            // tile width  (2 pixels per lane: x0+lane, x0+32+lane)
-constexpr int TH = 16;            // tile height (2 rows per warp: y0+warp, y0+8+warp)
+constexpr int TH = 2 * kConsumerWarps;   // tile height 14 (2 rows per consumer warp: y0+warp, y0+7+warp)
 constexpr int HALO = 4;           // I1 patch starts at x0-4 so that row starts are 16-byte aligned
 constexpr int S1PX = TW + 2 * HALO;
 constexpr int S1ROWS = TH + 2;
-constexpr int BW_MAX = 88;        // staged I2 window (pixels, multiple of 4); larger -> global path
-constexpr int BH_MAX = 28;
-constexpr int kSchedCap = 4096;   // pairs whose chunk table is cached in shared memory
+constexpr int BW_MAX = 96;        // staged I2 window; 96*C floats per row == 0 (mod 32 banks): lanes of a
+                                  // warp that sit on different window rows never collide
+constexpr int BH_MAX = 26;        // larger windows (strong rotation / zoom) take the global-memory path
+constexpr int SCR_PITCH = 36;     // floats per row of the per-warp transposition scratch
 
-template <int DH> struct RowVals { static constexpr int K = 3 * (DH + 1) + 2 * (DH / 2 + 1);
-                                   static constexpr int NP = K > 16 ? 32 : (K > 8 ? 16 : 8); };
+template <int DH> struct RowVals { static constexpr int K = 3 * (DH + 1) + 2 * (DH / 2 + 1); };
 
 template <int C> struct Stage {
   static constexpr int S1W = S1PX * C;
@@ -57,23 +57,30 @@ template <int C> struct Stage {
   static constexpr int kFloats = BH_MAX * S2W + S1ROWS * S1W;   // I2 window, then I1 patch
 };
 
-struct PairCtx {          // per-pair constants of the chunk being processed (shared memory)
+// Everything a consumer needs to know about a staged tile (written by the producer).
+struct TileCtl {
   double m64[9];          // warp matrix in fp64 (tie-break path of project_px)
   WarpCoef coef;
   float lo, hi;           // clip range of I2 at this level
   float lambda2;
-  int scale, need_h, pair;
+  int pair, chunk, nch, scale;
+  int need_h, first, last;
+  int x0, y0;
+  int bx0, by0, bw, bh, fits;
+  int nx, ny, pitch;
+  const float* I2;
 };
-
-struct StageCtl { int bx0, by0, bw, bh, fits; };
 
 // ---------------------------------------------------------------- mbarrier / bulk-copy PTX
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx_arrive(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   asm volatile(
@@ -89,6 +96,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// barrier among the consumer threads only (the producer warp never joins it)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
 
 // One image-row segment [xa, xa+w) of row yy: the part that lies inside the image and whose
 // byte range is a multiple of 16 goes through a bulk copy ([xs, xe4), `bytes`); the rest
@@ -125,75 +134,43 @@ __device__ __forceinline__ void fill_row_rest(float* dst, const float* __restric
   }
 }
 
-template <int C, int DH>
-__global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterParams P) {
-  constexpr int K = RowVals<DH>::K;
-  constexpr int NP = RowVals<DH>::NP;
-  constexpr int HW = DH + 1;        // x-powers kept for the Hessian moments
-  constexpr int BWN = DH / 2 + 1;   // x-powers kept for the b moments
-  constexpr int S1W = Stage<C>::S1W;
-  constexpr int S2W = Stage<C>::S2W;
-  constexpr int NENT = K * kYPow;
+// Jacobian entry k as a monomial, in registers (same table as ica_transform.cuh: jacobian_monomials)
+__device__ __forceinline__ void mono_of(int ttype, int k, Mono& jx, Mono& jy) {
+  Mono tx[ICA_MAX_PARAMS], ty[ICA_MAX_PARAMS];
+  jacobian_monomials(ttype, tx, ty);
+  jx = tx[0]; jy = ty[0];
+#pragma unroll
+  for (int i = 1; i < ICA_MAX_PARAMS; ++i) if (i == k) { jx = tx[i]; jy = ty[i]; }
+}
 
-  extern __shared__ __align__(128) float smem[];
-  float* const stage0 = smem;
-  float* const stage1 = smem + Stage<C>::kFloats;
-  int* const s_chunk_start = reinterpret_cast<int*>(smem + 2 * Stage<C>::kFloats);
-  __shared__ __align__(8) unsigned long long s_bar[2];
-  __shared__ PairCtx ctx;
-  __shared__ StageCtl sctl[2];
-  __shared__ unsigned int s_ticket;
-  __shared__ int s_pair, s_chunk, s_flag;
-  __shared__ double s_mom[kAccStride];
-  __shared__ double s_aug[ICA_MAX_PARAMS][2 * ICA_MAX_PARAMS + 1];
-  __shared__ double s_vec[2 * ICA_MAX_PARAMS];
+// Generic (rare) path kept out of line so that its address arithmetic is not hoisted into the fast path.
+template <int C>
+__device__ __noinline__ float sample_global_slow(const float* __restrict__ img, int pitch, int nx, int ny, int cx,
+                                                 int cy, int ch, float wx0, float wx1, float wx2, float wx3,
+                                                 float wy0, float wy1, float wy2, float wy3) {
+  const float wx[4] = {wx0, wx1, wx2, wx3}, wy[4] = {wy0, wy1, wy2, wy3};
+  return sample_global<C>(img, pitch, nx, ny, cx, cy, ch, wx, wy);
+}
 
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
-  const int B = P.B;
-  const int total_chunks = P.chunk_start[B];
-  if ((int)blockIdx.x >= total_chunks) return;
-
-  const bool sched_in_smem = B <= kSchedCap;
-  if (sched_in_smem)
-    for (int i = tid; i <= B; i += kThreads) s_chunk_start[i] = P.chunk_start[i];
-  if (tid == 0) {
-    mbar_init(&s_bar[0], 2);
-    mbar_init(&s_bar[1], 2);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  unsigned phase0 = 0, phase1 = 0;
-
-  const int delta = P.delta;
-  const bool frame = P.frame != 0;
-  const bool robust = P.robust_loop != 0;
-  const float chm = P.ch_mult;
-  const int rtype = P.robust_type;
-
+// ============================================================ producer warp
+template <int C>
+__device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0, float* stage1,
+                                              unsigned long long* full, unsigned long long* empty, TileCtl* tctl,
+                                              double* pm64, int total_chunks, int lane) {
+  constexpr int S1W = Stage<C>::S1W, S2W = Stage<C>::S2W;
+  unsigned k = 0;   // tiles staged so far by this CTA
   for (int item = blockIdx.x; item < total_chunks; item += gridDim.x) {
-    // ---------------- decode the work item: pair and chunk, per-pair constants
-    if (tid == 0) {
-      const int* cs = sched_in_smem ? s_chunk_start : P.chunk_start;
-      int lo_ = 0, hi_ = B;   // largest b with cs[b] <= item
-      while (hi_ - lo_ > 1) { const int mid = (lo_ + hi_) >> 1; if (cs[mid] <= item) lo_ = mid; else hi_ = mid; }
-      s_pair = lo_;
-      s_chunk = item - cs[lo_];
-      const PairState& st = P.state[lo_];
-      ctx.pair = lo_;
-      ctx.scale = st.scale;
-      warp_matrix(st.p, st.ttype, ctx.m64);
-      ctx.coef = make_warp_coef(ctx.m64);
-      const MinMaxKeys mm = P.mm[(lo_ * P.nscales + st.scale) * 2 + 1];
-      ctx.lo = key_float(mm.lo);
-      ctx.hi = key_float(mm.hi);
-      ctx.lambda2 = (float)(st.lambda_it * st.lambda_it);
-      ctx.need_h = (P.robust_loop || st.iter == 0) ? 1 : 0;
-    }
-    __syncthreads();
-    const int pair = s_pair, chunk = s_chunk;
-    const int s = ctx.scale;
+    const int pair = __ldg(P.item_pair + item);
+    const int chunk = item - __ldg(P.chunk_start + pair);
+    const PairState& st = P.state[pair];
+    const int s = st.scale;
+    if (lane == 0) warp_matrix(st.p, st.ttype, pm64);
+    __syncwarp();
+    const WarpCoef coef = make_warp_coef(pm64);
+    const MinMaxKeys mm = P.mm[(pair * P.nscales + s) * 2 + 1];
+    const float lo = key_float(mm.lo), hi = key_float(mm.hi);
+    const float lambda2 = (float)(st.lambda_it * st.lambda_it);
+    const int need_h = (P.robust_loop || st.iter == 0) ? 1 : 0;
     const LevelDesc L = P.lv[s];
     const int nx = L.nx, ny = L.ny, pitch = L.pitch;
     const float* __restrict__ I1 = s == 0 ? P.I1_0 + (long long)pair * P.in_stride
@@ -205,148 +182,166 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
     const int nch = ntiles < P.max_chunks ? ntiles : P.max_chunks;
     const int t_begin = (int)((long long)chunk * ntiles / nch);
     const int t_end = (int)((long long)(chunk + 1) * ntiles / nch);
-    const bool need_h = ctx.need_h != 0;
-    const WarpCoef coef = ctx.coef;
-    const float lo = ctx.lo, hi = ctx.hi, lambda2 = ctx.lambda2;
 
-    // ---------------- staging of one tile into one stage (warps 0 and 1 issue, the others go on)
-    auto issue_tile = [&](int tile, int sidx) {
-      const int x0 = (tile % L.tiles_x) * TW;
-      const int y0 = (tile / L.tiles_x) * TH;
+    for (int tile = t_begin; tile < t_end; ++tile, ++k) {
+      const int sidx = k & 1;
+      const unsigned use = k >> 1;
+      if (use >= 1) mbar_wait(&empty[sidx], (use - 1) & 1);   // consumers released the previous use
       float* s2 = sidx ? stage1 : stage0;
       float* s1 = s2 + BH_MAX * S2W;
-      unsigned long long* bar = &s_bar[sidx];
-      if (warp == 0) {
-        // window of I2 reachable from this tile: project the four corners of its in-image part
-        const int xe_ = min(x0 + TW, nx) - 1, ye_ = min(y0 + TH, ny) - 1;
-        const int px = (lane & 1) ? xe_ : x0, py = (lane & 2) ? ye_ : y0;
-        int cx, cy; float tx, ty;
-        const bool ok = project_px(coef, ctx.m64, px, py, cx, cy, tx, ty);
-        int mnx = cx, mxx = cx, mny = cy, mxy = cy, okall = ok ? 1 : 0;
+      unsigned long long* bar = &full[sidx];
+      TileCtl& tc = tctl[sidx];
+      const int x0 = (tile % L.tiles_x) * TW;
+      const int y0 = (tile / L.tiles_x) * TH;
+      // window of I2 reachable from this tile: project the four corners of its in-image part
+      const int xe_ = min(x0 + TW, nx) - 1, ye_ = min(y0 + TH, ny) - 1;
+      const int px = (lane & 1) ? xe_ : x0, py = (lane & 2) ? ye_ : y0;
+      int cx, cy; float tx, ty;
+      const bool ok = project_px(coef, pm64, px, py, cx, cy, tx, ty);
+      int mnx = cx, mxx = cx, mny = cy, mxy = cy, okall = ok ? 1 : 0;
 #pragma unroll
-        for (int o = 1; o < 4; o <<= 1) {
-          mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-          mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-          okall &= __shfl_xor_sync(0xffffffffu, okall, o);
-        }
-        const int bx0 = ((mnx - 2) >> 2) << 2;                   // floor to a multiple of 4 pixels
-        const int bw = ((mxx + 3 - bx0 + 1) + 3) & ~3;
-        const int by0 = mny - 2;
-        const int bh = mxy + 3 - by0 + 1;
-        const bool fits = okall && bw <= BW_MAX && bh <= BH_MAX && bw > 0 && bh > 0;
-        if (lane == 0) { sctl[sidx].bx0 = bx0; sctl[sidx].by0 = by0; sctl[sidx].bw = bw; sctl[sidx].bh = bh; sctl[sidx].fits = fits ? 1 : 0; }
-        RowPlan rp; rp.xs = bx0; rp.xe4 = bx0; rp.bytes = 0;
-        if (fits && lane < bh) rp = plan_row<C>(by0 + lane, bx0, bw, nx, ny, bulk_ok);
-        unsigned tot = rp.bytes;
+      for (int o = 1; o < 4; o <<= 1) {
+        mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        okall &= __shfl_xor_sync(0xffffffffu, okall, o);
+      }
+      const int bx0 = ((mnx - 2) >> 2) << 2;                   // floor to a multiple of 4 pixels
+      const int bw = ((mxx + 3 - bx0 + 1) + 3) & ~3;
+      const int by0 = mny - 2;
+      const int bh = mxy + 3 - by0 + 1;
+      const bool fits = okall && bw <= BW_MAX && bh <= BH_MAX && bw > 0 && bh > 0;
+      if (lane < 9) tc.m64[lane] = pm64[lane];
+      if (lane == 0) {
+        tc.coef = coef; tc.lo = lo; tc.hi = hi; tc.lambda2 = lambda2;
+        tc.pair = pair; tc.chunk = chunk; tc.nch = nch; tc.scale = s;
+        tc.need_h = need_h; tc.first = tile == t_begin; tc.last = tile + 1 == t_end;
+        tc.x0 = x0; tc.y0 = y0; tc.bx0 = bx0; tc.by0 = by0; tc.bw = bw; tc.bh = bh; tc.fits = fits ? 1 : 0;
+        tc.nx = nx; tc.ny = ny; tc.pitch = pitch; tc.I2 = I2;
+      }
+      const int xa1 = x0 - HALO;
+      RowPlan r2; r2.xs = bx0; r2.xe4 = bx0; r2.bytes = 0;
+      if (fits && lane < bh) r2 = plan_row<C>(by0 + lane, bx0, bw, nx, ny, bulk_ok);
+      RowPlan r1; r1.xs = xa1; r1.xe4 = xa1; r1.bytes = 0;
+      if (lane < S1ROWS) r1 = plan_row<C>(y0 - 1 + lane, xa1, S1PX, nx, ny, bulk_ok);
+      unsigned tot = r2.bytes + r1.bytes;
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        if (lane == 0) { fence_proxy_async(); mbar_expect_tx_arrive(bar, tot); }
-        __syncwarp();
-        if (rp.bytes) bulk_g2s(s2 + lane * S2W + (rp.xs - bx0) * C, I2 + (long long)(by0 + lane) * pitch + (long long)rp.xs * C, rp.bytes, bar);
-        if (fits) {
-          const float qnan = __int_as_float(0x7fc00000);         // skimage cval outside the image
-          unsigned need = __ballot_sync(0xffffffffu, lane < bh && (int)(rp.bytes / (4u * C)) != bw);
-          while (need) {
-            const int r = __ffs(need) - 1; need &= need - 1;
-            const int rxs = __shfl_sync(0xffffffffu, rp.xs, r), rxe = __shfl_sync(0xffffffffu, rp.xe4, r);
-            fill_row_rest<C>(s2 + r * S2W, I2, pitch, by0 + r, bx0, bw, nx, ny, rxs, rxe, qnan, lane);
-          }
-        }
-      } else if (warp == 1) {
-        const int xa = x0 - HALO;
-        RowPlan rp; rp.xs = xa; rp.xe4 = xa; rp.bytes = 0;
-        if (lane < S1ROWS) rp = plan_row<C>(y0 - 1 + lane, xa, S1PX, nx, ny, bulk_ok);
-        unsigned tot = rp.bytes;
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        if (lane == 0) { fence_proxy_async(); mbar_expect_tx_arrive(bar, tot); }
-        __syncwarp();
-        if (rp.bytes) bulk_g2s(s1 + lane * S1W + (rp.xs - xa) * C, I1 + (long long)(y0 - 1 + lane) * pitch + (long long)rp.xs * C, rp.bytes, bar);
-        unsigned need = __ballot_sync(0xffffffffu, lane < S1ROWS && (int)(rp.bytes / (4u * C)) != S1PX);
+      for (int o = 16; o >= 1; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      if (lane == 0) { fence_proxy_async(); mbar_expect_tx(bar, tot); }
+      __syncwarp();
+      if (r2.bytes) bulk_g2s(s2 + lane * S2W + (r2.xs - bx0) * C, I2 + (long long)(by0 + lane) * pitch + (long long)r2.xs * C, r2.bytes, bar);
+      if (r1.bytes) bulk_g2s(s1 + lane * S1W + (r1.xs - xa1) * C, I1 + (long long)(y0 - 1 + lane) * pitch + (long long)r1.xs * C, r1.bytes, bar);
+      if (fits) {
+        const float qnan = __int_as_float(0x7fc00000);         // skimage cval outside the image
+        unsigned need = __ballot_sync(0xffffffffu, lane < bh && (int)(r2.bytes / (4u * C)) != bw);
         while (need) {
           const int r = __ffs(need) - 1; need &= need - 1;
-          const int rxs = __shfl_sync(0xffffffffu, rp.xs, r), rxe = __shfl_sync(0xffffffffu, rp.xe4, r);
-          fill_row_rest<C>(s1 + r * S1W, I1, pitch, y0 - 1 + r, xa, S1PX, nx, ny, rxs, rxe, 0.0f, lane);
+          const int rxs = __shfl_sync(0xffffffffu, r2.xs, r), rxe = __shfl_sync(0xffffffffu, r2.xe4, r);
+          fill_row_rest<C>(s2 + r * S2W, I2, pitch, by0 + r, bx0, bw, nx, ny, rxs, rxe, qnan, lane);
         }
       }
-    };
+      {
+        unsigned need = __ballot_sync(0xffffffffu, lane < S1ROWS && (int)(r1.bytes / (4u * C)) != S1PX);
+        while (need) {
+          const int r = __ffs(need) - 1; need &= need - 1;
+          const int rxs = __shfl_sync(0xffffffffu, r1.xs, r), rxe = __shfl_sync(0xffffffffu, r1.xe4, r);
+          fill_row_rest<C>(s1 + r * S1W, I1, pitch, y0 - 1 + r, xa1, S1PX, nx, ny, rxs, rxe, 0.0f, lane);
+        }
+      }
+      __syncwarp();                       // every lane's ordinary stores precede the arrival
+      if (lane == 0) mbar_arrive(bar);    // release; the phase completes when the bulk bytes have landed too
+    }
+  }
+}
 
+// ============================================================ the kernel
+template <int C, int DH>
+__global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterParams P) {
+  constexpr int K = RowVals<DH>::K;
+  constexpr int HW = DH + 1;        // x-powers kept for the Hessian moments
+  constexpr int BWN = DH / 2 + 1;   // x-powers kept for the b moments
+  constexpr int S1W = Stage<C>::S1W;
+  constexpr int S2W = Stage<C>::S2W;
+  constexpr int NENT = K * kYPow;
+  constexpr int SCR = K * SCR_PITCH;                 // floats of transposition scratch per consumer warp
+
+  extern __shared__ __align__(128) float smem[];
+  float* const stage0 = smem;
+  float* const stage1 = smem + Stage<C>::kFloats;
+  float* const scratch = smem + 2 * Stage<C>::kFloats;   // kConsumerWarps * SCR floats
+  __shared__ __align__(8) unsigned long long s_full[2], s_empty[2];
+  __shared__ TileCtl tctl[2];
+  __shared__ double s_pm64[9];
+  __shared__ unsigned int s_ticket;
+  __shared__ int s_piv, s_flag;
+  __shared__ double s_mom[kAccStride];
+  __shared__ double s_aug[ICA_MAX_PARAMS][2 * ICA_MAX_PARAMS + 1];
+  __shared__ double s_vec[2 * ICA_MAX_PARAMS];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int total_chunks = P.chunk_start[P.B];
+  if ((int)blockIdx.x >= total_chunks) return;
+
+  if (tid == 0) {
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+    mbar_init(&s_empty[0], kConsumerWarps); mbar_init(&s_empty[1], kConsumerWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kConsumerWarps) {
+    producer_loop<C>(P, stage0, stage1, s_full, s_empty, tctl, s_pm64, total_chunks, lane);
+    return;
+  }
+
+  // ------------------------------------------------------------------ consumers
+  const int delta = P.delta;
+  const bool frame = P.frame != 0;
+  const bool robust = P.robust_loop != 0;
+  const float chm = P.ch_mult;
+  const int rtype = P.robust_type;
+  float* const sc = scratch + warp * SCR;
+  const int nitems = (total_chunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  unsigned k = 0;
+
+  for (int it = 0; it < nitems; ++it) {
     double acc[kYPow];
 #pragma unroll
     for (int i = 0; i < kYPow; ++i) acc[i] = 0.0;
-
-    issue_tile(t_begin, 0);
-    __syncthreads();   // ordinary stores of the first tile's fill + its StageCtl are visible
-    for (int tile = t_begin; tile < t_end; ++tile) {
-      const int sidx = (tile - t_begin) & 1;
-      if (tile + 1 < t_end) issue_tile(tile + 1, sidx ^ 1);      // overlaps with this tile's arithmetic
-      if (sidx == 0) { mbar_wait(&s_bar[0], phase0); phase0 ^= 1; } else { mbar_wait(&s_bar[1], phase1); phase1 ^= 1; }
+    int pair, chunk, nch, s, nx, ny;
+    bool need_h;
+    bool last;
+    do {
+      const int sidx = k & 1;
+      mbar_wait(&s_full[sidx], (k >> 1) & 1);
+      const TileCtl& tc = tctl[sidx];
       const float* s2 = sidx ? stage1 : stage0;
       const float* s1 = s2 + BH_MAX * S2W;
-      const int x0 = (tile % L.tiles_x) * TW;
-      const int y0 = (tile / L.tiles_x) * TH;
-      const int bx0 = sctl[sidx].bx0, by0 = sctl[sidx].by0, bw = sctl[sidx].bw, bh = sctl[sidx].bh;
-      const bool fits = sctl[sidx].fits != 0;
+      pair = tc.pair; chunk = tc.chunk; nch = tc.nch; s = tc.scale; nx = tc.nx; ny = tc.ny;
+      need_h = tc.need_h != 0; last = tc.last != 0;
+      const WarpCoef coef = tc.coef;
+      const float lo = tc.lo, hi = tc.hi, lambda2 = tc.lambda2;
+      const int x0 = tc.x0, y0 = tc.y0;
+      const int bx0 = tc.bx0, by0 = tc.by0, bw = tc.bw, bh = tc.bh;
+      const bool fits = tc.fits != 0;
+      const int pitch = tc.pitch;
+      const float* I2 = tc.I2;
 
 #pragma unroll 1
-      for (int rr = 0; rr < TH / kWarps; ++rr) {
-        const int ly = warp + rr * kWarps;
+      for (int rr = 0; rr < TH / kConsumerWarps; ++rr) {
+        const int ly = warp + rr * kConsumerWarps;
         const int y = y0 + ly;
-        float v[NP];
+        float v[K];
 #pragma unroll
-        for (int i = 0; i < NP; ++i) v[i] = 0.0f;
+        for (int i = 0; i < K; ++i) v[i] = 0.0f;
         if (y < ny) {
           const bool yin = !frame || (y >= delta && y < ny - delta);
-#pragma unroll
-          for (int half = 0; half < TW / 32; ++half) {
-            const int lx = lane + half * 32;
-            const int x = x0 + lx;
-            if (x >= nx) continue;
-            const bool inframe = yin && (!frame || (x >= delta && x < nx - delta));
-            int cx, cy; float tx, ty;
-            const bool pok = project_px(coef, ctx.m64, x, y, cx, cy, tx, ty);
-            float wx[4], wy[4];
-            keys_weights(tx, wx[0], wx[1], wx[2], wx[3]);
-            keys_weights(ty, wy[0], wy[1], wy[2], wy[3]);
-            const bool insm = fits && (cx - 1 >= bx0) && (cx + 2 < bx0 + bw) && (cy - 1 >= by0) && (cy + 2 < by0 + bh);
-            const float* t2base = s2 + (cy - 1 - by0) * S2W + (cx - 1 - bx0) * C;
-            const float* c1 = s1 + (ly + 1) * S1W + (lx + HALO) * C;
-            const bool gxok = inframe && x >= 1 && x <= nx - 2;
-            const bool gyok = inframe && y >= 1 && y <= ny - 2;
-            float sxx = 0.f, sxy = 0.f, syy = 0.f, vx = 0.f, vy = 0.f, t2 = 0.f;
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-              float iw;
-              if (!pok) {
-                iw = __int_as_float(0x7fc00000);
-              } else if (insm) {
-                float a = 0.0f;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float* r = t2base + q * S2W + ch;
-                  float hsum = wx[0] * r[0] + wx[1] * r[C] + wx[2] * r[2 * C] + wx[3] * r[3 * C];
-                  a = fmaf(wy[q], hsum, a);
-                }
-                iw = a;
-              } else {
-                iw = sample_global<C>(I2, pitch, nx, ny, cx, cy, ch, wx, wy);
-              }
-              const bool valid = iw == iw;               // NaN footprint
-              iw = fminf(fmaxf(iw, lo), hi);             // clip (only used when valid)
-              const float i1c = c1[ch];
-              const float gx = gxok ? 0.5f * (c1[ch + C] - c1[ch - C]) : 0.0f;
-              const float gy = gyok ? 0.5f * (c1[ch + S1W] - c1[ch - S1W]) : 0.0f;
-              const float di = valid ? iw - i1c : 0.0f;  // non-finite -> 0 (io.py:72, 134)
-              if (need_h) { sxx = fmaf(gx, gx, sxx); sxy = fmaf(gx, gy, sxy); syy = fmaf(gy, gy, syy); }
-              vx = fmaf(gx, di, vx); vy = fmaf(gy, di, vy);
-              t2 = fmaf(di, di, t2);
-            }
-            // gray image standing for its x3 replication (SURVEY Q12): every channel sum triples
-            const float rho = robust ? rho_prime(t2 * chm, lambda2, rtype) : 1.0f;
-            const float sc = rho * chm;
-            const float xf = (float)x;
+          const bool gyrow = yin && y >= 1 && y <= ny - 2;
+          // moments of one pixel: v[] += (rho' S, rho' v) * x^a
+          auto add_moments = [&](float scl, float sxx, float sxy, float syy, float vx, float vy, float xf) {
             if (need_h) {
-              float wq[3] = {sc * sxx, sc * sxy, sc * syy};
+              float wq[3] = {scl * sxx, scl * sxy, scl * syy};
 #pragma unroll
               for (int q = 0; q < 3; ++q) {
                 float xp = 1.0f;
@@ -354,19 +349,131 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
                 for (int a = 0; a < HW; ++a) { v[q * HW + a] = fmaf(wq[q], xp, v[q * HW + a]); xp *= xf; }
               }
             }
+            float uq[2] = {scl * vx, scl * vy};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              float xp = 1.0f;
+#pragma unroll
+              for (int a = 0; a < BWN; ++a) { v[3 * HW + q * BWN + a] = fmaf(uq[q], xp, v[3 * HW + q * BWN + a]); xp *= xf; }
+            }
+          };
+          // ---- the lane's two pixels A = (x0+lane, y), B = (x0+32+lane, y): projection and taps
+          const int xA = x0 + lane, xB = xA + 32;
+          int cxA, cyA, cxB, cyB; float txA, tyA, txB, tyB;
+          const bool pokA = project_px(coef, tc.m64, xA, y, cxA, cyA, txA, tyA);
+          const bool pokB = project_px(coef, tc.m64, xB, y, cxB, cyB, txB, tyB);
+          const bool insmA = fits && (cxA - 1 >= bx0) && (cxA + 2 < bx0 + bw) && (cyA - 1 >= by0) && (cyA + 2 < by0 + bh);
+          const bool insmB = fits && (cxB - 1 >= bx0) && (cxB + 2 < bx0 + bw) && (cyB - 1 >= by0) && (cyB + 2 < by0 + bh);
+          const bool fastlane = pokA && pokB && insmA && insmB && xB < nx;
+          if (__all_sync(0xffffffffu, fastlane)) {
+            // ===== straight-line path: both pixels in one instruction stream, packed fp32 (FFMA2)
+            float2 wx[4], wy[4];
             {
-              float uq[2] = {sc * vx, sc * vy};
+              float a0, a1, a2, a3, b0, b1, b2, b3;
+              keys_weights(txA, a0, a1, a2, a3); keys_weights(txB, b0, b1, b2, b3);
+              wx[0] = make_float2(a0, b0); wx[1] = make_float2(a1, b1); wx[2] = make_float2(a2, b2); wx[3] = make_float2(a3, b3);
+              keys_weights(tyA, a0, a1, a2, a3); keys_weights(tyB, b0, b1, b2, b3);
+              wy[0] = make_float2(a0, b0); wy[1] = make_float2(a1, b1); wy[2] = make_float2(a2, b2); wy[3] = make_float2(a3, b3);
+            }
+            const float* tA = s2 + (cyA - 1 - by0) * S2W + (cxA - 1 - bx0) * C;
+            const float* tB = s2 + (cyB - 1 - by0) * S2W + (cxB - 1 - bx0) * C;
+            const float* cA = s1 + (ly + 1) * S1W + (lane + HALO) * C;
+            const float* cB = cA + 32 * C;
+            const bool frA = yin && (!frame || (xA >= delta && xA < nx - delta));
+            const bool frB = yin && (!frame || (xB >= delta && xB < nx - delta));
+            // gradient masks fold the 1/2 of the central difference, the frame and the image border
+            const float2 mgx = make_float2((frA && xA >= 1 && xA <= nx - 2) ? 0.5f : 0.0f, (frB && xB >= 1 && xB <= nx - 2) ? 0.5f : 0.0f);
+            const float2 mgy = make_float2((frA && gyrow) ? 0.5f : 0.0f, (frB && gyrow) ? 0.5f : 0.0f);
+            const float2 nmgx = make_float2(-mgx.x, -mgx.y), nmgy = make_float2(-mgy.x, -mgy.y);
+            float2 sxx = make_float2(0.f, 0.f), sxy = sxx, syy = sxx, vx = sxx, vy = sxx, t2 = sxx;
 #pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                float xp = 1.0f;
+            for (int ch = 0; ch < C; ++ch) {
+              float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int a = 0; a < BWN; ++a) { v[3 * HW + q * BWN + a] = fmaf(uq[q], xp, v[3 * HW + q * BWN + a]); xp *= xf; }
+              for (int q = 0; q < 4; ++q) {
+                const float* rA = tA + q * S2W + ch;
+                const float* rB = tB + q * S2W + ch;
+                float2 h = __fmul2_rn(wx[0], make_float2(rA[0], rB[0]));
+                h = __ffma2_rn(wx[1], make_float2(rA[C], rB[C]), h);
+                h = __ffma2_rn(wx[2], make_float2(rA[2 * C], rB[2 * C]), h);
+                h = __ffma2_rn(wx[3], make_float2(rA[3 * C], rB[3 * C]), h);
+                acc2 = __ffma2_rn(wy[q], h, acc2);
               }
+              const bool vA = acc2.x == acc2.x, vB = acc2.y == acc2.y;   // NaN footprint
+              const float iwA = fminf(fmaxf(acc2.x, lo), hi), iwB = fminf(fmaxf(acc2.y, lo), hi);
+              const float2 gx = __ffma2_rn(make_float2(cA[ch + C], cB[ch + C]), mgx, __fmul2_rn(make_float2(cA[ch - C], cB[ch - C]), nmgx));
+              const float2 gy = __ffma2_rn(make_float2(cA[ch + S1W], cB[ch + S1W]), mgy, __fmul2_rn(make_float2(cA[ch - S1W], cB[ch - S1W]), nmgy));
+              const float2 di = make_float2(vA ? iwA - cA[ch] : 0.0f, vB ? iwB - cB[ch] : 0.0f);   // non-finite -> 0 (io.py:72, 134)
+              if (need_h) { sxx = __ffma2_rn(gx, gx, sxx); sxy = __ffma2_rn(gx, gy, sxy); syy = __ffma2_rn(gy, gy, syy); }
+              vx = __ffma2_rn(gx, di, vx); vy = __ffma2_rn(gy, di, vy);
+              t2 = __ffma2_rn(di, di, t2);
+            }
+            // gray image standing for its x3 replication (SURVEY Q12): every channel sum triples
+            const float rhoA = robust ? rho_prime(t2.x * chm, lambda2, rtype) : 1.0f;
+            const float rhoB = robust ? rho_prime(t2.y * chm, lambda2, rtype) : 1.0f;
+            add_moments(rhoA * chm, sxx.x, sxy.x, syy.x, vx.x, vy.x, (float)xA);
+            add_moments(rhoB * chm, sxx.y, sxy.y, syy.y, vx.y, vy.y, (float)xB);
+          } else {
+            // ===== generic path: image edges, windows that do not fit, degenerate projections
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+              const int x = half ? xB : xA;
+              if (x >= nx) continue;
+              const int lx = lane + half * 32;
+              const int cx = half ? cxB : cxA, cy = half ? cyB : cyA;
+              const bool pok = half ? pokB : pokA, insm = half ? insmB : insmA;
+              float wxs[4], wys[4];
+              keys_weights(half ? txB : txA, wxs[0], wxs[1], wxs[2], wxs[3]);
+              keys_weights(half ? tyB : tyA, wys[0], wys[1], wys[2], wys[3]);
+              const bool inframe = yin && (!frame || (x >= delta && x < nx - delta));
+              const float* t2base = s2 + (cy - 1 - by0) * S2W + (cx - 1 - bx0) * C;
+              const float* c1 = s1 + (ly + 1) * S1W + (lx + HALO) * C;
+              const bool gxok = inframe && x >= 1 && x <= nx - 2;
+              const bool gyok = inframe && y >= 1 && y <= ny - 2;
+              float sxx = 0.f, sxy = 0.f, syy = 0.f, vx = 0.f, vy = 0.f, t2 = 0.f;
+#pragma unroll
+              for (int ch = 0; ch < C; ++ch) {
+                float iw;
+                if (!pok) {
+                  iw = __int_as_float(0x7fc00000);
+                } else if (insm) {
+                  float a = 0.0f;
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float* r = t2base + q * S2W + ch;
+                    float hsum = wxs[0] * r[0] + wxs[1] * r[C] + wxs[2] * r[2 * C] + wxs[3] * r[3 * C];
+                    a = fmaf(wys[q], hsum, a);
+                  }
+                  iw = a;
+                } else {
+                  iw = sample_global_slow<C>(I2, pitch, nx, ny, cx, cy, ch, wxs[0], wxs[1], wxs[2], wxs[3], wys[0], wys[1], wys[2], wys[3]);
+                }
+                const bool valid = iw == iw;               // NaN footprint
+                iw = fminf(fmaxf(iw, lo), hi);             // clip (only used when valid)
+                const float i1c = c1[ch];
+                const float gx = gxok ? 0.5f * (c1[ch + C] - c1[ch - C]) : 0.0f;
+                const float gy = gyok ? 0.5f * (c1[ch + S1W] - c1[ch - S1W]) : 0.0f;
+                const float di = valid ? iw - i1c : 0.0f;  // non-finite -> 0 (io.py:72, 134)
+                if (need_h) { sxx = fmaf(gx, gx, sxx); sxy = fmaf(gx, gy, sxy); syy = fmaf(gy, gy, syy); }
+                vx = fmaf(gx, di, vx); vy = fmaf(gy, di, vy);
+                t2 = fmaf(di, di, t2);
+              }
+              const float rho = robust ? rho_prime(t2 * chm, lambda2, rtype) : 1.0f;
+              add_moments(rho * chm, sxx, sxy, syy, vx, vy, (float)x);
             }
           }
         }
-        // moment k of the row lands on lane (k << log2(32/NP)); fold in y^b in fp64
-        const float tot = warp_transpose_reduce<NP>(v, lane);
+        // transpose through shared memory: moment k of the row lands on lane k (fixed summation order)
+#pragma unroll
+        for (int i = 0; i < K; ++i) sc[i * SCR_PITCH + lane] = v[i];
+        __syncwarp();
+        float tot = 0.0f;
+        if (lane < K) {
+          const float4* r4 = reinterpret_cast<const float4*>(sc + lane * SCR_PITCH);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float4 q4 = r4[j]; tot += q4.x; tot += q4.y; tot += q4.z; tot += q4.w; }
+        }
+        __syncwarp();
         if (y < ny) {
           const double yd = (double)y, t = (double)tot;
           double yp = 1.0;
@@ -374,99 +481,109 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
           for (int b = 0; b < kYPow; ++b) { acc[b] = fma(t, yp, acc[b]); yp *= yd; }
         }
       }
-      __syncthreads();   // stage sidx is free again; fills of the next stage are visible
-    }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sidx]);   // this warp is done with the stage (and its TileCtl)
+      ++k;
+    } while (!last);
 
     // ---------------- chunk partial: [K][kYPow] doubles, warps summed in fixed order
-    double* red = reinterpret_cast<double*>(smem);   // 8 warps * NENT doubles; the stages are idle here
-    constexpr int SH = (NP == 32) ? 0 : (NP == 16 ? 1 : 2);
-    {
-      const int k = lane >> SH;
-      if ((lane & ((1 << SH) - 1)) == 0 && k < K) {
+    double* const myred = reinterpret_cast<double*>(sc);   // this warp's scratch, 105 doubles <= SCR floats * 4
+    if (lane < K) {
 #pragma unroll
-        for (int b = 0; b < kYPow; ++b) red[(warp * K + k) * kYPow + b] = acc[b];
-      }
+      for (int b = 0; b < kYPow; ++b) myred[lane * kYPow + b] = acc[b];
     }
-    __syncthreads();
+    consumer_sync();
     {
       double* out = P.partials + ((long long)pair * P.max_chunks + chunk) * kAccStride;
-      for (int i = tid; i < NENT; i += kThreads) {
+      for (int i = tid; i < NENT; i += kConsumerThreads) {
         double sum = 0.0;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) sum += red[w * NENT + i];
+        for (int w = 0; w < kConsumerWarps; ++w) sum += reinterpret_cast<const double*>(scratch + w * SCR)[i];
         out[i] = sum;
       }
     }
     // ---------------- arrive; the block that delivers the pair's last chunk runs the epilogue
     __threadfence();
-    __syncthreads();
+    consumer_sync();
     if (tid == 0) s_ticket = atomicAdd(&P.state[pair].ticket, 1u);
-    __syncthreads();
-    if (s_ticket != (unsigned)(nch - 1)) continue;   // block-uniform
+    consumer_sync();
+    if (s_ticket != (unsigned)(nch - 1)) continue;   // uniform over the consumers
     __threadfence();
 
     // ================= K3: reduce the chunks, solve, compose, schedule =================
     PairState& st = P.state[pair];
     {
-      // fixed summation order: NG groups of consecutive chunks per entry, groups combined in order
-      constexpr int NG = kThreads / NENT;            // 2 (DH=4), 3 (DH=2), 10 (DH=0)
-      double* part = reinterpret_cast<double*>(smem);
-      const int e = tid % NENT, gI = tid / NENT;
-      if (gI < NG) {
-        const int c0 = (int)((long long)gI * nch / NG), c1 = (int)((long long)(gI + 1) * nch / NG);
-        const double* src = P.partials + (long long)pair * P.max_chunks * kAccStride + e;
-        double sum = 0.0;
-        int c = c0;
-        for (; c + 4 <= c1; c += 4) {
-          const double a0 = __ldcg(src + (long long)(c + 0) * kAccStride), a1 = __ldcg(src + (long long)(c + 1) * kAccStride);
-          const double a2 = __ldcg(src + (long long)(c + 2) * kAccStride), a3 = __ldcg(src + (long long)(c + 3) * kAccStride);
-          sum += a0; sum += a1; sum += a2; sum += a3;
-        }
-        for (; c < c1; ++c) sum += __ldcg(src + (long long)c * kAccStride);
-        part[gI * NENT + e] = sum;
-      }
-      __syncthreads();
-      if (tid < NENT) {
-        double sum = 0.0;
+      // fixed summation order: warp w sums its contiguous range of chunks, then warps in order
+      double* part = reinterpret_cast<double*>(scratch);      // [kConsumerWarps][NENT]
+      const int c0 = (int)((long long)warp * nch / kConsumerWarps), c1 = (int)((long long)(warp + 1) * nch / kConsumerWarps);
+      const double* src = P.partials + (long long)pair * P.max_chunks * kAccStride;
+      constexpr int NJ = (NENT + 31) / 32;
+      double sum[NJ];
 #pragma unroll
-        for (int g2 = 0; g2 < NG; ++g2) sum += part[g2 * NENT + tid];
-        // quadratic loop after the first iteration of a scale: the H moments were not gathered
-        s_mom[tid] = (!need_h && tid < 3 * HW * kYPow) ? 0.0 : sum;
+      for (int j = 0; j < NJ; ++j) sum[j] = 0.0;
+      int c = c0;
+      for (; c + 2 <= c1; c += 2) {
+        double a0[NJ], a1[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int e = lane + 32 * j;
+          a0[j] = e < NENT ? __ldcg(src + (long long)c * kAccStride + e) : 0.0;
+          a1[j] = e < NENT ? __ldcg(src + (long long)(c + 1) * kAccStride + e) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) { sum[j] += a0[j]; sum[j] += a1[j]; }
       }
-      __syncthreads();
+      for (; c < c1; ++c) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) { const int e = lane + 32 * j; if (e < NENT) sum[j] += __ldcg(src + (long long)c * kAccStride + e); }
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { const int e = lane + 32 * j; if (e < NENT) part[warp * NENT + e] = sum[j]; }
+      consumer_sync();
+      if (tid < NENT) {
+        double tsum = 0.0;
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; ++w) tsum += part[w * NENT + tid];
+        // quadratic loop after the first iteration of a scale: the H moments were not gathered
+        s_mom[tid] = (!need_h && tid < 3 * HW * kYPow) ? 0.0 : tsum;
+      }
+      consumer_sync();
     }
     const int ttype = st.ttype;
     const int n = nparams_of(ttype);
     // assemble H (n x n) and b (n) from the moments, one entry per thread (same sums as
     // ica_transform.cuh: assemble_system)
     if (tid < n * n + n) {
-      Mono jx[ICA_MAX_PARAMS], jy[ICA_MAX_PARAMS];
-      jacobian_monomials(ttype, jx, jy);
       constexpr int hw = DH + 1, bwn = DH / 2 + 1, boff = 3 * hw;
       if (tid < n * n) {
-        const int k = tid / n, l = tid % n;
+        const int kk = tid / n, l = tid % n;
+        Mono jxk, jyk, jxl, jyl;
+        mono_of(ttype, kk, jxk, jyk);
+        mono_of(ttype, l, jxl, jyl);
         double sum = 0.0;
-        if (jx[k].coef && jx[l].coef) sum += (double)(jx[k].coef * jx[l].coef) * s_mom[(0 * hw + jx[k].a + jx[l].a) * kYPow + jx[k].b + jx[l].b];
-        if (jx[k].coef && jy[l].coef) sum += (double)(jx[k].coef * jy[l].coef) * s_mom[(1 * hw + jx[k].a + jy[l].a) * kYPow + jx[k].b + jy[l].b];
-        if (jy[k].coef && jx[l].coef) sum += (double)(jy[k].coef * jx[l].coef) * s_mom[(1 * hw + jy[k].a + jx[l].a) * kYPow + jy[k].b + jx[l].b];
-        if (jy[k].coef && jy[l].coef) sum += (double)(jy[k].coef * jy[l].coef) * s_mom[(2 * hw + jy[k].a + jy[l].a) * kYPow + jy[k].b + jy[l].b];
-        s_aug[k][l] = sum;
-        s_aug[k][n + l] = (k == l) ? 1.0 : 0.0;
+        if (jxk.coef && jxl.coef) sum += (double)(jxk.coef * jxl.coef) * s_mom[(0 * hw + jxk.a + jxl.a) * kYPow + jxk.b + jxl.b];
+        if (jxk.coef && jyl.coef) sum += (double)(jxk.coef * jyl.coef) * s_mom[(1 * hw + jxk.a + jyl.a) * kYPow + jxk.b + jyl.b];
+        if (jyk.coef && jxl.coef) sum += (double)(jyk.coef * jxl.coef) * s_mom[(1 * hw + jyk.a + jxl.a) * kYPow + jyk.b + jxl.b];
+        if (jyk.coef && jyl.coef) sum += (double)(jyk.coef * jyl.coef) * s_mom[(2 * hw + jyk.a + jyl.a) * kYPow + jyk.b + jyl.b];
+        s_aug[kk][l] = sum;
+        s_aug[kk][n + l] = (kk == l) ? 1.0 : 0.0;
       } else {
-        const int k = tid - n * n;
+        const int kk = tid - n * n;
+        Mono jxk, jyk;
+        mono_of(ttype, kk, jxk, jyk);
         double sum = 0.0;
-        if (jx[k].coef) sum += (double)jx[k].coef * s_mom[(boff + 0 * bwn + jx[k].a) * kYPow + jx[k].b];
-        if (jy[k].coef) sum += (double)jy[k].coef * s_mom[(boff + 1 * bwn + jy[k].a) * kYPow + jy[k].b];
-        s_vec[k] = sum;
+        if (jxk.coef) sum += (double)jxk.coef * s_mom[(boff + 0 * bwn + jxk.a) * kYPow + jxk.b];
+        if (jyk.coef) sum += (double)jyk.coef * s_mom[(boff + 1 * bwn + jyk.a) * kYPow + jyk.b];
+        s_vec[kk] = sum;
       }
     }
     if (tid == 0) s_flag = 0;
-    __syncthreads();
+    consumer_sync();
     if (P.dbg_Hb) {  // parity hook (ica_hessian_b_host): export, leave the state untouched
       if (tid < n * n) P.dbg_Hb[tid] = s_aug[tid / n][tid % n];
       if (tid < n) P.dbg_Hb[64 + tid] = s_vec[tid];
       if (tid == 0) st.ticket = 0;
-      __syncthreads();
+      consumer_sync();
       continue;
     }
     // de.inverse_hessian: Gauss-Jordan with partial pivoting on [H | I], one thread per entry
@@ -475,42 +592,42 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
     if (need_h) {
       const int i = tid / (2 * ICA_MAX_PARAMS), j = tid % (2 * ICA_MAX_PARAMS);
       const bool act = tid < ICA_MAX_PARAMS * 2 * ICA_MAX_PARAMS && i < n && j < 2 * n;
-      for (int k = 0; k < n; ++k) {
+      for (int kk = 0; kk < n; ++kk) {
         if (tid == 0) {
-          int piv = k; double best = fabs(s_aug[k][k]);
-          for (int r = k + 1; r < n; ++r) { const double vv = fabs(s_aug[r][k]); if (vv > best) { best = vv; piv = r; } }
+          int piv = kk; double best = fabs(s_aug[kk][kk]);
+          for (int r = kk + 1; r < n; ++r) { const double vv = fabs(s_aug[r][kk]); if (vv > best) { best = vv; piv = r; } }
           if (!(best > 0.0)) s_flag = 1;
-          s_chunk = piv;
+          s_piv = piv;
         }
-        __syncthreads();
-        const int piv = s_chunk;
-        if (s_flag) break;                       // block-uniform
-        const bool swp = act && piv != k && (i == k || i == piv);
+        consumer_sync();
+        const int piv = s_piv;
+        if (s_flag) break;                       // uniform
+        const bool swp = act && piv != kk && (i == kk || i == piv);
         double other = 0.0;
-        if (swp) other = s_aug[i == k ? piv : k][j];
-        __syncthreads();
+        if (swp) other = s_aug[i == kk ? piv : kk][j];
+        consumer_sync();
         if (swp) s_aug[i][j] = other;
-        __syncthreads();
-        const double inv = 1.0 / s_aug[k][k];
-        __syncthreads();
-        if (act && i == k) s_aug[k][j] *= inv;
-        __syncthreads();
-        const double f = act ? s_aug[i][k] : 0.0;
-        const double pk = act ? s_aug[k][j] : 0.0;
-        __syncthreads();
-        if (act && i != k && f != 0.0) s_aug[i][j] -= f * pk;
-        __syncthreads();
+        consumer_sync();
+        const double inv = 1.0 / s_aug[kk][kk];
+        consumer_sync();
+        if (act && i == kk) s_aug[kk][j] *= inv;
+        consumer_sync();
+        const double f = act ? s_aug[i][kk] : 0.0;
+        const double pk = act ? s_aug[kk][j] : 0.0;
+        consumer_sync();
+        if (act && i != kk && f != 0.0) s_aug[i][j] -= f * pk;
+        consumer_sync();
       }
-      __syncthreads();
+      consumer_sync();
       if (tid < n * n) st.hinv[tid] = s_flag ? 0.0 : s_aug[tid / n][n + tid % n];
-      __syncthreads();
+      consumer_sync();
     }
     if (tid < n) {                                 // io.parametric_solve (io.py:146-155)
       double a = 0.0;
       for (int j = 0; j < n; ++j) a += st.hinv[tid * n + j] * s_vec[j];
       s_vec[ICA_MAX_PARAMS + tid] = a;
     }
-    __syncthreads();
+    consumer_sync();
     if (tid == 0) {
       double dp[ICA_MAX_PARAMS];
       double e2 = 0.0;
@@ -524,20 +641,20 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
       }
       for (int i = 0; i < n; ++i) st.p_prev[i] = st.p[i];
       update_transform(st.p, dp, ttype);
-      const int it = st.iter + 1;
+      const int itn = st.iter + 1;
       st.err = err;
       st.lambda_it = lam;
       st.total_iters += 1;
       if (P.traj && st.traj_count < P.traj_cap) {
         double* t = P.traj + ((long long)pair * P.traj_cap + st.traj_count) * ICA_TRAJ_STRIDE;
-        t[0] = s; t[1] = it - 1; t[2] = err; t[3] = lam;
+        t[0] = s; t[1] = itn - 1; t[2] = err; t[3] = lam;
         for (int i = 0; i < ICA_MAX_PARAMS; ++i) t[4 + i] = i < n ? st.p[i] : 0.0;
         st.traj_count += 1;
       }
-      if (err > P.tol && it < P.max_iter) {
-        st.iter = it;
+      if (err > P.tol && itn < P.max_iter) {
+        st.iter = itn;
       } else {  // this scale is done (ica.py:109, 225)
-        st.iters_per_scale[s] = it;
+        st.iters_per_scale[s] = itn;
         if (s > 0) {
           double q[ICA_MAX_PARAMS];
           const LevelDesc Lf = P.lv[s - 1];
@@ -552,12 +669,13 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
       }
       st.ticket = 0;
     }
-    __syncthreads();
+    consumer_sync();
   }
 }
 
 // Work list of the next launch: chunk_start[b] = exclusive prefix sum of chunks per pair,
-// chunk_start[B] = total; also publishes the number of unfinished pairs.  One block.
+// chunk_start[B] = total, item_pair[i] = pair of work item i; also publishes the number of
+// unfinished pairs.  One block.
 __global__ void __launch_bounds__(1024) ica_schedule_kernel(const IterParams P) {
   __shared__ int s_warp[32];
   __shared__ int s_carry, s_act;
@@ -587,7 +705,10 @@ __global__ void __launch_bounds__(1024) ica_schedule_kernel(const IterParams P) 
     }
     __syncthreads();
     const int excl = s_carry + s_warp[warp] + incl - c;
-    if (b < B) P.chunk_start[b] = excl;
+    if (b < B) {
+      P.chunk_start[b] = excl;
+      for (int i = 0; i < c; ++i) P.item_pair[excl + i] = b;
+    }
     if (lane == 0 && actmask) atomicAdd(&s_act, __popc(actmask));
     __syncthreads();
     if (tid == 1023) s_carry = excl + c;
@@ -714,11 +835,11 @@ __global__ void ica_gradient_kernel(const float* __restrict__ img, int nx, int n
 }
 
 template <int C, int DH>
-cudaError_t launch_iterate_t(const IterParams& P, int grid, size_t smem, cudaStream_t stream) {
+cudaError_t launch_iterate_t(const IterParams& P, int grid, cudaStream_t stream) {
+  constexpr size_t smem = (2 * (size_t)Stage<C>::kFloats + (size_t)kConsumerWarps * RowVals<DH>::K * SCR_PITCH) * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ica_iterate_kernel<C, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(2 * Stage<C>::kFloats * sizeof(float) + (kSchedCap + 1) * sizeof(int)));
+    cudaError_t e = cudaFuncSetAttribute(ica_iterate_kernel<C, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -737,17 +858,14 @@ cudaError_t launch_schedule(const IterParams& P, cudaStream_t stream) {
 }
 
 cudaError_t launch_iterate(const IterParams& P, int channels, int dh, int grid, cudaStream_t stream) {
-  const int nsched = (P.B <= kSchedCap ? P.B : 0) + 1;
-  const size_t per_stage = (size_t)(channels == 3 ? Stage<3>::kFloats : Stage<1>::kFloats) * sizeof(float);
-  const size_t smem = 2 * per_stage + (size_t)nsched * sizeof(int);
   if (channels == 3) {
-    if (dh == 4) return launch_iterate_t<3, 4>(P, grid, smem, stream);
-    if (dh == 2) return launch_iterate_t<3, 2>(P, grid, smem, stream);
-    return launch_iterate_t<3, 0>(P, grid, smem, stream);
+    if (dh == 4) return launch_iterate_t<3, 4>(P, grid, stream);
+    if (dh == 2) return launch_iterate_t<3, 2>(P, grid, stream);
+    return launch_iterate_t<3, 0>(P, grid, stream);
   }
-  if (dh == 4) return launch_iterate_t<1, 4>(P, grid, smem, stream);
-  if (dh == 2) return launch_iterate_t<1, 2>(P, grid, smem, stream);
-  return launch_iterate_t<1, 0>(P, grid, smem, stream);
+  if (dh == 4) return launch_iterate_t<1, 4>(P, grid, stream);
+  if (dh == 2) return launch_iterate_t<1, 2>(P, grid, stream);
+  return launch_iterate_t<1, 0>(P, grid, stream);
 }
 
 cudaError_t launch_init_state(PairState* state, const double* p_in, const int* ttypes, int B, int nscales,

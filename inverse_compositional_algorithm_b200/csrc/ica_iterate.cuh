@@ -20,6 +20,7 @@ struct IterParams {
   double* dbg_Hb;         // nullptr, or 72 doubles: H (<=64) then b (8); state left untouched
   int* n_active;
   int* chunk_start;       // [B+1] work list of the current launch (ica_schedule_kernel)
+  int* item_pair;         // [B*max_chunks] pair of each work item
   int B;
   int max_chunks;         // partial slots per pair
   int traj_cap;
