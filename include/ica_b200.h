@@ -119,6 +119,10 @@ ICA_API int ica_plan_run_host(ica_plan* plan, const void* I1_host, const void* I
    first host->device copy to the last device->host copy */
 ICA_API int ica_plan_last_host_run_ms(ica_plan* plan, float* ms_out);
 
+/* Profiling hook: per-CTA %globaltimer stamps (16 per CTA) of the LAST iterate launch's first work
+   item; enable != 0 allocates the buffer, host_out (grid*16 int64) receives it; returns the grid size */
+ICA_API int ica_plan_debug_timeline(ica_plan* plan, long long* host_out, int32_t enable);
+
 /* Results of the last run (device -> host copies; synchronises the plan's stream). */
 ICA_API int ica_plan_get_results(ica_plan* plan, double* p_out, double* err_out, int32_t* iters_out);
 /* trajectory of the last run: traj_out[B][nscales*max_iter][ICA_TRAJ_STRIDE], count_out[B] */

@@ -56,6 +56,7 @@ SIGNATURES = {
     "ica_plan_run_device": (C.c_int, [_P, _P, _P, _P, _P]),
     "ica_plan_run_host": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "ica_plan_last_host_run_ms": (C.c_int, [_P, _PF]),
+    "ica_plan_debug_timeline": (C.c_int, [_P, _P, C.c_int32]),
     "ica_plan_get_results": (C.c_int, [_P, _P, _P, _P]),
     "ica_plan_get_trajectory": (C.c_int, [_P, _P, _P]),
     "ica_plan_get_di_iw_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
@@ -367,6 +368,14 @@ class Plan:
         ms = C.c_float()
         check(lib().ica_plan_last_host_run_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def debug_timeline(self, enable=True, fetch=False):
+        grid = lib().ica_plan_debug_timeline(self._h, None, 1 if enable else 0)
+        if not fetch:
+            return None
+        out = np.zeros((grid, 16), dtype=np.int64)
+        lib().ica_plan_debug_timeline(self._h, _ptr(out), 1 if enable else 0)
+        return out
 
     def trajectory(self):
         """List (per pair) of arrays [count][12]: scale, iter, |dp|, lambda, p[8]."""

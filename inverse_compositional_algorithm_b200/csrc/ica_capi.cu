@@ -39,6 +39,7 @@ struct ica_plan {
   int max_chunks = 0, grid = 0;
   int* chunk_start = nullptr;
   int* item_pair = nullptr;
+  long long* dbg_time = nullptr;   // optional per-CTA timeline (ica_plan_debug_timeline)
   LevelDesc lv[ICA_MAX_SCALES];
   long long in_stride = 0, pyr_stride = 0;
   float *pyr1 = nullptr, *pyr2 = nullptr;
@@ -143,6 +144,7 @@ void fill_iter_params(const ica_plan* pl, const float* I1, const float* I2, Iter
   P->state = pl->state; P->mm = pl->mm; P->partials = pl->partials;
   P->traj = (pl->cfg.flags & ICA_FLAG_RECORD_TRAJECTORY) ? pl->traj : nullptr;
   P->dbg_Hb = nullptr;
+  P->dbg_time = pl->dbg_time;
   P->n_active = pl->n_active;
   P->traj_cap = pl->traj_cap;
   P->chunk_start = pl->chunk_start;
@@ -223,7 +225,7 @@ int ica_plan_destroy(ica_plan* pl) {
   if (!pl) return ICA_OK;
   cudaFree(pl->pyr1); cudaFree(pl->pyr2); cudaFree(pl->tmp);
   for (int s = 0; s < ICA_MAX_SCALES; ++s) { free_resample(&pl->ry[s]); free_resample(&pl->rx[s]); }
-  cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->item_pair); cudaFree(pl->traj); cudaFree(pl->n_active);
+  cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->item_pair); cudaFree(pl->dbg_time); cudaFree(pl->traj); cudaFree(pl->n_active);
   if (pl->h_n_active) cudaFreeHost(pl->h_n_active);
   cudaFree(pl->ttypes_dev); cudaFree(pl->p_dev); cudaFree(pl->err_dev); cudaFree(pl->iters_dev);
   cudaFree(pl->in1_dev); cudaFree(pl->in2_dev); cudaFree(pl->raw_dev); cudaFree(pl->DI_dev); cudaFree(pl->Iw_dev);
@@ -480,6 +482,21 @@ int ica_plan_last_host_run_ms(ica_plan* pl, float* ms_out) {
   if (!pl || !ms_out) return ICA_ERR_INVALID;
   ICA_CUDA_CHECK(cudaEventElapsedTime(ms_out, pl->ev_host0, pl->ev_host1));
   return ICA_OK;
+}
+
+int ica_plan_debug_timeline(ica_plan* pl, long long* host_out, int32_t enable) {
+  if (!pl) return ICA_ERR_INVALID;
+  const size_t n = (size_t)pl->grid * 16;
+  if (enable && !pl->dbg_time) {
+    if (int rc = dev_alloc(pl, &pl->dbg_time, n)) return rc;
+    ICA_CUDA_CHECK(cudaMemset(pl->dbg_time, 0, n * sizeof(long long)));
+  }
+  if (host_out && pl->dbg_time) {
+    ICA_CUDA_CHECK(cudaDeviceSynchronize());
+    ICA_CUDA_CHECK(cudaMemcpy(host_out, pl->dbg_time, n * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  if (!enable && pl->dbg_time) { cudaFree(pl->dbg_time); pl->dbg_time = nullptr; }
+  return pl->grid;
 }
 
 int ica_plan_get_results(ica_plan* pl, double* p_out, double* err_out, int32_t* iters_out) {

@@ -68,7 +68,9 @@ struct TileCtl {
   int x0, y0;
   int bx0, by0, bw, bh, fits;
   int nx, ny, pitch;
+  int fill, bulk_ok;
   const float* I2;
+  const float* I1;
 };
 
 // ---------------------------------------------------------------- mbarrier / bulk-copy PTX
@@ -96,13 +98,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define ICA_STAMP(slot) do { if (P.dbg_time && it == 0 && tid == 0) P.dbg_time[blockIdx.x * 16 + (slot)] = gtime(); } while (0)
 // barrier among the consumer threads only (the producer warp never joins it)
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
 
 // One image-row segment [xa, xa+w) of row yy: the part that lies inside the image and whose
 // byte range is a multiple of 16 goes through a bulk copy ([xs, xe4), `bytes`); the rest
 // (out-of-image pixels, a ragged right end, or everything when bulk copies are not possible)
-// is filled by fill_row_rest with ordinary loads/stores.
+// is written by fill_window.
 struct RowPlan { int xs, xe4; unsigned bytes; };
 
 template <int C>
@@ -116,21 +120,38 @@ __device__ __forceinline__ RowPlan plan_row(int yy, int xa, int w, int nx, int n
   return r;
 }
 
+// Everything of a staged window [xa, xa+w) x [ya, ya+h) that the bulk copies do not deliver: rows and
+// column strips outside the image get `fill` (plain independent stores, no loads); pixels inside
+// the image but outside the 16-byte-aligned bulk range (a ragged right end when nx % 4 != 0, or the
+// whole row when bulk copies are impossible) are copied with ordinary loads.  Called by the consumer
+// warps (rows are dealt round-robin to the `nw` warps) for tiles the producer flagged.
 template <int C>
-__device__ __forceinline__ void fill_row_rest(float* dst, const float* __restrict__ img, int pitch, int yy, int xa,
-                                              int w, int nx, int ny, int xs, int xe4, float fill, int lane) {
-  const bool rowin = yy >= 0 && yy < ny;
-  const float* src = img + (long long)yy * pitch + (long long)xa * C;
-  const int left = (xs - xa) * C;            // floats before the bulk part
-  const int right0 = (xe4 - xa) * C;         // first float after it
-  const int total = w * C;
-  for (int i = lane; i < left; i += 32) {
-    const int xx = xa + i / C;
-    dst[i] = (rowin && xx >= 0 && xx < nx) ? __ldg(src + i) : fill;
+__device__ __forceinline__ void fill_window(float* sbase, int SW, const float* __restrict__ img, int pitch, int xa,
+                                            int w, int ya, int h, int nx, int ny, float fill, bool bulk_ok, int lane,
+                                            int warp, int nw) {
+  const int wf = w * C;
+  const int r0 = min(h, max(0, -ya));          // first in-image row of the window
+  const int r1 = max(r0, min(h, ny - ya));     // one past the last in-image row
+  for (int r = warp; r < h; r += nw) {
+    if (r >= r0 && r < r1) continue;
+    for (int i = lane; i < wf; i += 32) sbase[r * SW + i] = fill;
   }
-  for (int i = right0 + lane; i < total; i += 32) {
-    const int xx = xa + i / C;
-    dst[i] = (rowin && xx >= 0 && xx < nx) ? __ldg(src + i) : fill;
+  const int xs = max(xa, 0), xe = max(xs, min(xa + w, nx));
+  const int left = min(wf, (xs - xa) * C);     // floats left of the image
+  const int right0 = (xe - xa) * C;            // first float right of the image
+  if (left > 0 || right0 < wf) {
+    for (int r = r0 + warp; r < r1; r += nw) {
+      for (int i = lane; i < left; i += 32) sbase[r * SW + i] = fill;
+      for (int i = right0 + lane; i < wf; i += 32) sbase[r * SW + i] = fill;
+    }
+  }
+  const int xe4 = xs + ((xe - xs) & ~3);
+  const int rem0 = ((bulk_ok ? xe4 : xs) - xa) * C;
+  if (rem0 < right0) {
+    for (int r = r0 + warp; r < r1; r += nw) {
+      const float* src = img + (long long)(ya + r) * pitch + (long long)xa * C;
+      for (int i = rem0 + lane; i < right0; i += 32) sbase[r * SW + i] = __ldg(src + i);
+    }
   }
 }
 
@@ -183,6 +204,7 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
     const int t_begin = (int)((long long)chunk * ntiles / nch);
     const int t_end = (int)((long long)(chunk + 1) * ntiles / nch);
 
+    if (P.dbg_time && k == 0 && lane == 0) P.dbg_time[blockIdx.x * 16 + 9] = gtime();
     for (int tile = t_begin; tile < t_end; ++tile, ++k) {
       const int sidx = k & 1;
       const unsigned use = k >> 1;
@@ -210,13 +232,18 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
       const int by0 = mny - 2;
       const int bh = mxy + 3 - by0 + 1;
       const bool fits = okall && bw <= BW_MAX && bh <= BH_MAX && bw > 0 && bh > 0;
+      const int xa1_ = x0 - HALO;
       if (lane < 9) tc.m64[lane] = pm64[lane];
       if (lane == 0) {
         tc.coef = coef; tc.lo = lo; tc.hi = hi; tc.lambda2 = lambda2;
         tc.pair = pair; tc.chunk = chunk; tc.nch = nch; tc.scale = s;
         tc.need_h = need_h; tc.first = tile == t_begin; tc.last = tile + 1 == t_end;
         tc.x0 = x0; tc.y0 = y0; tc.bx0 = bx0; tc.by0 = by0; tc.bw = bw; tc.bh = bh; tc.fits = fits ? 1 : 0;
-        tc.nx = nx; tc.ny = ny; tc.pitch = pitch; tc.I2 = I2;
+        tc.nx = nx; tc.ny = ny; tc.pitch = pitch; tc.I2 = I2; tc.I1 = I1; tc.bulk_ok = bulk_ok ? 1 : 0;
+        // anything the bulk copies cannot deliver (image borders, ragged ends) is filled by the consumers
+        const bool in2 = !fits || (bx0 >= 0 && bx0 + bw <= nx && by0 >= 0 && by0 + bh <= ny);
+        const bool in1 = xa1_ >= 0 && xa1_ + S1PX <= nx && y0 - 1 >= 0 && y0 - 1 + S1ROWS <= ny;
+        tc.fill = (bulk_ok && in1 && in2) ? 0 : 1;
       }
       const int xa1 = x0 - HALO;
       RowPlan r2; r2.xs = bx0; r2.xe4 = bx0; r2.bytes = 0;
@@ -228,25 +255,11 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
       for (int o = 16; o >= 1; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
       if (lane == 0) { fence_proxy_async(); mbar_expect_tx(bar, tot); }
       __syncwarp();
+      if (P.dbg_time && k == 0 && lane == 0) P.dbg_time[blockIdx.x * 16 + 10] = gtime();
       if (r2.bytes) bulk_g2s(s2 + lane * S2W + (r2.xs - bx0) * C, I2 + (long long)(by0 + lane) * pitch + (long long)r2.xs * C, r2.bytes, bar);
       if (r1.bytes) bulk_g2s(s1 + lane * S1W + (r1.xs - xa1) * C, I1 + (long long)(y0 - 1 + lane) * pitch + (long long)r1.xs * C, r1.bytes, bar);
-      if (fits) {
-        const float qnan = __int_as_float(0x7fc00000);         // skimage cval outside the image
-        unsigned need = __ballot_sync(0xffffffffu, lane < bh && (int)(r2.bytes / (4u * C)) != bw);
-        while (need) {
-          const int r = __ffs(need) - 1; need &= need - 1;
-          const int rxs = __shfl_sync(0xffffffffu, r2.xs, r), rxe = __shfl_sync(0xffffffffu, r2.xe4, r);
-          fill_row_rest<C>(s2 + r * S2W, I2, pitch, by0 + r, bx0, bw, nx, ny, rxs, rxe, qnan, lane);
-        }
-      }
-      {
-        unsigned need = __ballot_sync(0xffffffffu, lane < S1ROWS && (int)(r1.bytes / (4u * C)) != S1PX);
-        while (need) {
-          const int r = __ffs(need) - 1; need &= need - 1;
-          const int rxs = __shfl_sync(0xffffffffu, r1.xs, r), rxe = __shfl_sync(0xffffffffu, r1.xe4, r);
-          fill_row_rest<C>(s1 + r * S1W, I1, pitch, y0 - 1 + r, xa1, S1PX, nx, ny, rxs, rxe, 0.0f, lane);
-        }
-      }
+      if (P.dbg_time && k == 0 && lane == 0) P.dbg_time[blockIdx.x * 16 + 11] = gtime();
+      if (P.dbg_time && k == 0 && lane == 0) P.dbg_time[blockIdx.x * 16 + 12] = gtime();
       __syncwarp();                       // every lane's ordinary stores precede the arrival
       if (lane == 0) mbar_arrive(bar);    // release; the phase completes when the bulk bytes have landed too
     }
@@ -272,7 +285,6 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
   __shared__ TileCtl tctl[2];
   __shared__ double s_pm64[9];
   __shared__ unsigned int s_ticket;
-  __shared__ int s_piv, s_flag;
   __shared__ double s_mom[kAccStride];
   __shared__ double s_aug[ICA_MAX_PARAMS][2 * ICA_MAX_PARAMS + 1];
   __shared__ double s_vec[2 * ICA_MAX_PARAMS];
@@ -305,6 +317,7 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
   const int nitems = (total_chunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   unsigned k = 0;
 
+  if (P.dbg_time && tid == 0) P.dbg_time[blockIdx.x * 16 + 0] = gtime();
   for (int it = 0; it < nitems; ++it) {
     double acc[kYPow];
 #pragma unroll
@@ -315,6 +328,7 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
     do {
       const int sidx = k & 1;
       mbar_wait(&s_full[sidx], (k >> 1) & 1);
+      if (k == 0) ICA_STAMP(1);
       const TileCtl& tc = tctl[sidx];
       const float* s2 = sidx ? stage1 : stage0;
       const float* s1 = s2 + BH_MAX * S2W;
@@ -327,6 +341,15 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
       const bool fits = tc.fits != 0;
       const int pitch = tc.pitch;
       const float* I2 = tc.I2;
+      if (tc.fill) {   // uniform over the consumers: border tile
+        float* w2 = sidx ? stage1 : stage0;
+        float* w1 = w2 + BH_MAX * S2W;
+        if (fits) fill_window<C>(w2, S2W, I2, pitch, bx0, bw, by0, bh, nx, ny, __int_as_float(0x7fc00000) /* skimage cval */,
+                                 tc.bulk_ok != 0, lane, warp, kConsumerWarps);
+        fill_window<C>(w1, S1W, tc.I1, pitch, x0 - HALO, S1PX, y0 - 1, S1ROWS, nx, ny, 0.0f, tc.bulk_ok != 0, lane, warp,
+                       kConsumerWarps);
+        consumer_sync();
+      }
 
 #pragma unroll 1
       for (int rr = 0; rr < TH / kConsumerWarps; ++rr) {
@@ -485,6 +508,7 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
       if (lane == 0) mbar_arrive(&s_empty[sidx]);   // this warp is done with the stage (and its TileCtl)
       ++k;
     } while (!last);
+    ICA_STAMP(2);
 
     // ---------------- chunk partial: [K][kYPow] doubles, warps summed in fixed order
     double* const myred = reinterpret_cast<double*>(sc);   // this warp's scratch, 105 doubles <= SCR floats * 4
@@ -505,8 +529,10 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
     // ---------------- arrive; the block that delivers the pair's last chunk runs the epilogue
     __threadfence();
     consumer_sync();
+    ICA_STAMP(3);
     if (tid == 0) s_ticket = atomicAdd(&P.state[pair].ticket, 1u);
     consumer_sync();
+    ICA_STAMP(4);
     if (s_ticket != (unsigned)(nch - 1)) continue;   // uniform over the consumers
     __threadfence();
 
@@ -518,20 +544,24 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
       const int c0 = (int)((long long)warp * nch / kConsumerWarps), c1 = (int)((long long)(warp + 1) * nch / kConsumerWarps);
       const double* src = P.partials + (long long)pair * P.max_chunks * kAccStride;
       constexpr int NJ = (NENT + 31) / 32;
+      constexpr int UN = 4;                                    // chunks in flight per lane
       double sum[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) sum[j] = 0.0;
       int c = c0;
-      for (; c + 2 <= c1; c += 2) {
-        double a0[NJ], a1[NJ];
+      for (; c + UN <= c1; c += UN) {
+        double a[UN][NJ];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          const int e = lane + 32 * j;
-          a0[j] = e < NENT ? __ldcg(src + (long long)c * kAccStride + e) : 0.0;
-          a1[j] = e < NENT ? __ldcg(src + (long long)(c + 1) * kAccStride + e) : 0.0;
-        }
+        for (int u = 0; u < UN; ++u)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) { sum[j] += a0[j]; sum[j] += a1[j]; }
+          for (int j = 0; j < NJ; ++j) {
+            const int e = lane + 32 * j;
+            a[u][j] = e < NENT ? __ldcg(src + (long long)(c + u) * kAccStride + e) : 0.0;
+          }
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) sum[j] += a[u][j];
       }
       for (; c < c1; ++c) {
 #pragma unroll
@@ -549,14 +579,16 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
       }
       consumer_sync();
     }
+    ICA_STAMP(5);
+    // The n x n part is warp 0's job; the other consumer warps go on with the CTA's next chunk.
+    if (warp != 0) continue;
     const int ttype = st.ttype;
     const int n = nparams_of(ttype);
-    // assemble H (n x n) and b (n) from the moments, one entry per thread (same sums as
-    // ica_transform.cuh: assemble_system)
-    if (tid < n * n + n) {
+    // assemble H (n x n) and b (n) from the moments (same sums as ica_transform.cuh: assemble_system)
+    for (int e = lane; e < n * n + n; e += 32) {
       constexpr int hw = DH + 1, bwn = DH / 2 + 1, boff = 3 * hw;
-      if (tid < n * n) {
-        const int kk = tid / n, l = tid % n;
+      if (e < n * n) {
+        const int kk = e / n, l = e % n;
         Mono jxk, jyk, jxl, jyl;
         mono_of(ttype, kk, jxk, jyk);
         mono_of(ttype, l, jxl, jyl);
@@ -568,7 +600,7 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
         s_aug[kk][l] = sum;
         s_aug[kk][n + l] = (kk == l) ? 1.0 : 0.0;
       } else {
-        const int kk = tid - n * n;
+        const int kk = e - n * n;
         Mono jxk, jyk;
         mono_of(ttype, kk, jxk, jyk);
         double sum = 0.0;
@@ -577,58 +609,69 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
         s_vec[kk] = sum;
       }
     }
-    if (tid == 0) s_flag = 0;
-    consumer_sync();
+    __syncwarp();
+    ICA_STAMP(6);
     if (P.dbg_Hb) {  // parity hook (ica_hessian_b_host): export, leave the state untouched
-      if (tid < n * n) P.dbg_Hb[tid] = s_aug[tid / n][tid % n];
-      if (tid < n) P.dbg_Hb[64 + tid] = s_vec[tid];
-      if (tid == 0) st.ticket = 0;
-      consumer_sync();
+      for (int e = lane; e < n * n; e += 32) P.dbg_Hb[e] = s_aug[e / n][e % n];
+      if (lane < n) P.dbg_Hb[64 + lane] = s_vec[lane];
+      if (lane == 0) st.ticket = 0;
       continue;
     }
-    // de.inverse_hessian: Gauss-Jordan with partial pivoting on [H | I], one thread per entry
-    // (element by element the arithmetic of ica_transform.cuh: inverse_hessian); zero matrix when
-    // a pivot is exactly zero (np.linalg.LinAlgError branch, derivatives.py:127-129)
+    // de.inverse_hessian: Gauss-Jordan with partial pivoting on [H | I] in shared memory, 4 entries
+    // per lane (element by element the arithmetic of ica_transform.cuh: inverse_hessian); zero matrix
+    // when a pivot is exactly zero (np.linalg.LinAlgError branch, derivatives.py:127-129)
     if (need_h) {
-      const int i = tid / (2 * ICA_MAX_PARAMS), j = tid % (2 * ICA_MAX_PARAMS);
-      const bool act = tid < ICA_MAX_PARAMS * 2 * ICA_MAX_PARAMS && i < n && j < 2 * n;
+      bool singular = false;
       for (int kk = 0; kk < n; ++kk) {
-        if (tid == 0) {
-          int piv = kk; double best = fabs(s_aug[kk][kk]);
+        int piv = kk;
+        {
+          double best = fabs(s_aug[kk][kk]);
           for (int r = kk + 1; r < n; ++r) { const double vv = fabs(s_aug[r][kk]); if (vv > best) { best = vv; piv = r; } }
-          if (!(best > 0.0)) s_flag = 1;
-          s_piv = piv;
+          if (!(best > 0.0)) singular = true;          // every lane computes the same thing
         }
-        consumer_sync();
-        const int piv = s_piv;
-        if (s_flag) break;                       // uniform
-        const bool swp = act && piv != kk && (i == kk || i == piv);
-        double other = 0.0;
-        if (swp) other = s_aug[i == kk ? piv : kk][j];
-        consumer_sync();
-        if (swp) s_aug[i][j] = other;
-        consumer_sync();
+        if (singular) break;
+        if (piv != kk) {
+          double t0 = 0.0, t1 = 0.0;
+          if (lane < 2 * n) { t0 = s_aug[kk][lane]; t1 = s_aug[piv][lane]; }
+          __syncwarp();
+          if (lane < 2 * n) { s_aug[kk][lane] = t1; s_aug[piv][lane] = t0; }
+          __syncwarp();
+        }
         const double inv = 1.0 / s_aug[kk][kk];
-        consumer_sync();
-        if (act && i == kk) s_aug[kk][j] *= inv;
-        consumer_sync();
-        const double f = act ? s_aug[i][kk] : 0.0;
-        const double pk = act ? s_aug[kk][j] : 0.0;
-        consumer_sync();
-        if (act && i != kk && f != 0.0) s_aug[i][j] -= f * pk;
-        consumer_sync();
+        __syncwarp();
+        if (lane < 2 * n) s_aug[kk][lane] *= inv;
+        __syncwarp();
+        double f[4], pk[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int e = lane + 32 * m, i = e >> 4, j = e & 15;
+          const bool act = i < n && j < 2 * n;
+          f[m] = act ? s_aug[i][kk] : 0.0;
+          pk[m] = act ? s_aug[kk][j] : 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int e = lane + 32 * m, i = e >> 4, j = e & 15;
+          if (i < n && j < 2 * n && i != kk && f[m] != 0.0) s_aug[i][j] -= f[m] * pk[m];
+        }
+        __syncwarp();
       }
-      consumer_sync();
-      if (tid < n * n) st.hinv[tid] = s_flag ? 0.0 : s_aug[tid / n][n + tid % n];
-      consumer_sync();
+      for (int e = lane; e < n * n; e += 32) {
+        const double hv = singular ? 0.0 : s_aug[e / n][n + e % n];
+        s_aug[e / n][n + e % n] = hv;
+        st.hinv[e] = hv;                               // kept for the quadratic loop's later iterations
+      }
+      __syncwarp();
     }
-    if (tid < n) {                                 // io.parametric_solve (io.py:146-155)
+    ICA_STAMP(7);
+    if (lane < n) {                                    // io.parametric_solve (io.py:146-155)
       double a = 0.0;
-      for (int j = 0; j < n; ++j) a += st.hinv[tid * n + j] * s_vec[j];
-      s_vec[ICA_MAX_PARAMS + tid] = a;
+      for (int j = 0; j < n; ++j) a += (need_h ? s_aug[lane][n + j] : st.hinv[lane * n + j]) * s_vec[j];
+      s_vec[ICA_MAX_PARAMS + lane] = a;
     }
-    consumer_sync();
-    if (tid == 0) {
+    __syncwarp();
+    if (lane == 0) {
       double dp[ICA_MAX_PARAMS];
       double e2 = 0.0;
       for (int i = 0; i < n; ++i) { dp[i] = s_vec[ICA_MAX_PARAMS + i]; e2 += dp[i] * dp[i]; }
@@ -669,7 +712,8 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
       }
       st.ticket = 0;
     }
-    consumer_sync();
+    __syncwarp();
+    ICA_STAMP(8);
   }
 }
 

@@ -1,0 +1,30 @@
+"""Per-CTA timeline of one iterate launch (profiling hook).  Runs a 1-pair registration limited
+to a given number of launches so that the last launch is the one of interest."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from inverse_compositional_algorithm_b200 import _native, synthetic
+from inverse_compositional_algorithm_b200.transformation import TransformType
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+nscales = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+H = W = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+max_iter = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+t = TransformType.HOMOGRAPHY
+pairs = [synthetic.make_pair(i, H, W, 3, t, max_shift=1.0) for i in range(min(B, 2))]
+I1 = np.stack([pairs[i % len(pairs)][0] for i in range(B)]); I2 = np.stack([pairs[i % len(pairs)][1] for i in range(B)])
+plan = _native.Plan(batch=B, height=H, width=W, channels=3, nscales=nscales, nu=0.5, transform_type=t.value,
+                    robust_type=3, robust_loop=True, lambda_=0.0, tol=1e-9, max_iter=max_iter, delta=10, nanifoutside=True)
+plan.debug_timeline(True)
+plan.run_host(I1, I2)
+plan.run_host(I1, I2)
+tl = plan.debug_timeline(True, fetch=True)
+act = tl[tl[:, 0] > 0]
+t0 = act[:, 0].min()
+names = ["start", "first_tile_ready", "tiles_done", "partial_written", "ticket", "sums_done", "assembled", "gj_done", "end", "P:decoded", "P:planned", "P:issued", "P:filled"]
+print("CTAs with work:", len(act))
+for i, nm in enumerate(names):
+    col = act[:, i]
+    col = col[col > 0]
+    if len(col):
+        print(f"{nm:18s} n={len(col):4d}  min={(col.min()-t0)/1e3:8.2f} us  median={(np.median(col)-t0)/1e3:8.2f}  max={(col.max()-t0)/1e3:8.2f}")
