@@ -91,6 +91,7 @@ int dev_alloc(ica_plan* pl, T** ptr, size_t count) {
 
 int upload_resample(ica_plan* pl, const Resample1D& r, DeviceResample* d) {
   d->n_in = r.n_in; d->n_out = r.n_out; d->taps = r.taps;
+  detect_uniform_rows(r, &d->fast);
   int rc;
   if ((rc = dev_alloc(pl, &d->start, r.start.size()))) return rc;
   if ((rc = dev_alloc(pl, &d->weights, r.weights.size()))) return rc;
@@ -183,13 +184,14 @@ int build_pyramids(ica_plan* pl, const float* I1, const float* I2, cudaStream_t 
                                   : pyr[which] + (long long)b0 * pl->pyr_stride + Li.offset;
         const long long istr = s == 0 ? pl->in_stride : pl->pyr_stride;
         float* out0 = pyr[which] + (long long)b0 * pl->pyr_stride + Lo.offset;
+        int nl = 0;
         if (pl->timing && pl->n_ev_pyr + 2 <= (int)pl->ev_pyr.size()) cudaEventRecord(pl->ev_pyr[pl->n_ev_pyr++], stream);
         ICA_LAUNCH_CHECK(launch_pyr_down(in0, istr, Li.pitch, Li.nx, Li.ny, pl->C, pl->ry[s], pl->rx[s], pl->tmp,
                                          pl->tmp_stride, out0, pl->pyr_stride, Lo.pitch, nimg,
                                          pl->mm + ((long long)b0 * ns + s) * 2 + which, ns * 2,
-                                         pl->mm + ((long long)b0 * ns + s + 1) * 2 + which, ns * 2, stream));
+                                         pl->mm + ((long long)b0 * ns + s + 1) * 2 + which, ns * 2, stream, &nl));
         if (pl->timing && pl->n_ev_pyr + 1 <= (int)pl->ev_pyr.size()) cudaEventRecord(pl->ev_pyr[pl->n_ev_pyr++], stream);
-        pl->launches += 2;
+        pl->launches += nl;
       }
     }
   }
@@ -267,7 +269,8 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   pl->pyr_stride = off;
   const int nt0 = pl->lv[0].tiles_x * pl->lv[0].tiles_y;
   // chunks (= partial slots) per pair: enough for one straggler pair to cover the whole chip
-  int mc = cfg->blocks_per_pair > 0 ? cfg->blocks_per_pair : (pl->B <= 4 ? 1024 : 256);
+  // (independent of the batch size, so a pair's result does not depend on what it is batched with)
+  int mc = cfg->blocks_per_pair > 0 ? cfg->blocks_per_pair : (nt0 > 16384 ? 1024 : 256);
   pl->max_chunks = std::max(1, std::min(mc, nt0));
   {
     int dev = 0, sms = 148;

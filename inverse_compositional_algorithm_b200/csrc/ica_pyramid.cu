@@ -121,26 +121,69 @@ void build_resample_1d(int n_in, int n_out, Resample1D* out, double rel_threshol
   }
 }
 
+// Rows of a banded operator whose weights are identical up to a shift of 2 samples per output
+// (exact 2:1 levels away from the borders): start[o] = 2*o + s0 and the same `taps` weights.
+void detect_uniform_rows(const Resample1D& r, FastRows* f) {
+  f->lo = f->hi = 0; f->s0 = 0; f->taps = 0;
+  if (r.n_out < 16 || r.taps > kFastTapsMax) return;
+  const int mid = r.n_out / 2;
+  const int s0 = r.start[mid] - 2 * mid;
+  const float* wm = &r.weights[(size_t)mid * r.taps];
+  float mx = 0.f;
+  for (int k = 0; k < r.taps; ++k) mx = std::max(mx, fabsf(wm[k]));
+  auto same = [&](int o) {
+    if (r.start[o] != 2 * o + s0) return false;
+    const float* w = &r.weights[(size_t)o * r.taps];
+    for (int k = 0; k < r.taps; ++k) if (fabsf(w[k] - wm[k]) > 2e-8f * mx) return false;
+    return true;
+  };
+  int lo = mid, hi = mid + 1;
+  while (lo > 0 && same(lo - 1)) --lo;
+  while (hi < r.n_out && same(hi)) ++hi;
+  if (hi - lo < 8) return;
+  f->lo = lo; f->hi = hi; f->s0 = s0; f->taps = r.taps;
+  for (int k = 0; k < kFastTapsMax; ++k) f->w[k] = k < r.taps ? wm[k] : 0.f;
+}
+
 namespace {
 
 constexpr int kVR = 4;        // output rows per thread in the vertical pass
 constexpr int kMaxTaps = 64;
+constexpr int kFR = 4;        // outputs per thread along the filtered axis in the uniform (fast) kernels
 
-// ---- vertical pass: tmp[oy][j] = sum_k Wy[oy][k] * in[sy[oy]+k][j],  j over nx*C floats
+struct FastW { float w[kFastTapsMax]; };
+
+// logical index of the general kernels -> output index, skipping the range [lo, hi) the fast kernel covers
+__device__ __forceinline__ int skip_range(int i, int lo, int hi) { return i < lo ? i : i + (hi - lo); }
+
+// ---- vertical pass, general rows: tmp[oy][j] = sum_k Wy[oy][k] * in[sy[oy]+k][j],  j over nx*C floats
 __global__ void __launch_bounds__(256) pyr_vertical_kernel(
-    const float* __restrict__ in0, long long in_stride, int in_pitch, int ncols, int ny_out,
+    const float* __restrict__ in0, long long in_stride, int in_pitch, int ncols, int ny_out, int skip_lo, int skip_hi,
     const float* __restrict__ W, const int* __restrict__ start, int taps,
     float* __restrict__ tmp, long long tmp_stride) {
   __shared__ float sw[kVR][kMaxTaps];
-  __shared__ int sst[kVR];
+  __shared__ int sst[kVR], soy[kVR];
   const int img = blockIdx.z;
-  const int oy0 = blockIdx.y * kVR;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  // row groups never straddle the range [skip_lo, skip_hi) the fast kernel covers
+  const int gA = (skip_lo + kVR - 1) / kVR;
+  if (threadIdx.x < kVR) {
+    int oy;
+    if ((int)blockIdx.y < gA) { oy = blockIdx.y * kVR + threadIdx.x; if (oy >= skip_lo) oy = -1; }
+    else { oy = skip_hi + ((int)blockIdx.y - gA) * kVR + threadIdx.x; if (oy >= ny_out) oy = -1; }
+    soy[threadIdx.x] = oy;
+  }
+  __syncthreads();
+  if (threadIdx.x < kVR) {
+    int oy = soy[threadIdx.x];
+    if (oy < 0) oy = soy[0];     // inactive slots reuse the group's first row (always valid) for the loop bounds
+    sst[threadIdx.x] = start[oy];
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < kVR * taps; i += blockDim.x) {
     const int r = i / taps, k = i % taps;
-    sw[r][k] = (oy0 + r < ny_out) ? W[(long long)(oy0 + r) * taps + k] : 0.f;
+    sw[r][k] = soy[r] >= 0 ? W[(long long)soy[r] * taps + k] : 0.f;
   }
-  if (threadIdx.x < kVR) sst[threadIdx.x] = start[min(oy0 + threadIdx.x, ny_out - 1)];
   __syncthreads();
   if (j >= ncols) return;
   int row_lo = sst[0], row_hi = sst[0] + taps;
@@ -160,34 +203,44 @@ __global__ void __launch_bounds__(256) pyr_vertical_kernel(
   }
   float* o = tmp + (long long)img * tmp_stride + j;
 #pragma unroll
-  for (int r = 0; r < kVR; ++r) if (oy0 + r < ny_out) o[(long long)(oy0 + r) * ncols] = acc[r];
+  for (int r = 0; r < kVR; ++r) if (soy[r] >= 0) o[(long long)soy[r] * ncols] = acc[r];
 }
 
-// ---- horizontal pass + clip to the parent's range + min/max of the new level
-template <int C>
-__global__ void __launch_bounds__(256) pyr_horizontal_kernel(
-    const float* __restrict__ tmp, long long tmp_stride, int ncols_in, int nx_out, int ny_out,
-    const float* __restrict__ Wt /* [taps][nx_out] */, const int* __restrict__ start, int taps,
-    float* __restrict__ out0, long long out_stride, int out_pitch,
-    const MinMaxKeys* __restrict__ mm_parent, int mm_parent_stride,
-    MinMaxKeys* __restrict__ mm_child, int mm_child_stride) {
+// ---- vertical pass, uniform rows (exact 2:1, interior): 4 float columns x kFR output rows per
+// thread, every input row loaded once per thread (LDG.128), weights as constant-bank operands.
+template <int TP>
+__global__ void __launch_bounds__(128) pyr_vertical_fast_kernel(
+    const float* __restrict__ in0, long long in_stride, int in_pitch, int ncols4, int oy_lo, int ngroups, int s0,
+    const FastW fw, float* __restrict__ tmp, long long tmp_stride, int tmp_pitch) {
   const int img = blockIdx.z;
-  const int oy = blockIdx.y;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;   // flat ox*C + c
-  const MinMaxKeys pk = mm_parent[(long long)img * mm_parent_stride];
-  const float lo = key_float(pk.lo), hi = key_float(pk.hi);
-  float val = 0.f;
-  const bool active = e < nx_out * C;
-  if (active) {
-    const int ox = e / C, c = e - ox * C;
-    const float* row = tmp + (long long)img * tmp_stride + (long long)oy * ncols_in + c;
-    const int st = __ldg(start + ox);
-    float acc = 0.f;
-    for (int k = 0; k < taps; ++k) acc = fmaf(__ldg(Wt + (long long)k * nx_out + ox), __ldg(row + (st + k) * C), acc);
-    val = fminf(fmaxf(acc, lo), hi);
-    out0[(long long)img * out_stride + (long long)oy * out_pitch + e] = val;
+  const int j4 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j4 >= ncols4 || (int)blockIdx.y >= ngroups) return;
+  const int oy = oy_lo + blockIdx.y * kFR;
+  const float4* in = reinterpret_cast<const float4*>(in0 + (long long)img * in_stride + (long long)(2 * oy + s0) * in_pitch) + j4;
+  const int p4 = in_pitch >> 2;
+  float4 acc[kFR];
+#pragma unroll
+  for (int r = 0; r < kFR; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < TP + 2 * (kFR - 1); ++j) {
+    const float4 v = __ldg(in + (long long)j * p4);
+#pragma unroll
+    for (int r = 0; r < kFR; ++r) {
+      const int k = j - 2 * r;
+      if (k >= 0 && k < TP) {
+        const float w = fw.w[k];
+        acc[r].x = fmaf(w, v.x, acc[r].x); acc[r].y = fmaf(w, v.y, acc[r].y);
+        acc[r].z = fmaf(w, v.z, acc[r].z); acc[r].w = fmaf(w, v.w, acc[r].w);
+      }
+    }
   }
-  // block min/max -> order-preserving keys -> one atomic pair per block
+  float4* o = reinterpret_cast<float4*>(tmp + (long long)img * tmp_stride + (long long)oy * tmp_pitch) + j4;
+  const int t4 = tmp_pitch >> 2;
+#pragma unroll
+  for (int r = 0; r < kFR; ++r) o[(long long)r * t4] = acc[r];
+}
+
+__device__ __forceinline__ void block_minmax_atomic(float val, bool active, MinMaxKeys* ck) {
   unsigned kmin = active ? float_key(val) : 0xffffffffu;
   unsigned kmax = active ? float_key(val) : 0u;
 #pragma unroll
@@ -200,10 +253,97 @@ __global__ void __launch_bounds__(256) pyr_horizontal_kernel(
   if (lane == 0) { smin[warp] = kmin; smax[warp] = kmax; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { kmin = min(kmin, smin[w]); kmax = max(kmax, smax[w]); }
-    MinMaxKeys* ck = mm_child + (long long)img * mm_child_stride;
-    atomicMin(&ck->lo, kmin);
-    atomicMax(&ck->hi, kmax);
+    for (int w = 1; w < (int)((blockDim.x + 31) >> 5); ++w) { kmin = min(kmin, smin[w]); kmax = max(kmax, smax[w]); }
+    if (kmin <= kmax) { atomicMin(&ck->lo, kmin); atomicMax(&ck->hi, kmax); }
+  }
+}
+
+// ---- horizontal pass (general columns) + clip to the parent's range + min/max of the new level
+template <int C>
+__global__ void __launch_bounds__(256) pyr_horizontal_kernel(
+    const float* __restrict__ tmp, long long tmp_stride, int ncols_in, int nx_out, int ny_out, int skip_lo, int skip_hi,
+    const float* __restrict__ Wt /* [taps][nx_out] */, const int* __restrict__ start, int taps,
+    float* __restrict__ out0, long long out_stride, int out_pitch,
+    const MinMaxKeys* __restrict__ mm_parent, int mm_parent_stride,
+    MinMaxKeys* __restrict__ mm_child, int mm_child_stride) {
+  const int img = blockIdx.z;
+  const int oy = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;   // logical flat index over the general columns
+  const int ncol = nx_out - (skip_hi - skip_lo);
+  const MinMaxKeys pk = mm_parent[(long long)img * mm_parent_stride];
+  const float lo = key_float(pk.lo), hi = key_float(pk.hi);
+  float val = 0.f;
+  const bool active = e < ncol * C;
+  if (active) {
+    const int oxl = e / C, c = e - oxl * C;
+    const int ox = skip_range(oxl, skip_lo, skip_hi);
+    const float* row = tmp + (long long)img * tmp_stride + (long long)oy * ncols_in + c;
+    const int st = __ldg(start + ox);
+    float acc = 0.f;
+    for (int k = 0; k < taps; ++k) acc = fmaf(__ldg(Wt + (long long)k * nx_out + ox), __ldg(row + (st + k) * C), acc);
+    val = fminf(fmaxf(acc, lo), hi);
+    out0[(long long)img * out_stride + (long long)oy * out_pitch + ox * C + c] = val;
+  }
+  block_minmax_atomic(val, active, mm_child + (long long)img * mm_child_stride);
+}
+
+// ---- horizontal pass, uniform columns: kFR consecutive outputs per thread, inputs loaded once
+template <int C, int TP>
+__global__ void __launch_bounds__(128) pyr_horizontal_fast_kernel(
+    const float* __restrict__ tmp, long long tmp_stride, int ncols_in, int ox_lo, int ngroups, int s0, const FastW fw,
+    float* __restrict__ out0, long long out_stride, int out_pitch,
+    const MinMaxKeys* __restrict__ mm_parent, int mm_parent_stride,
+    MinMaxKeys* __restrict__ mm_child, int mm_child_stride) {
+  const int img = blockIdx.z;
+  const int oy = blockIdx.y;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;   // (group of kFR columns) * C + channel
+  const MinMaxKeys pk = mm_parent[(long long)img * mm_parent_stride];
+  const float lo = key_float(pk.lo), hi = key_float(pk.hi);
+  const bool active = g < ngroups * C;
+  float vmin = 0.f, vmax = 0.f;
+  if (active) {
+    const int og = g / C, c = g - og * C;
+    const int ox = ox_lo + og * kFR;
+    const float* row = tmp + (long long)img * tmp_stride + (long long)oy * ncols_in + (long long)(2 * ox + s0) * C + c;
+    float acc[kFR];
+#pragma unroll
+    for (int r = 0; r < kFR; ++r) acc[r] = 0.f;
+#pragma unroll
+    for (int j = 0; j < TP + 2 * (kFR - 1); ++j) {
+      const float v = __ldg(row + j * C);
+#pragma unroll
+      for (int r = 0; r < kFR; ++r) {
+        const int k = j - 2 * r;
+        if (k >= 0 && k < TP) acc[r] = fmaf(fw.w[k], v, acc[r]);
+      }
+    }
+    float* o = out0 + (long long)img * out_stride + (long long)oy * out_pitch + ox * C + c;
+    vmin = 3.4e38f; vmax = -3.4e38f;
+#pragma unroll
+    for (int r = 0; r < kFR; ++r) {
+      const float val = fminf(fmaxf(acc[r], lo), hi);
+      o[r * C] = val;
+      vmin = fminf(vmin, val); vmax = fmaxf(vmax, val);
+    }
+  }
+  // two-sided reduction: feed min and max through the same helper
+  {
+    unsigned kmin = active ? float_key(vmin) : 0xffffffffu;
+    unsigned kmax = active ? float_key(vmax) : 0u;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+      kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    __shared__ unsigned smin[4], smax[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { smin[warp] = kmin; smax[warp] = kmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { kmin = min(kmin, smin[w]); kmax = max(kmax, smax[w]); }
+      MinMaxKeys* ck = mm_child + (long long)img * mm_child_stride;
+      if (kmin <= kmax) { atomicMin(&ck->lo, kmin); atomicMax(&ck->hi, kmax); }
+    }
   }
 }
 
@@ -260,33 +400,102 @@ cudaError_t launch_minmax(const float* img0, long long stride, long long count, 
   return cudaGetLastError();
 }
 
+// Groups of kFR outputs of the uniform range whose (zero-padded) TP-tap footprint stays inside [0, n_in):
+// the padding taps have weight 0, but 0 * (whatever lies past the data) must never be formed.
+static void fast_groups(const FastRows& f, int n_in, int TP, int* lo, int* ngroups) {
+  int l = f.lo;
+  while (2 * l + f.s0 < 0) ++l;
+  const int omax = (n_in - f.s0 - TP - 2 * (kFR - 1)) / 2;   // last admissible group base
+  int ng = 0;
+  if (f.hi - l >= kFR && omax >= l) ng = std::min((f.hi - l) / kFR, (omax - l) / kFR + 1);
+  *lo = l; *ngroups = std::max(ng, 0);
+}
+
+template <int TP>
+static void launch_vfast(const float* in0, long long in_stride, int in_pitch, int ncols, const FastRows& f, int lo, int ngroups,
+                         float* tmp, long long tmp_stride, int nimg, cudaStream_t stream) {
+  FastW fw;
+  for (int k = 0; k < kFastTapsMax; ++k) fw.w[k] = f.w[k];
+  const int ncols4 = ncols / 4;
+  dim3 grid((ncols4 + 127) / 128, ngroups, nimg);
+  pyr_vertical_fast_kernel<TP><<<grid, 128, 0, stream>>>(in0, in_stride, in_pitch, ncols4, lo, ngroups, f.s0, fw, tmp,
+                                                          tmp_stride, ncols);
+}
+
+template <int C, int TP>
+static void launch_hfast(const float* tmp, long long tmp_stride, int ncols, const FastRows& f, int lo, int ngroups, int ny_out,
+                         float* out0, long long out_stride, int out_pitch, int nimg, const MinMaxKeys* mm_parent,
+                         int mm_parent_stride, MinMaxKeys* mm_child, int mm_child_stride, cudaStream_t stream) {
+  FastW fw;
+  for (int k = 0; k < kFastTapsMax; ++k) fw.w[k] = f.w[k];
+  dim3 grid((ngroups * C + 127) / 128, ny_out, nimg);
+  pyr_horizontal_fast_kernel<C, TP><<<grid, 128, 0, stream>>>(tmp, tmp_stride, ncols, lo, ngroups, f.s0, fw, out0, out_stride,
+                                                               out_pitch, mm_parent, mm_parent_stride, mm_child,
+                                                               mm_child_stride);
+}
+
 cudaError_t launch_pyr_down(const float* in0, long long in_stride, int in_pitch, int nx_in, int ny_in, int channels,
                             const DeviceResample& ry, const DeviceResample& rx, float* tmp, long long tmp_stride,
                             float* out0, long long out_stride, int out_pitch, int nimg,
                             const MinMaxKeys* mm_parent, int mm_parent_stride, MinMaxKeys* mm_child,
-                            int mm_child_stride, cudaStream_t stream) {
+                            int mm_child_stride, cudaStream_t stream, int* launches) {
   const int ncols = nx_in * channels;
   const int ny_out = ry.n_out, nx_out = rx.n_out;
-  {
-    dim3 grid((ncols + 255) / 256, (ny_out + kVR - 1) / kVR, nimg);
-    pyr_vertical_kernel<<<grid, 256, 0, stream>>>(in0, in_stride, in_pitch, ncols, ny_out, ry.weights, ry.start,
-                                                   ry.taps, tmp, tmp_stride);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+  int nl = 0;
+  // ---- vertical pass: uniform interior rows through the fast kernel (needs 16-byte rows), the rest general
+  int vlo = 0, vhi = 0;
+  const bool valign = (ncols % 4 == 0) && (in_pitch % 4 == 0) && (in_stride % 4 == 0) &&
+                      ((reinterpret_cast<unsigned long long>(in0) | reinterpret_cast<unsigned long long>(tmp)) & 15ull) == 0 &&
+                      (tmp_stride % 4 == 0);
+  if (valign && ry.fast.hi - ry.fast.lo >= kFR) {
+    const int TP = ry.fast.taps <= 32 ? 32 : kFastTapsMax;
+    int lo = 0, ngroups = 0;
+    fast_groups(ry.fast, ny_in, TP, &lo, &ngroups);
+    if (ngroups > 0) {
+      vlo = lo; vhi = vlo + ngroups * kFR;
+      if (TP == 32) launch_vfast<32>(in0, in_stride, in_pitch, ncols, ry.fast, lo, ngroups, tmp, tmp_stride, nimg, stream);
+      else launch_vfast<kFastTapsMax>(in0, in_stride, in_pitch, ncols, ry.fast, lo, ngroups, tmp, tmp_stride, nimg, stream);
+      ++nl;
+    }
   }
-  {
-    const int ne = nx_out * channels;
+  if (ny_out - (vhi - vlo) > 0) {
+    dim3 grid((ncols + 255) / 256, (vlo + kVR - 1) / kVR + (ny_out - vhi + kVR - 1) / kVR, nimg);
+    pyr_vertical_kernel<<<grid, 256, 0, stream>>>(in0, in_stride, in_pitch, ncols, ny_out, vlo, vhi, ry.weights, ry.start,
+                                                   ry.taps, tmp, tmp_stride);
+    ++nl;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  // ---- horizontal pass
+  int hlo = 0, hhi = 0;
+  if (rx.fast.hi - rx.fast.lo >= kFR) {
+    const int TP = rx.fast.taps <= 32 ? 32 : kFastTapsMax;
+    int lo = 0, ngroups = 0;
+    fast_groups(rx.fast, nx_in, TP, &lo, &ngroups);
+    if (ngroups > 0) {
+      hlo = lo; hhi = hlo + ngroups * kFR;
+#define ICA_HF(CC, TT) launch_hfast<CC, TT>(tmp, tmp_stride, ncols, rx.fast, lo, ngroups, ny_out, out0, out_stride, out_pitch, nimg, mm_parent, mm_parent_stride, mm_child, mm_child_stride, stream)
+      if (channels == 3) { if (TP == 32) ICA_HF(3, 32); else ICA_HF(3, kFastTapsMax); }
+      else { if (TP == 32) ICA_HF(1, 32); else ICA_HF(1, kFastTapsMax); }
+#undef ICA_HF
+      ++nl;
+    }
+  }
+  if (nx_out - (hhi - hlo) > 0) {
+    const int ne = (nx_out - (hhi - hlo)) * channels;
     const int threads = ne >= 256 ? 256 : ((ne + 31) / 32) * 32;
     dim3 grid((ne + threads - 1) / threads, ny_out, nimg);
     if (channels == 3)
-      pyr_horizontal_kernel<3><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, ny_out, rx.weights_t,
+      pyr_horizontal_kernel<3><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, ny_out, hlo, hhi, rx.weights_t,
                                                               rx.start, rx.taps, out0, out_stride, out_pitch, mm_parent,
                                                               mm_parent_stride, mm_child, mm_child_stride);
     else
-      pyr_horizontal_kernel<1><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, ny_out, rx.weights_t,
+      pyr_horizontal_kernel<1><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, ny_out, hlo, hhi, rx.weights_t,
                                                               rx.start, rx.taps, out0, out_stride, out_pitch, mm_parent,
                                                               mm_parent_stride, mm_child, mm_child_stride);
+    ++nl;
   }
+  if (launches) *launches = nl;
   return cudaGetLastError();
 }
 

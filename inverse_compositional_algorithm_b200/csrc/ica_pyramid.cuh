@@ -12,17 +12,23 @@ struct Resample1D {
   std::vector<float> weights;
 };
 
+constexpr int kFastTapsMax = 40;
+// Output rows [lo, hi) of an operator that share one weight vector: start[o] = 2*o + s0 (exact 2:1 interior)
+struct FastRows { int lo = 0, hi = 0, s0 = 0, taps = 0; float w[kFastTapsMax] = {0}; };
+
 // The same operator on the device; weights_t is the [taps][n_out] transpose for the horizontal pass
 struct DeviceResample {
   int n_in = 0, n_out = 0, taps = 0;
   int* start = nullptr;
   float* weights = nullptr;
   float* weights_t = nullptr;
+  FastRows fast;
 };
 
 int round_half_even(double v);
 int zoomed_size(int n, double factor);   // src/zoom.py:8-22
 void build_resample_1d(int n_in, int n_out, Resample1D* out, double rel_threshold = 1e-9);
+void detect_uniform_rows(const Resample1D& r, FastRows* f);
 int max_taps();
 
 cudaError_t launch_minmax_reset(MinMaxKeys* mm, int count, cudaStream_t stream);
@@ -33,7 +39,7 @@ cudaError_t launch_pyr_down(const float* in0, long long in_stride, int in_pitch,
                             const DeviceResample& ry, const DeviceResample& rx, float* tmp, long long tmp_stride,
                             float* out0, long long out_stride, int out_pitch, int nimg,
                             const MinMaxKeys* mm_parent, int mm_parent_stride, MinMaxKeys* mm_child,
-                            int mm_child_stride, cudaStream_t stream);
+                            int mm_child_stride, cudaStream_t stream, int* launches = nullptr);
 cudaError_t launch_convert_u8(const unsigned char* in, float* out, long long n, cudaStream_t stream);
 cudaError_t launch_convert_f64(const double* in, float* out, long long n, cudaStream_t stream);
 
