@@ -39,6 +39,7 @@ struct ica_plan {
   int max_chunks = 0, grid = 0;
   int* chunk_start = nullptr;
   int* item_pair = nullptr;
+  unsigned int* solve_ticket = nullptr;
   long long* dbg_time = nullptr;   // optional per-CTA timeline (ica_plan_debug_timeline)
   LevelDesc lv[ICA_MAX_SCALES];
   long long in_stride = 0, pyr_stride = 0;
@@ -150,6 +151,7 @@ void fill_iter_params(const ica_plan* pl, const float* I1, const float* I2, Iter
   P->traj_cap = pl->traj_cap;
   P->chunk_start = pl->chunk_start;
   P->item_pair = pl->item_pair;
+  P->solve_ticket = pl->solve_ticket;
   P->B = pl->B;
   P->max_chunks = pl->max_chunks;
   P->robust_type = pl->cfg.robust_type;
@@ -227,7 +229,7 @@ int ica_plan_destroy(ica_plan* pl) {
   if (!pl) return ICA_OK;
   cudaFree(pl->pyr1); cudaFree(pl->pyr2); cudaFree(pl->tmp);
   for (int s = 0; s < ICA_MAX_SCALES; ++s) { free_resample(&pl->ry[s]); free_resample(&pl->rx[s]); }
-  cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->item_pair); cudaFree(pl->dbg_time); cudaFree(pl->traj); cudaFree(pl->n_active);
+  cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->item_pair); cudaFree(pl->solve_ticket); cudaFree(pl->dbg_time); cudaFree(pl->traj); cudaFree(pl->n_active);
   if (pl->h_n_active) cudaFreeHost(pl->h_n_active);
   cudaFree(pl->ttypes_dev); cudaFree(pl->p_dev); cudaFree(pl->err_dev); cudaFree(pl->iters_dev);
   cudaFree(pl->in1_dev); cudaFree(pl->in2_dev); cudaFree(pl->raw_dev); cudaFree(pl->DI_dev); cudaFree(pl->Iw_dev);
@@ -276,7 +278,7 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    pl->grid = 2 * sms;   // persistent: 2 CTAs per SM (register- and shared-memory-limited)
+    pl->grid = iterate_blocks_per_sm() * sms;   // persistent kernel: every CTA resident
   }
   int rc = ICA_OK;
 #define TRY(expr) do { if ((rc = (expr)) != ICA_OK) { ica_plan_destroy(pl); return rc; } } while (0)
@@ -303,6 +305,8 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   TRY(dev_alloc(pl, &pl->partials, (size_t)pl->B * pl->max_chunks * kAccStride));
   TRY(dev_alloc(pl, &pl->chunk_start, (size_t)pl->B + 1));
   TRY(dev_alloc(pl, &pl->item_pair, (size_t)pl->B * pl->max_chunks));
+  TRY(dev_alloc(pl, &pl->solve_ticket, 1));
+  TRY_CUDA(cudaMemset(pl->solve_ticket, 0, sizeof(unsigned int)));
   pl->traj_cap = pl->nscales * cfg->max_iter;
   if (cfg->flags & ICA_FLAG_RECORD_TRAJECTORY) TRY(dev_alloc(pl, &pl->traj, (size_t)pl->B * pl->traj_cap * ICA_TRAJ_STRIDE));
   TRY(dev_alloc(pl, &pl->n_active, 1));
@@ -401,15 +405,17 @@ int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* 
   int done = 0;
   // a pair needs at least one launch per scale, so the first poll can wait that long
   int next_poll = std::max(pl->nscales, poll_every);
+  ICA_LAUNCH_CHECK(launch_schedule(P, stream));   // work list of the first iteration
+  pl->launches += 1;
   for (int it = 0; it < max_launches && !done; ++it) {
     const bool timed = pl->timing && pl->n_ev_iter + 2 <= (int)pl->ev_iter.size();
-    ICA_LAUNCH_CHECK(launch_schedule(P, stream));   // work list + number of unfinished pairs
     if (timed) cudaEventRecord(pl->ev_iter[pl->n_ev_iter++], stream);
     ICA_LAUNCH_CHECK(launch_iterate(P, pl->C, pl->dh, pl->grid, stream));
     if (timed) cudaEventRecord(pl->ev_iter[pl->n_ev_iter++], stream);
+    // per-pair solve / compose; its last block publishes the next work list and the number of unfinished pairs
+    ICA_LAUNCH_CHECK(launch_solve(P, pl->dh, stream));
     pl->launches += 2;
     if (it + 1 >= next_poll && it + 1 < max_launches) {
-      // n_active was written by the schedule kernel of THIS iteration: 0 means the launch above was empty
       ICA_CUDA_CHECK(cudaMemcpyAsync(pl->h_n_active, pl->n_active, sizeof(int), cudaMemcpyDeviceToHost, stream));
       ICA_CUDA_CHECK(cudaStreamSynchronize(stream));
       if (*pl->h_n_active <= 0) done = 1;
@@ -683,6 +689,7 @@ int ica_hessian_b_host(const float* I1, const float* I2, int32_t height, int32_t
     P.dbg_Hb = d_dbg;
     if (e == cudaSuccess) e = launch_schedule(P, 0);
     if (e == cudaSuccess) e = launch_iterate(P, channels, pl->dh, pl->grid, 0);
+    if (e == cudaSuccess) e = launch_solve(P, pl->dh, 0);
     double hb[72];
     if (e == cudaSuccess) e = cudaMemcpy(hb, d_dbg, sizeof(hb), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { set_error("ica_hessian_b_host: %s", cudaGetErrorString(e)); rc = ICA_ERR_CUDA; }

@@ -36,6 +36,7 @@ namespace ica {
 
 namespace {
 
+constexpr int kBlocksPerSM = 2;      // 2 CTAs x 8 warps per SM at 128 registers per thread
 constexpr int kConsumerWarps = 7;    // + 1 producer warp = 8 warps: warps are allocated in groups of 4
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = kConsumerThreads + 32;   // + one producer warp
@@ -46,7 +47,7 @@ constexpr int S1PX = TW + 2 * HALO;
 constexpr int S1ROWS = TH + 2;
 constexpr int BW_MAX = 96;        // staged I2 window; 96*C floats per row == 0 (mod 32 banks): lanes of a
                                   // warp that sit on different window rows never collide
-constexpr int BH_MAX = 26;        // larger windows (strong rotation / zoom) take the global-memory path
+constexpr int BH_MAX = 24;        // larger windows (strong rotation / zoom) take the global-memory path
 constexpr int SCR_PITCH = 36;     // floats per row of the per-warp transposition scratch
 
 template <int DH> struct RowVals { static constexpr int K = 3 * (DH + 1) + 2 * (DH / 2 + 1); };
@@ -268,7 +269,7 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
 
 // ============================================================ the kernel
 template <int C, int DH>
-__global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterParams P) {
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(const IterParams P) {
   constexpr int K = RowVals<DH>::K;
   constexpr int HW = DH + 1;        // x-powers kept for the Hessian moments
   constexpr int BWN = DH / 2 + 1;   // x-powers kept for the b moments
@@ -284,10 +285,6 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
   __shared__ __align__(8) unsigned long long s_full[2], s_empty[2];
   __shared__ TileCtl tctl[2];
   __shared__ double s_pm64[9];
-  __shared__ unsigned int s_ticket;
-  __shared__ double s_mom[kAccStride];
-  __shared__ double s_aug[ICA_MAX_PARAMS][2 * ICA_MAX_PARAMS + 1];
-  __shared__ double s_vec[2 * ICA_MAX_PARAMS];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -314,14 +311,17 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
   const float chm = P.ch_mult;
   const int rtype = P.robust_type;
   float* const sc = scratch + warp * SCR;
+  double* const accs = reinterpret_cast<double*>(scratch + kConsumerWarps * SCR);   // [kConsumerWarps][K][kYPow]
+  double* const myacc = accs + (warp * K + (lane < K ? lane : 0)) * kYPow;
   const int nitems = (total_chunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   unsigned k = 0;
 
   if (P.dbg_time && tid == 0) P.dbg_time[blockIdx.x * 16 + 0] = gtime();
   for (int it = 0; it < nitems; ++it) {
-    double acc[kYPow];
+    if (lane < K) {
 #pragma unroll
-    for (int i = 0; i < kYPow; ++i) acc[i] = 0.0;
+      for (int b = 0; b < kYPow; ++b) myacc[b] = 0.0;
+    }
     int pair, chunk, nch, s, nx, ny;
     bool need_h;
     bool last;
@@ -329,41 +329,36 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
       const int sidx = k & 1;
       mbar_wait(&s_full[sidx], (k >> 1) & 1);
       if (k == 0) ICA_STAMP(1);
-      const TileCtl& tc = tctl[sidx];
+      // Tile constants stay in shared memory and are re-read (volatile) where they are used: the
+      // register file is the scarce resource of this kernel, it must hold the tap loads in flight.
+      const volatile TileCtl* tcv = &tctl[sidx];
       const float* s2 = sidx ? stage1 : stage0;
       const float* s1 = s2 + BH_MAX * S2W;
-      pair = tc.pair; chunk = tc.chunk; nch = tc.nch; s = tc.scale; nx = tc.nx; ny = tc.ny;
-      need_h = tc.need_h != 0; last = tc.last != 0;
-      const WarpCoef coef = tc.coef;
-      const float lo = tc.lo, hi = tc.hi, lambda2 = tc.lambda2;
-      const int x0 = tc.x0, y0 = tc.y0;
-      const int bx0 = tc.bx0, by0 = tc.by0, bw = tc.bw, bh = tc.bh;
-      const bool fits = tc.fits != 0;
-      const int pitch = tc.pitch;
-      const float* I2 = tc.I2;
-      if (tc.fill) {   // uniform over the consumers: border tile
+      if (tcv->fill) {   // uniform over the consumers: border tile
+        const TileCtl& tc = tctl[sidx];
         float* w2 = sidx ? stage1 : stage0;
         float* w1 = w2 + BH_MAX * S2W;
-        if (fits) fill_window<C>(w2, S2W, I2, pitch, bx0, bw, by0, bh, nx, ny, __int_as_float(0x7fc00000) /* skimage cval */,
-                                 tc.bulk_ok != 0, lane, warp, kConsumerWarps);
-        fill_window<C>(w1, S1W, tc.I1, pitch, x0 - HALO, S1PX, y0 - 1, S1ROWS, nx, ny, 0.0f, tc.bulk_ok != 0, lane, warp,
-                       kConsumerWarps);
+        if (tc.fits) fill_window<C>(w2, S2W, tc.I2, tc.pitch, tc.bx0, tc.bw, tc.by0, tc.bh, tc.nx, tc.ny,
+                                    __int_as_float(0x7fc00000) /* skimage cval */, tc.bulk_ok != 0, lane, warp, kConsumerWarps);
+        fill_window<C>(w1, S1W, tc.I1, tc.pitch, tc.x0 - HALO, S1PX, tc.y0 - 1, S1ROWS, tc.nx, tc.ny, 0.0f, tc.bulk_ok != 0,
+                       lane, warp, kConsumerWarps);
         consumer_sync();
       }
 
 #pragma unroll 1
       for (int rr = 0; rr < TH / kConsumerWarps; ++rr) {
         const int ly = warp + rr * kConsumerWarps;
-        const int y = y0 + ly;
+        const int y = tcv->y0 + ly;
+        const int ny = tcv->ny;
         float v[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) v[i] = 0.0f;
         if (y < ny) {
-          const bool yin = !frame || (y >= delta && y < ny - delta);
-          const bool gyrow = yin && y >= 1 && y <= ny - 2;
+          const int nx = tcv->nx;
+          const bool need_hr = tcv->need_h != 0;
           // moments of one pixel: v[] += (rho' S, rho' v) * x^a
           auto add_moments = [&](float scl, float sxx, float sxy, float syy, float vx, float vy, float xf) {
-            if (need_h) {
+            if (need_hr) {
               float wq[3] = {scl * sxx, scl * sxy, scl * syy};
 #pragma unroll
               for (int q = 0; q < 3; ++q) {
@@ -380,64 +375,93 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
               for (int a = 0; a < BWN; ++a) { v[3 * HW + q * BWN + a] = fmaf(uq[q], xp, v[3 * HW + q * BWN + a]); xp *= xf; }
             }
           };
-          // ---- the lane's two pixels A = (x0+lane, y), B = (x0+32+lane, y): projection and taps
-          const int xA = x0 + lane, xB = xA + 32;
+          // ---- the lane's two pixels A = (x0+lane, y), B = (x0+32+lane, y): projection
+          const int xA = tcv->x0 + lane, xB = xA + 32;
           int cxA, cyA, cxB, cyB; float txA, tyA, txB, tyB;
-          const bool pokA = project_px(coef, tc.m64, xA, y, cxA, cyA, txA, tyA);
-          const bool pokB = project_px(coef, tc.m64, xB, y, cxB, cyB, txB, tyB);
-          const bool insmA = fits && (cxA - 1 >= bx0) && (cxA + 2 < bx0 + bw) && (cyA - 1 >= by0) && (cyA + 2 < by0 + bh);
-          const bool insmB = fits && (cxB - 1 >= bx0) && (cxB + 2 < bx0 + bw) && (cyB - 1 >= by0) && (cyB + 2 < by0 + bh);
+          bool pokA, pokB;
+          {
+            WarpCoef coef;
+            coef.d00 = tcv->coef.d00; coef.m01 = tcv->coef.m01; coef.m02 = tcv->coef.m02; coef.m10 = tcv->coef.m10;
+            coef.d11 = tcv->coef.d11; coef.m12 = tcv->coef.m12; coef.m20 = tcv->coef.m20; coef.m21 = tcv->coef.m21;
+            pokA = project_px(coef, tctl[sidx].m64, xA, y, cxA, cyA, txA, tyA);
+            pokB = project_px(coef, tctl[sidx].m64, xB, y, cxB, cyB, txB, tyB);
+          }
+          bool insmA, insmB;
+          int offA, offB;    // float offsets of the first tap inside the staged I2 window
+          {
+            const int bx0 = tcv->bx0, by0 = tcv->by0, bw = tcv->bw, bh = tcv->bh;
+            const bool fits = tcv->fits != 0;
+            insmA = fits && (cxA - 1 >= bx0) && (cxA + 2 < bx0 + bw) && (cyA - 1 >= by0) && (cyA + 2 < by0 + bh);
+            insmB = fits && (cxB - 1 >= bx0) && (cxB + 2 < bx0 + bw) && (cyB - 1 >= by0) && (cyB + 2 < by0 + bh);
+            offA = (cyA - 1 - by0) * S2W + (cxA - 1 - bx0) * C;
+            offB = (cyB - 1 - by0) * S2W + (cxB - 1 - bx0) * C;
+          }
           const bool fastlane = pokA && pokB && insmA && insmB && xB < nx;
           if (__all_sync(0xffffffffu, fastlane)) {
             // ===== straight-line path: both pixels in one instruction stream, packed fp32 (FFMA2)
-            float2 wx[4], wy[4];
+            // phase 1: the 2 x 16 taps of every channel -> warped values (few live registers besides the loads)
+            float2 iw[C];
             {
-              float a0, a1, a2, a3, b0, b1, b2, b3;
-              keys_weights(txA, a0, a1, a2, a3); keys_weights(txB, b0, b1, b2, b3);
-              wx[0] = make_float2(a0, b0); wx[1] = make_float2(a1, b1); wx[2] = make_float2(a2, b2); wx[3] = make_float2(a3, b3);
-              keys_weights(tyA, a0, a1, a2, a3); keys_weights(tyB, b0, b1, b2, b3);
-              wy[0] = make_float2(a0, b0); wy[1] = make_float2(a1, b1); wy[2] = make_float2(a2, b2); wy[3] = make_float2(a3, b3);
+              float2 wx[4], wy[4];
+              {
+                float a0, a1, a2, a3, b0, b1, b2, b3;
+                keys_weights(txA, a0, a1, a2, a3); keys_weights(txB, b0, b1, b2, b3);
+                wx[0] = make_float2(a0, b0); wx[1] = make_float2(a1, b1); wx[2] = make_float2(a2, b2); wx[3] = make_float2(a3, b3);
+                keys_weights(tyA, a0, a1, a2, a3); keys_weights(tyB, b0, b1, b2, b3);
+                wy[0] = make_float2(a0, b0); wy[1] = make_float2(a1, b1); wy[2] = make_float2(a2, b2); wy[3] = make_float2(a3, b3);
+              }
+              const float* tA = s2 + offA;
+              const float* tB = s2 + offB;
+#pragma unroll
+              for (int ch = 0; ch < C; ++ch) {
+                float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float* rA = tA + q * S2W + ch;
+                  const float* rB = tB + q * S2W + ch;
+                  float2 h = __fmul2_rn(wx[0], make_float2(rA[0], rB[0]));
+                  h = __ffma2_rn(wx[1], make_float2(rA[C], rB[C]), h);
+                  h = __ffma2_rn(wx[2], make_float2(rA[2 * C], rB[2 * C]), h);
+                  h = __ffma2_rn(wx[3], make_float2(rA[3 * C], rB[3 * C]), h);
+                  acc2 = __ffma2_rn(wy[q], h, acc2);
+                }
+                iw[ch] = acc2;
+              }
             }
-            const float* tA = s2 + (cyA - 1 - by0) * S2W + (cxA - 1 - bx0) * C;
-            const float* tB = s2 + (cyB - 1 - by0) * S2W + (cxB - 1 - bx0) * C;
-            const float* cA = s1 + (ly + 1) * S1W + (lane + HALO) * C;
-            const float* cB = cA + 32 * C;
-            const bool frA = yin && (!frame || (xA >= delta && xA < nx - delta));
-            const bool frB = yin && (!frame || (xB >= delta && xB < nx - delta));
-            // gradient masks fold the 1/2 of the central difference, the frame and the image border
+            // phase 2: residual, gradient of I1 (masks fold the 1/2, the frame and the image border), S, v
+            const int delta_ = delta;
+            const bool yin = !frame || (y >= delta_ && y < ny - delta_);
+            const bool frA = yin && (!frame || (xA >= delta_ && xA < nx - delta_));
+            const bool frB = yin && (!frame || (xB >= delta_ && xB < nx - delta_));
+            const bool gyrow = y >= 1 && y <= ny - 2;
             const float2 mgx = make_float2((frA && xA >= 1 && xA <= nx - 2) ? 0.5f : 0.0f, (frB && xB >= 1 && xB <= nx - 2) ? 0.5f : 0.0f);
             const float2 mgy = make_float2((frA && gyrow) ? 0.5f : 0.0f, (frB && gyrow) ? 0.5f : 0.0f);
             const float2 nmgx = make_float2(-mgx.x, -mgx.y), nmgy = make_float2(-mgy.x, -mgy.y);
+            const float* cA = s1 + (ly + 1) * S1W + (lane + HALO) * C;
+            const float* cB = cA + 32 * C;
+            const float lo = tcv->lo, hi = tcv->hi;
             float2 sxx = make_float2(0.f, 0.f), sxy = sxx, syy = sxx, vx = sxx, vy = sxx, t2 = sxx;
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) {
-              float2 acc2 = make_float2(0.f, 0.f);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float* rA = tA + q * S2W + ch;
-                const float* rB = tB + q * S2W + ch;
-                float2 h = __fmul2_rn(wx[0], make_float2(rA[0], rB[0]));
-                h = __ffma2_rn(wx[1], make_float2(rA[C], rB[C]), h);
-                h = __ffma2_rn(wx[2], make_float2(rA[2 * C], rB[2 * C]), h);
-                h = __ffma2_rn(wx[3], make_float2(rA[3 * C], rB[3 * C]), h);
-                acc2 = __ffma2_rn(wy[q], h, acc2);
-              }
-              const bool vA = acc2.x == acc2.x, vB = acc2.y == acc2.y;   // NaN footprint
-              const float iwA = fminf(fmaxf(acc2.x, lo), hi), iwB = fminf(fmaxf(acc2.y, lo), hi);
+              const bool vA = iw[ch].x == iw[ch].x, vB = iw[ch].y == iw[ch].y;   // NaN footprint
+              const float iwA = fminf(fmaxf(iw[ch].x, lo), hi), iwB = fminf(fmaxf(iw[ch].y, lo), hi);
               const float2 gx = __ffma2_rn(make_float2(cA[ch + C], cB[ch + C]), mgx, __fmul2_rn(make_float2(cA[ch - C], cB[ch - C]), nmgx));
               const float2 gy = __ffma2_rn(make_float2(cA[ch + S1W], cB[ch + S1W]), mgy, __fmul2_rn(make_float2(cA[ch - S1W], cB[ch - S1W]), nmgy));
               const float2 di = make_float2(vA ? iwA - cA[ch] : 0.0f, vB ? iwB - cB[ch] : 0.0f);   // non-finite -> 0 (io.py:72, 134)
-              if (need_h) { sxx = __ffma2_rn(gx, gx, sxx); sxy = __ffma2_rn(gx, gy, sxy); syy = __ffma2_rn(gy, gy, syy); }
+              if (need_hr) { sxx = __ffma2_rn(gx, gx, sxx); sxy = __ffma2_rn(gx, gy, sxy); syy = __ffma2_rn(gy, gy, syy); }
               vx = __ffma2_rn(gx, di, vx); vy = __ffma2_rn(gy, di, vy);
               t2 = __ffma2_rn(di, di, t2);
             }
-            // gray image standing for its x3 replication: every channel sum triples
+            // phase 3: robust weight and moments.  A gray image stands for its x3 replication
+            // (SURVEY Q12): every channel sum triples
+            const float lambda2 = tcv->lambda2;
             const float rhoA = robust ? rho_prime(t2.x * chm, lambda2, rtype) : 1.0f;
             const float rhoB = robust ? rho_prime(t2.y * chm, lambda2, rtype) : 1.0f;
             add_moments(rhoA * chm, sxx.x, sxy.x, syy.x, vx.x, vy.x, (float)xA);
             add_moments(rhoB * chm, sxx.y, sxy.y, syy.y, vx.y, vy.y, (float)xB);
           } else {
             // ===== generic path: image edges, windows that do not fit, degenerate projections
+            const bool yin = !frame || (y >= delta && y < ny - delta);
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
               const int x = half ? xB : xA;
@@ -449,16 +473,17 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
               keys_weights(half ? txB : txA, wxs[0], wxs[1], wxs[2], wxs[3]);
               keys_weights(half ? tyB : tyA, wys[0], wys[1], wys[2], wys[3]);
               const bool inframe = yin && (!frame || (x >= delta && x < nx - delta));
-              const float* t2base = s2 + (cy - 1 - by0) * S2W + (cx - 1 - bx0) * C;
+              const float* t2base = s2 + (half ? offB : offA);
               const float* c1 = s1 + (ly + 1) * S1W + (lx + HALO) * C;
               const bool gxok = inframe && x >= 1 && x <= nx - 2;
               const bool gyok = inframe && y >= 1 && y <= ny - 2;
+              const float lo = tcv->lo, hi = tcv->hi;
               float sxx = 0.f, sxy = 0.f, syy = 0.f, vx = 0.f, vy = 0.f, t2 = 0.f;
 #pragma unroll
               for (int ch = 0; ch < C; ++ch) {
-                float iw;
+                float iwv;
                 if (!pok) {
-                  iw = __int_as_float(0x7fc00000);
+                  iwv = __int_as_float(0x7fc00000);
                 } else if (insm) {
                   float a = 0.0f;
 #pragma unroll
@@ -467,21 +492,21 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
                     float hsum = wxs[0] * r[0] + wxs[1] * r[C] + wxs[2] * r[2 * C] + wxs[3] * r[3 * C];
                     a = fmaf(wys[q], hsum, a);
                   }
-                  iw = a;
+                  iwv = a;
                 } else {
-                  iw = sample_global_slow<C>(I2, pitch, nx, ny, cx, cy, ch, wxs[0], wxs[1], wxs[2], wxs[3], wys[0], wys[1], wys[2], wys[3]);
+                  iwv = sample_global_slow<C>(tctl[sidx].I2, tcv->pitch, nx, ny, cx, cy, ch, wxs[0], wxs[1], wxs[2], wxs[3], wys[0], wys[1], wys[2], wys[3]);
                 }
-                const bool valid = iw == iw;               // NaN footprint
-                iw = fminf(fmaxf(iw, lo), hi);             // clip (only used when valid)
+                const bool valid = iwv == iwv;             // NaN footprint
+                iwv = fminf(fmaxf(iwv, lo), hi);           // clip (only used when valid)
                 const float i1c = c1[ch];
                 const float gx = gxok ? 0.5f * (c1[ch + C] - c1[ch - C]) : 0.0f;
                 const float gy = gyok ? 0.5f * (c1[ch + S1W] - c1[ch - S1W]) : 0.0f;
-                const float di = valid ? iw - i1c : 0.0f;  // non-finite -> 0 (io.py:72, 134)
-                if (need_h) { sxx = fmaf(gx, gx, sxx); sxy = fmaf(gx, gy, sxy); syy = fmaf(gy, gy, syy); }
+                const float di = valid ? iwv - i1c : 0.0f; // non-finite -> 0 (io.py:72, 134)
+                if (need_hr) { sxx = fmaf(gx, gx, sxx); sxy = fmaf(gx, gy, sxy); syy = fmaf(gy, gy, syy); }
                 vx = fmaf(gx, di, vx); vy = fmaf(gy, di, vy);
                 t2 = fmaf(di, di, t2);
               }
-              const float rho = robust ? rho_prime(t2 * chm, lambda2, rtype) : 1.0f;
+              const float rho = robust ? rho_prime(t2 * chm, tcv->lambda2, rtype) : 1.0f;
               add_moments(rho * chm, sxx, sxy, syy, vx, vy, (float)x);
             }
           }
@@ -490,20 +515,21 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
 #pragma unroll
         for (int i = 0; i < K; ++i) sc[i * SCR_PITCH + lane] = v[i];
         __syncwarp();
-        float tot = 0.0f;
-        if (lane < K) {
+        if (lane < K && y < ny) {
           const float4* r4 = reinterpret_cast<const float4*>(sc + lane * SCR_PITCH);
+          float tot = 0.0f;
 #pragma unroll
           for (int j = 0; j < 8; ++j) { const float4 q4 = r4[j]; tot += q4.x; tot += q4.y; tot += q4.z; tot += q4.w; }
-        }
-        __syncwarp();
-        if (y < ny) {
+          // fold in y^b in fp64; the per-lane accumulators live in shared memory
           const double yd = (double)y, t = (double)tot;
           double yp = 1.0;
 #pragma unroll
-          for (int b = 0; b < kYPow; ++b) { acc[b] = fma(t, yp, acc[b]); yp *= yd; }
+          for (int b = 0; b < kYPow; ++b) { myacc[b] = fma(t, yp, myacc[b]); yp *= yd; }
         }
+        __syncwarp();
       }
+      pair = tcv->pair; chunk = tcv->chunk; nch = tcv->nch; s = tcv->scale; nx = tcv->nx; ny = tcv->ny;
+      need_h = tcv->need_h != 0; last = tcv->last != 0;
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sidx]);   // this warp is done with the stage (and its TileCtl)
       ++k;
@@ -511,37 +537,107 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
     ICA_STAMP(2);
 
     // ---------------- chunk partial: [K][kYPow] doubles, warps summed in fixed order
-    double* const myred = reinterpret_cast<double*>(sc);   // this warp's scratch, 105 doubles <= SCR floats * 4
-    if (lane < K) {
-#pragma unroll
-      for (int b = 0; b < kYPow; ++b) myred[lane * kYPow + b] = acc[b];
-    }
     consumer_sync();
     {
       double* out = P.partials + ((long long)pair * P.max_chunks + chunk) * kAccStride;
       for (int i = tid; i < NENT; i += kConsumerThreads) {
         double sum = 0.0;
 #pragma unroll
-        for (int w = 0; w < kConsumerWarps; ++w) sum += reinterpret_cast<const double*>(scratch + w * SCR)[i];
+        for (int w = 0; w < kConsumerWarps; ++w) sum += accs[w * NENT + i];
         out[i] = sum;
       }
     }
-    // ---------------- arrive; the block that delivers the pair's last chunk runs the epilogue
-    __threadfence();
-    consumer_sync();
-    ICA_STAMP(3);
-    if (tid == 0) s_ticket = atomicAdd(&P.state[pair].ticket, 1u);
-    consumer_sync();
-    ICA_STAMP(4);
-    if (s_ticket != (unsigned)(nch - 1)) continue;   // uniform over the consumers
-    __threadfence();
+    consumer_sync();   // every warp's shared accumulators may be reused by the CTA's next chunk
+  }
+  if (P.dbg_time && tid == 32) { P.dbg_time[blockIdx.x * 16 + 13] = gtime(); P.dbg_time[blockIdx.x * 16 + 14] = nitems; }
+}
 
-    // ================= K3: reduce the chunks, solve, compose, schedule =================
-    PairState& st = P.state[pair];
+// Work list of the next launch: chunk_start[b] = exclusive prefix sum of chunks per pair,
+// chunk_start[B] = total, item_pair[i] = pair of work item i; also publishes the number of
+// unfinished pairs.  Executed by one whole block (any size that is a multiple of 32, <= 1024).
+__device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthr = blockDim.x, nwarp = nthr >> 5;
+  const int B = P.B;
+  if (tid == 0) { s_scal[0] = 0; s_scal[1] = 0; }   // carry, active pairs
+  __syncthreads();
+  for (int base = 0; base < B; base += nthr) {
+    const int b = base + tid;
+    int c = 0;
+    if (b < B) {
+      const int s = __ldcg(&P.state[b].scale);
+      if (s >= 0) { const int nt = P.lv[s].tiles_x * P.lv[s].tiles_y; c = nt < P.max_chunks ? nt : P.max_chunks; }
+    }
+    const unsigned actmask = __ballot_sync(0xffffffffu, c > 0);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = lane < nwarp ? s_warp[lane] : 0;
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+      s_warp[lane] = wi - w;   // exclusive
+    }
+    __syncthreads();
+    const int excl = s_scal[0] + s_warp[warp] + incl - c;
+    if (b < B) {
+      P.chunk_start[b] = excl;
+      for (int i = 0; i < c; ++i) P.item_pair[excl + i] = b;
+    }
+    if (lane == 0 && actmask) atomicAdd(&s_scal[1], __popc(actmask));
+    __syncthreads();
+    if (tid == nthr - 1) s_scal[0] = excl + c;
+    __syncthreads();
+  }
+  if (tid == 0) { P.chunk_start[B] = s_scal[0]; *P.n_active = s_scal[1]; }
+}
+
+__global__ void __launch_bounds__(1024) ica_schedule_kernel(const IterParams P) {
+  __shared__ int s_warp[32];
+  __shared__ int s_scal[2];
+  schedule_block(P, s_warp, s_scal);
+}
+
+
+// K3: one block per image pair, after the iterate kernel: sums the pair's chunk partials in a fixed
+// order, assembles H and b, de.inverse_hessian + io.parametric_solve + tr.update_transform, the
+// lambda schedule, the stopping rule and zm.zoom_in_parameters at a scale change
+// (ica.py:223-259, 102-131).  The last block to finish builds the work list of the next
+// iteration (what ica_schedule_kernel does for the first one), so an iteration is two launches.
+constexpr int kSolveThreads = 256;
+constexpr int kSolveWarps = kSolveThreads / 32;
+
+template <int DH>
+__global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterParams P) {
+  constexpr int K = RowVals<DH>::K;
+  constexpr int HW = DH + 1;
+  constexpr int NENT = K * kYPow;
+  __shared__ double s_part[kSolveWarps * NENT];
+  __shared__ double s_mom[kAccStride];
+  __shared__ double s_aug[ICA_MAX_PARAMS][2 * ICA_MAX_PARAMS + 1];
+  __shared__ double s_vec[2 * ICA_MAX_PARAMS];
+  __shared__ int s_warp[32];
+  __shared__ int s_scal[2];
+  __shared__ unsigned int s_ticket;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pair = blockIdx.x;
+  PairState& st = P.state[pair];
+  const int s = st.scale;
+  const bool robust = P.robust_loop != 0;
+  if (s >= 0) {   // the pair took part in the iteration that just ran
+    const LevelDesc L = P.lv[s];
+    const int nx = L.nx, ny = L.ny;
+    const int ntiles = L.tiles_x * L.tiles_y;
+    const int nch = ntiles < P.max_chunks ? ntiles : P.max_chunks;
+    const bool need_h = P.robust_loop || st.iter == 0;
+    bool solved = false;
     {
       // fixed summation order: warp w sums its contiguous range of chunks, then warps in order
-      double* part = reinterpret_cast<double*>(scratch);      // [kConsumerWarps][NENT]
-      const int c0 = (int)((long long)warp * nch / kConsumerWarps), c1 = (int)((long long)(warp + 1) * nch / kConsumerWarps);
+      double* part = s_part;      // [kSolveWarps][NENT]
+      const int c0 = (int)((long long)warp * nch / kSolveWarps), c1 = (int)((long long)(warp + 1) * nch / kSolveWarps);
       const double* src = P.partials + (long long)pair * P.max_chunks * kAccStride;
       constexpr int NJ = (NENT + 31) / 32;
       constexpr int UN = 4;                                    // chunks in flight per lane
@@ -569,19 +665,17 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
       }
 #pragma unroll
       for (int j = 0; j < NJ; ++j) { const int e = lane + 32 * j; if (e < NENT) part[warp * NENT + e] = sum[j]; }
-      consumer_sync();
+      __syncthreads();
       if (tid < NENT) {
         double tsum = 0.0;
 #pragma unroll
-        for (int w = 0; w < kConsumerWarps; ++w) tsum += part[w * NENT + tid];
+        for (int w = 0; w < kSolveWarps; ++w) tsum += part[w * NENT + tid];
         // quadratic loop after the first iteration of a scale: the H moments were not gathered
         s_mom[tid] = (!need_h && tid < 3 * HW * kYPow) ? 0.0 : tsum;
       }
-      consumer_sync();
+      __syncthreads();
     }
-    ICA_STAMP(5);
-    // The n x n part is warp 0's job; the other consumer warps go on with the CTA's next chunk.
-    if (warp != 0) continue;
+    if (warp == 0) {   // the n x n part is one warp's job
     const int ttype = st.ttype;
     const int n = nparams_of(ttype);
     // assemble H (n x n) and b (n) from the moments (same sums as ica_transform.cuh: assemble_system)
@@ -610,13 +704,12 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
       }
     }
     __syncwarp();
-    ICA_STAMP(6);
     if (P.dbg_Hb) {  // parity hook (ica_hessian_b_host): export, leave the state untouched
       for (int e = lane; e < n * n; e += 32) P.dbg_Hb[e] = s_aug[e / n][e % n];
       if (lane < n) P.dbg_Hb[64 + lane] = s_vec[lane];
-      if (lane == 0) st.ticket = 0;
-      continue;
+      solved = true;
     }
+    if (!solved) {
     // de.inverse_hessian: Gauss-Jordan with partial pivoting on [H | I] in shared memory, 4 entries
     // per lane (element by element the arithmetic of ica_transform.cuh: inverse_hessian); zero matrix
     // when a pivot is exactly zero (np.linalg.LinAlgError branch, derivatives.py:127-129)
@@ -664,7 +757,6 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
       }
       __syncwarp();
     }
-    ICA_STAMP(7);
     if (lane < n) {                                    // io.parametric_solve (io.py:146-155)
       double a = 0.0;
       for (int j = 0; j < n; ++j) a += (need_h ? s_aug[lane][n + j] : st.hinv[lane * n + j]) * s_vec[j];
@@ -710,55 +802,19 @@ __global__ void __launch_bounds__(kThreads, 2) ica_iterate_kernel(const IterPara
           st.scale = -1;
         }
       }
-      st.ticket = 0;
     }
-    __syncwarp();
-    ICA_STAMP(8);
+    }  // !solved
+    }  // warp 0
   }
-}
-
-// Work list of the next launch: chunk_start[b] = exclusive prefix sum of chunks per pair,
-// chunk_start[B] = total, item_pair[i] = pair of work item i; also publishes the number of
-// unfinished pairs.  One block.
-__global__ void __launch_bounds__(1024) ica_schedule_kernel(const IterParams P) {
-  __shared__ int s_warp[32];
-  __shared__ int s_carry, s_act;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int B = P.B;
-  if (tid == 0) { s_carry = 0; s_act = 0; }
+  // ---- the last block builds the next work list
+  __threadfence();
   __syncthreads();
-  for (int base = 0; base < B; base += 1024) {
-    const int b = base + tid;
-    int c = 0;
-    if (b < B) {
-      const int s = P.state[b].scale;
-      if (s >= 0) { const int nt = P.lv[s].tiles_x * P.lv[s].tiles_y; c = nt < P.max_chunks ? nt : P.max_chunks; }
-    }
-    const unsigned actmask = __ballot_sync(0xffffffffu, c > 0);
-    int incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      const int w = s_warp[lane];
-      int wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
-      s_warp[lane] = wi - w;   // exclusive
-    }
-    __syncthreads();
-    const int excl = s_carry + s_warp[warp] + incl - c;
-    if (b < B) {
-      P.chunk_start[b] = excl;
-      for (int i = 0; i < c; ++i) P.item_pair[excl + i] = b;
-    }
-    if (lane == 0 && actmask) atomicAdd(&s_act, __popc(actmask));
-    __syncthreads();
-    if (tid == 1023) s_carry = excl + c;
-    __syncthreads();
-  }
-  if (tid == 0) { P.chunk_start[B] = s_carry; *P.n_active = s_act; }
+  if (tid == 0) s_ticket = atomicAdd(P.solve_ticket, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  schedule_block(P, s_warp, s_scal);
+  if (tid == 0) *P.solve_ticket = 0;
 }
 
 // Resets the per-pair state at the start of a run (ica.py:319-337: ps[0] = p, ps[s>0] = 0;
@@ -880,7 +936,8 @@ __global__ void ica_gradient_kernel(const float* __restrict__ img, int nx, int n
 
 template <int C, int DH>
 cudaError_t launch_iterate_t(const IterParams& P, int grid, cudaStream_t stream) {
-  constexpr size_t smem = (2 * (size_t)Stage<C>::kFloats + (size_t)kConsumerWarps * RowVals<DH>::K * SCR_PITCH) * sizeof(float);
+  constexpr size_t smem = (2 * (size_t)Stage<C>::kFloats + (size_t)kConsumerWarps * RowVals<DH>::K * SCR_PITCH) * sizeof(float) +
+                          (size_t)kConsumerWarps * RowVals<DH>::K * kYPow * sizeof(double);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(ica_iterate_kernel<C, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -895,9 +952,17 @@ cudaError_t launch_iterate_t(const IterParams& P, int grid, cudaStream_t stream)
 
 int iterate_tile_w() { return TW; }
 int iterate_tile_h() { return TH; }
+int iterate_blocks_per_sm() { return kBlocksPerSM; }
 
 cudaError_t launch_schedule(const IterParams& P, cudaStream_t stream) {
   ica_schedule_kernel<<<1, 1024, 0, stream>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_solve(const IterParams& P, int dh, cudaStream_t stream) {
+  if (dh == 4) ica_solve_kernel<4><<<P.B, kSolveThreads, 0, stream>>>(P);
+  else if (dh == 2) ica_solve_kernel<2><<<P.B, kSolveThreads, 0, stream>>>(P);
+  else ica_solve_kernel<0><<<P.B, kSolveThreads, 0, stream>>>(P);
   return cudaGetLastError();
 }
 

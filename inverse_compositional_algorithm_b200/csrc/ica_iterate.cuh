@@ -22,6 +22,7 @@ struct IterParams {
   int* n_active;
   int* chunk_start;       // [B+1] work list of the current launch (ica_schedule_kernel)
   int* item_pair;         // [B*max_chunks] pair of each work item
+  unsigned int* solve_ticket;   // blocks of the solve kernel that are done (the last one schedules)
   int B;
   int max_chunks;         // partial slots per pair
   int traj_cap;
@@ -37,7 +38,9 @@ struct IterParams {
 
 int iterate_tile_w();
 int iterate_tile_h();
+int iterate_blocks_per_sm();
 cudaError_t launch_schedule(const IterParams& P, cudaStream_t stream);
+cudaError_t launch_solve(const IterParams& P, int dh, cudaStream_t stream);
 cudaError_t launch_iterate(const IterParams& P, int channels, int dh, int grid, cudaStream_t stream);
 cudaError_t launch_init_state(PairState* state, const double* p_in, const int* ttypes, int B, int nscales,
                               double lambda_cfg, int* n_active, cudaStream_t stream);

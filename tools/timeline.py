@@ -21,10 +21,14 @@ plan.run_host(I1, I2)
 tl = plan.debug_timeline(True, fetch=True)
 act = tl[tl[:, 0] > 0]
 t0 = act[:, 0].min()
-names = ["start", "first_tile_ready", "tiles_done", "partial_written", "ticket", "sums_done", "assembled", "gj_done", "end", "P:decoded", "P:planned", "P:issued", "P:filled"]
+names = ["start", "first_tile_ready", "tiles_done", "partial_written", "ticket", "sums_done", "assembled", "gj_done", "end", "P:decoded", "P:planned", "P:issued", "P:filled", "block_end"]
 print("CTAs with work:", len(act))
 for i, nm in enumerate(names):
     col = act[:, i]
     col = col[col > 0]
     if len(col):
         print(f"{nm:18s} n={len(col):4d}  min={(col.min()-t0)/1e3:8.2f} us  median={(np.median(col)-t0)/1e3:8.2f}  max={(col.max()-t0)/1e3:8.2f}")
+
+end = act[:, 13]; end = end[end > 0] - t0
+print("block_end percentiles (us):", [round(float(np.percentile(end, q)) / 1e3, 1) for q in (0, 10, 25, 50, 75, 90, 99, 100)])
+print("items per block:", np.unique(act[:, 14], return_counts=True))
