@@ -151,6 +151,12 @@ ICA_API int ica_warp_host(const float* image, int32_t height, int32_t width, int
    zoom_size(height, width, nu) x C; out_h/out_w receive it. */
 ICA_API int ica_rescale_host(const float* image, int32_t height, int32_t width, int32_t channels,
                      double nu, float* out, int32_t* out_h, int32_t* out_w);
+/* The banded 1-D operator the pyramid kernels apply along one axis (host computation, no GPU needed):
+   out[o] = sum_k weights[o*taps + k] * in[start[o] + k] reproduces, per axis, skimage.transform.rescale's
+   Gaussian -> 12-sample zero pad -> cubic-spline prefilter -> spline evaluation (ica.py:333-336).
+   weights_out needs n_out * 64 floats at most; fast_range_out[3] = {lo, hi, s0} of the uniform rows. */
+ICA_API int ica_resample_operator(int32_t n_in, int32_t n_out, int32_t* taps_out, int32_t* start_out,
+                                  float* weights_out, int32_t weights_capacity, int32_t* fast_range_out);
 /* zoom.zoom_size (src/zoom.py:8-22), round-half-to-even */
 ICA_API int ica_zoom_size(int32_t nx, int32_t ny, double factor, int32_t* nxx, int32_t* nyy);
 /* Gradient of I1 + frame (ica.py:81-93): Ix, Iy float32 [H][W][C]; NaN on the frame */

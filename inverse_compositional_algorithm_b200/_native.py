@@ -66,6 +66,7 @@ SIGNATURES = {
     "ica_plan_get_timing": (C.c_int, [_P, _PF, _PI, _PF, _PI]),
     "ica_warp_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "ica_rescale_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _PI, _PI]),
+    "ica_resample_operator": (C.c_int, [C.c_int32, C.c_int32, _PI, _PI, _P, C.c_int32, _PI]),
     "ica_zoom_size": (C.c_int, [C.c_int32, C.c_int32, C.c_double, _PI, _PI]),
     "ica_gradient_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "ica_hessian_b_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P,
@@ -177,6 +178,20 @@ def zoom_size(nx: int, ny: int, factor: float):
     a, b = C.c_int32(), C.c_int32()
     check(lib().ica_zoom_size(int(nx), int(ny), float(factor), C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def resample_operator(n_in: int, n_out: int):
+    """Dense (n_out x n_in) matrix of the banded pyramid operator along one axis, plus the uniform range."""
+    taps = C.c_int32()
+    start = np.zeros(n_out, dtype=np.int32)
+    w = np.zeros(n_out * 64, dtype=np.float32)
+    fast = np.zeros(3, dtype=np.int32)
+    check(lib().ica_resample_operator(int(n_in), int(n_out), C.byref(taps), start.ctypes.data_as(_PI), _ptr(w), w.size,
+                                      fast.ctypes.data_as(_PI)))
+    A = np.zeros((n_out, n_in))
+    for o in range(n_out):
+        A[o, start[o]:start[o] + taps.value] = w[o * taps.value:(o + 1) * taps.value]
+    return A, taps.value, fast
 
 
 def inverse_hessian(H: np.ndarray) -> np.ndarray:

@@ -557,6 +557,25 @@ int ica_zoom_size(int32_t nx, int32_t ny, double factor, int32_t* nxx, int32_t* 
   return ICA_OK;
 }
 
+int ica_resample_operator(int32_t n_in, int32_t n_out, int32_t* taps_out, int32_t* start_out, float* weights_out,
+                          int32_t weights_capacity, int32_t* fast_range_out) {
+  if (n_in < 1 || n_out < 1 || !taps_out) { set_error("bad argument"); return ICA_ERR_INVALID; }
+  Resample1D r;
+  build_resample_1d(n_in, n_out, &r);
+  *taps_out = r.taps;
+  if (start_out) for (int o = 0; o < n_out; ++o) start_out[o] = r.start[o];
+  if (weights_out) {
+    if ((long long)weights_capacity < (long long)n_out * r.taps) { set_error("weights buffer too small"); return ICA_ERR_INVALID; }
+    for (size_t i = 0; i < r.weights.size(); ++i) weights_out[i] = r.weights[i];
+  }
+  if (fast_range_out) {
+    FastRows f;
+    detect_uniform_rows(r, &f);
+    fast_range_out[0] = f.lo; fast_range_out[1] = f.hi; fast_range_out[2] = f.s0;
+  }
+  return ICA_OK;
+}
+
 int ica_nparams(int32_t t) { int n = nparams_of(t); if (n < 0) set_error("Unknown transform type"); return n < 0 ? ICA_ERR_INVALID : n; }
 
 int ica_params2matrix(const double* p, int32_t t, double* m9) {
