@@ -40,6 +40,8 @@ struct ica_plan {
   int* chunk_start = nullptr;
   int* item_pair = nullptr;
   unsigned int* solve_ticket = nullptr;
+  AsmEntry* asm_tab = nullptr;
+  int asm_dh = -1;
   long long* dbg_time = nullptr;   // optional per-CTA timeline (ica_plan_debug_timeline)
   LevelDesc lv[ICA_MAX_SCALES];
   long long in_stride = 0, pyr_stride = 0;
@@ -106,6 +108,15 @@ int upload_resample(ica_plan* pl, const Resample1D& r, DeviceResample* d) {
   return ICA_OK;
 }
 
+int upload_assembly(ica_plan* pl) {
+  if (pl->asm_dh == pl->dh) return ICA_OK;
+  std::vector<AsmEntry> tab((size_t)6 * 72);
+  build_assembly_table(pl->dh, tab.data());
+  ICA_CUDA_CHECK(cudaMemcpy(pl->asm_tab, tab.data(), tab.size() * sizeof(AsmEntry), cudaMemcpyHostToDevice));
+  pl->asm_dh = pl->dh;
+  return ICA_OK;
+}
+
 void free_resample(DeviceResample* d) {
   cudaFree(d->start); cudaFree(d->weights); cudaFree(d->weights_t);
   d->start = nullptr; d->weights = nullptr; d->weights_t = nullptr;
@@ -152,6 +163,7 @@ void fill_iter_params(const ica_plan* pl, const float* I1, const float* I2, Iter
   P->chunk_start = pl->chunk_start;
   P->item_pair = pl->item_pair;
   P->solve_ticket = pl->solve_ticket;
+  P->asm_tab = pl->asm_tab;
   P->B = pl->B;
   P->max_chunks = pl->max_chunks;
   P->robust_type = pl->cfg.robust_type;
@@ -229,7 +241,7 @@ int ica_plan_destroy(ica_plan* pl) {
   if (!pl) return ICA_OK;
   cudaFree(pl->pyr1); cudaFree(pl->pyr2); cudaFree(pl->tmp);
   for (int s = 0; s < ICA_MAX_SCALES; ++s) { free_resample(&pl->ry[s]); free_resample(&pl->rx[s]); }
-  cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->item_pair); cudaFree(pl->solve_ticket); cudaFree(pl->dbg_time); cudaFree(pl->traj); cudaFree(pl->n_active);
+  cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->item_pair); cudaFree(pl->solve_ticket); cudaFree(pl->asm_tab); cudaFree(pl->dbg_time); cudaFree(pl->traj); cudaFree(pl->n_active);
   if (pl->h_n_active) cudaFreeHost(pl->h_n_active);
   cudaFree(pl->ttypes_dev); cudaFree(pl->p_dev); cudaFree(pl->err_dev); cudaFree(pl->iters_dev);
   cudaFree(pl->in1_dev); cudaFree(pl->in2_dev); cudaFree(pl->raw_dev); cudaFree(pl->DI_dev); cudaFree(pl->Iw_dev);
@@ -306,6 +318,8 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   TRY(dev_alloc(pl, &pl->chunk_start, (size_t)pl->B + 1));
   TRY(dev_alloc(pl, &pl->item_pair, (size_t)pl->B * pl->max_chunks));
   TRY(dev_alloc(pl, &pl->solve_ticket, 1));
+  TRY(dev_alloc(pl, &pl->asm_tab, (size_t)6 * 72));
+  TRY(upload_assembly(pl));
   TRY_CUDA(cudaMemset(pl->solve_ticket, 0, sizeof(unsigned int)));
   pl->traj_cap = pl->nscales * cfg->max_iter;
   if (cfg->flags & ICA_FLAG_RECORD_TRAJECTORY) TRY(dev_alloc(pl, &pl->traj, (size_t)pl->B * pl->traj_cap * ICA_TRAJ_STRIDE));
@@ -339,6 +353,7 @@ int ica_plan_set_transform_types(ica_plan* pl, const int32_t* types, int32_t cou
   }
   pl->ttypes.assign(types, types + count);
   pl->dh = dh;
+  if (int rc = upload_assembly(pl)) return rc;
   ICA_CUDA_CHECK(cudaMemcpy(pl->ttypes_dev, pl->ttypes.data(), count * sizeof(int), cudaMemcpyHostToDevice));
   return ICA_OK;
 }

@@ -615,16 +615,22 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
   constexpr int K = RowVals<DH>::K;
   constexpr int HW = DH + 1;
   constexpr int NENT = K * kYPow;
+  constexpr int kStateWords = (int)(sizeof(PairState) / 8);
+  static_assert(sizeof(PairState) % 8 == 0, "PairState is copied as 8-byte words");
   __shared__ double s_part[kSolveWarps * NENT];
   __shared__ double s_mom[kAccStride];
   __shared__ double s_aug[ICA_MAX_PARAMS][2 * ICA_MAX_PARAMS + 1];
   __shared__ double s_vec[2 * ICA_MAX_PARAMS];
+  __shared__ __align__(8) PairState s_st;       // the pair's state is staged here and written back once
   __shared__ int s_warp[32];
   __shared__ int s_scal[2];
   __shared__ unsigned int s_ticket;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pair = blockIdx.x;
-  PairState& st = P.state[pair];
+  if (tid < kStateWords)
+    reinterpret_cast<unsigned long long*>(&s_st)[tid] = __ldcg(reinterpret_cast<const unsigned long long*>(&P.state[pair]) + tid);
+  __syncthreads();
+  PairState& st = s_st;
   const int s = st.scale;
   const bool robust = P.robust_loop != 0;
   if (s >= 0) {   // the pair took part in the iteration that just ran
@@ -633,10 +639,8 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
     const int ntiles = L.tiles_x * L.tiles_y;
     const int nch = ntiles < P.max_chunks ? ntiles : P.max_chunks;
     const bool need_h = P.robust_loop || st.iter == 0;
-    bool solved = false;
     {
       // fixed summation order: warp w sums its contiguous range of chunks, then warps in order
-      double* part = s_part;      // [kSolveWarps][NENT]
       const int c0 = (int)((long long)warp * nch / kSolveWarps), c1 = (int)((long long)(warp + 1) * nch / kSolveWarps);
       const double* src = P.partials + (long long)pair * P.max_chunks * kAccStride;
       constexpr int NJ = (NENT + 31) / 32;
@@ -664,147 +668,136 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
         for (int j = 0; j < NJ; ++j) { const int e = lane + 32 * j; if (e < NENT) sum[j] += __ldcg(src + (long long)c * kAccStride + e); }
       }
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) { const int e = lane + 32 * j; if (e < NENT) part[warp * NENT + e] = sum[j]; }
+      for (int j = 0; j < NJ; ++j) { const int e = lane + 32 * j; if (e < NENT) s_part[warp * NENT + e] = sum[j]; }
       __syncthreads();
       if (tid < NENT) {
         double tsum = 0.0;
 #pragma unroll
-        for (int w = 0; w < kSolveWarps; ++w) tsum += part[w * NENT + tid];
+        for (int w = 0; w < kSolveWarps; ++w) tsum += s_part[w * NENT + tid];
         // quadratic loop after the first iteration of a scale: the H moments were not gathered
         s_mom[tid] = (!need_h && tid < 3 * HW * kYPow) ? 0.0 : tsum;
       }
       __syncthreads();
     }
     if (warp == 0) {   // the n x n part is one warp's job
-    const int ttype = st.ttype;
-    const int n = nparams_of(ttype);
-    // assemble H (n x n) and b (n) from the moments (same sums as ica_transform.cuh: assemble_system)
-    for (int e = lane; e < n * n + n; e += 32) {
-      constexpr int hw = DH + 1, bwn = DH / 2 + 1, boff = 3 * hw;
-      if (e < n * n) {
-        const int kk = e / n, l = e % n;
-        Mono jxk, jyk, jxl, jyl;
-        mono_of(ttype, kk, jxk, jyk);
-        mono_of(ttype, l, jxl, jyl);
-        double sum = 0.0;
-        if (jxk.coef && jxl.coef) sum += (double)(jxk.coef * jxl.coef) * s_mom[(0 * hw + jxk.a + jxl.a) * kYPow + jxk.b + jxl.b];
-        if (jxk.coef && jyl.coef) sum += (double)(jxk.coef * jyl.coef) * s_mom[(1 * hw + jxk.a + jyl.a) * kYPow + jxk.b + jyl.b];
-        if (jyk.coef && jxl.coef) sum += (double)(jyk.coef * jxl.coef) * s_mom[(1 * hw + jyk.a + jxl.a) * kYPow + jyk.b + jxl.b];
-        if (jyk.coef && jyl.coef) sum += (double)(jyk.coef * jyl.coef) * s_mom[(2 * hw + jyk.a + jyl.a) * kYPow + jyk.b + jyl.b];
-        s_aug[kk][l] = sum;
-        s_aug[kk][n + l] = (kk == l) ? 1.0 : 0.0;
-      } else {
-        const int kk = e - n * n;
-        Mono jxk, jyk;
-        mono_of(ttype, kk, jxk, jyk);
-        double sum = 0.0;
-        if (jxk.coef) sum += (double)jxk.coef * s_mom[(boff + 0 * bwn + jxk.a) * kYPow + jxk.b];
-        if (jyk.coef) sum += (double)jyk.coef * s_mom[(boff + 1 * bwn + jyk.a) * kYPow + jyk.b];
-        s_vec[kk] = sum;
-      }
-    }
-    __syncwarp();
-    if (P.dbg_Hb) {  // parity hook (ica_hessian_b_host): export, leave the state untouched
-      for (int e = lane; e < n * n; e += 32) P.dbg_Hb[e] = s_aug[e / n][e % n];
-      if (lane < n) P.dbg_Hb[64 + lane] = s_vec[lane];
-      solved = true;
-    }
-    if (!solved) {
-    // de.inverse_hessian: Gauss-Jordan with partial pivoting on [H | I] in shared memory, 4 entries
-    // per lane (element by element the arithmetic of ica_transform.cuh: inverse_hessian); zero matrix
-    // when a pivot is exactly zero (np.linalg.LinAlgError branch, derivatives.py:127-129)
-    if (need_h) {
-      bool singular = false;
-      for (int kk = 0; kk < n; ++kk) {
-        int piv = kk;
-        {
-          double best = fabs(s_aug[kk][kk]);
-          for (int r = kk + 1; r < n; ++r) { const double vv = fabs(s_aug[r][kk]); if (vv > best) { best = vv; piv = r; } }
-          if (!(best > 0.0)) singular = true;          // every lane computes the same thing
-        }
-        if (singular) break;
-        if (piv != kk) {
-          double t0 = 0.0, t1 = 0.0;
-          if (lane < 2 * n) { t0 = s_aug[kk][lane]; t1 = s_aug[piv][lane]; }
-          __syncwarp();
-          if (lane < 2 * n) { s_aug[kk][lane] = t1; s_aug[piv][lane] = t0; }
-          __syncwarp();
-        }
-        const double inv = 1.0 / s_aug[kk][kk];
-        __syncwarp();
-        if (lane < 2 * n) s_aug[kk][lane] *= inv;
-        __syncwarp();
-        double f[4], pk[4];
+      const int ttype = st.ttype;
+      const int n = nparams_of(ttype);
+      // assemble H (n x n) and b (n): every entry is a fixed +-1 combination of at most 4 moments
+      // (table built on the host from the Jacobian monomials, ica_transform.cuh: assemble_system)
+      for (int e = lane; e < 72; e += 32) {
+        const int kk = e < 64 ? e >> 3 : e - 64, l = e < 64 ? e & 7 : 0;
+        if (kk < n && l < n) {
+          const AsmEntry t = P.asm_tab[ttype * 72 + e];
+          double sum = 0.0;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const int e = lane + 32 * m, i = e >> 4, j = e & 15;
-          const bool act = i < n && j < 2 * n;
-          f[m] = act ? s_aug[i][kk] : 0.0;
-          pk[m] = act ? s_aug[kk][j] : 0.0;
+          for (int q = 0; q < 4; ++q) if (t.coef[q] != 0.0f) sum += (double)t.coef[q] * s_mom[t.idx[q]];
+          if (e < 64) { s_aug[kk][l] = sum; s_aug[kk][n + l] = (kk == l) ? 1.0 : 0.0; }
+          else s_vec[kk] = sum;
         }
-        __syncwarp();
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const int e = lane + 32 * m, i = e >> 4, j = e & 15;
-          if (i < n && j < 2 * n && i != kk && f[m] != 0.0) s_aug[i][j] -= f[m] * pk[m];
-        }
-        __syncwarp();
-      }
-      for (int e = lane; e < n * n; e += 32) {
-        const double hv = singular ? 0.0 : s_aug[e / n][n + e % n];
-        s_aug[e / n][n + e % n] = hv;
-        st.hinv[e] = hv;                               // kept for the quadratic loop's later iterations
       }
       __syncwarp();
-    }
-    if (lane < n) {                                    // io.parametric_solve (io.py:146-155)
-      double a = 0.0;
-      for (int j = 0; j < n; ++j) a += (need_h ? s_aug[lane][n + j] : st.hinv[lane * n + j]) * s_vec[j];
-      s_vec[ICA_MAX_PARAMS + lane] = a;
-    }
-    __syncwarp();
-    if (lane == 0) {
-      double dp[ICA_MAX_PARAMS];
-      double e2 = 0.0;
-      for (int i = 0; i < n; ++i) { dp[i] = s_vec[ICA_MAX_PARAMS + i]; e2 += dp[i] * dp[i]; }
-      const double err = sqrt(e2);
-      // lambda decays after rho' was evaluated with the old value (ica.py:235-238)
-      double lam = st.lambda_it;
-      if (robust && P.lambda_cfg <= 0.0 && lam > kLambdaN) {
-        lam *= kLambdaRatio;
-        if (lam < kLambdaN) lam = kLambdaN;
-      }
-      for (int i = 0; i < n; ++i) st.p_prev[i] = st.p[i];
-      update_transform(st.p, dp, ttype);
-      const int itn = st.iter + 1;
-      st.err = err;
-      st.lambda_it = lam;
-      st.total_iters += 1;
-      if (P.traj && st.traj_count < P.traj_cap) {
-        double* t = P.traj + ((long long)pair * P.traj_cap + st.traj_count) * ICA_TRAJ_STRIDE;
-        t[0] = s; t[1] = itn - 1; t[2] = err; t[3] = lam;
-        for (int i = 0; i < ICA_MAX_PARAMS; ++i) t[4 + i] = i < n ? st.p[i] : 0.0;
-        st.traj_count += 1;
-      }
-      if (err > P.tol && itn < P.max_iter) {
-        st.iter = itn;
-      } else {  // this scale is done (ica.py:109, 225)
-        st.iters_per_scale[s] = itn;
-        if (s > 0) {
-          double q[ICA_MAX_PARAMS];
-          const LevelDesc Lf = P.lv[s - 1];
-          zoom_in_parameters(st.p, ttype, (double)nx, (double)ny, (double)Lf.nx, (double)Lf.ny, q);
-          for (int i = 0; i < n; ++i) st.p[i] = q[i];
-          st.scale = s - 1;
-          st.iter = 0;
-          st.lambda_it = P.lambda_cfg > 0.0 ? P.lambda_cfg : kLambda0;  // new call per scale (ica.py:223)
-        } else {
-          st.scale = -1;
+      if (P.dbg_Hb) {  // parity hook (ica_hessian_b_host): export, leave the state untouched
+        for (int e = lane; e < n * n; e += 32) P.dbg_Hb[e] = s_aug[e / n][e % n];
+        if (lane < n) P.dbg_Hb[64 + lane] = s_vec[lane];
+      } else {
+        // de.inverse_hessian: Gauss-Jordan with partial pivoting on [H | I] in shared memory, 4 entries per
+        // lane (element by element the arithmetic of ica_transform.cuh: inverse_hessian); zero matrix when a
+        // pivot is exactly zero (np.linalg.LinAlgError branch, derivatives.py:127-129)
+        if (need_h) {
+          bool singular = false;
+          for (int kk = 0; kk < n; ++kk) {
+            // pivot: largest |a[r][kk]|, r >= kk, first one on ties (lanes 0..7 hold the candidates)
+            double best = (lane >= kk && lane < n) ? fabs(s_aug[lane][kk]) : -1.0;
+            int piv = lane;
+#pragma unroll
+            for (int o = 4; o >= 1; o >>= 1) {
+              const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+              const int op = __shfl_xor_sync(0xffffffffu, piv, o);
+              if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
+            }
+            best = __shfl_sync(0xffffffffu, best, 0); piv = __shfl_sync(0xffffffffu, piv, 0);
+            if (!(best > 0.0)) { singular = true; break; }
+            if (piv != kk) {
+              double t0 = 0.0, t1 = 0.0;
+              if (lane < 2 * n) { t0 = s_aug[kk][lane]; t1 = s_aug[piv][lane]; }
+              __syncwarp();
+              if (lane < 2 * n) { s_aug[kk][lane] = t1; s_aug[piv][lane] = t0; }
+              __syncwarp();
+            }
+            const double inv = 1.0 / s_aug[kk][kk];
+            __syncwarp();
+            if (lane < 2 * n) s_aug[kk][lane] *= inv;
+            __syncwarp();
+            double f[4], pk[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int e = lane + 32 * m, i = e >> 4, j = e & 15;
+              const bool act = i < n && j < 2 * n;
+              f[m] = act ? s_aug[i][kk] : 0.0;
+              pk[m] = act ? s_aug[kk][j] : 0.0;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int e = lane + 32 * m, i = e >> 4, j = e & 15;
+              if (i < n && j < 2 * n && i != kk && f[m] != 0.0) s_aug[i][j] -= f[m] * pk[m];
+            }
+            __syncwarp();
+          }
+          for (int e = lane; e < n * n; e += 32) st.hinv[e] = singular ? 0.0 : s_aug[e / n][n + e % n];
+          __syncwarp();
+        }
+        if (lane < n) {                                    // io.parametric_solve (io.py:146-155)
+          double a = 0.0;
+          for (int j = 0; j < n; ++j) a += st.hinv[lane * n + j] * s_vec[j];
+          s_vec[ICA_MAX_PARAMS + lane] = a;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          double dp[ICA_MAX_PARAMS];
+          double e2 = 0.0;
+          for (int i = 0; i < n; ++i) { dp[i] = s_vec[ICA_MAX_PARAMS + i]; e2 += dp[i] * dp[i]; }
+          const double err = sqrt(e2);
+          // lambda decays after rho' was evaluated with the old value (ica.py:235-238)
+          double lam = st.lambda_it;
+          if (robust && P.lambda_cfg <= 0.0 && lam > kLambdaN) {
+            lam *= kLambdaRatio;
+            if (lam < kLambdaN) lam = kLambdaN;
+          }
+          for (int i = 0; i < n; ++i) st.p_prev[i] = st.p[i];
+          update_transform(st.p, dp, ttype);
+          const int itn = st.iter + 1;
+          st.err = err;
+          st.lambda_it = lam;
+          st.total_iters += 1;
+          if (P.traj && st.traj_count < P.traj_cap) {
+            double* t = P.traj + ((long long)pair * P.traj_cap + st.traj_count) * ICA_TRAJ_STRIDE;
+            t[0] = s; t[1] = itn - 1; t[2] = err; t[3] = lam;
+            for (int i = 0; i < ICA_MAX_PARAMS; ++i) t[4 + i] = i < n ? st.p[i] : 0.0;
+            st.traj_count += 1;
+          }
+          if (err > P.tol && itn < P.max_iter) {
+            st.iter = itn;
+          } else {  // this scale is done (ica.py:109, 225)
+            st.iters_per_scale[s] = itn;
+            if (s > 0) {
+              double q[ICA_MAX_PARAMS];
+              const LevelDesc Lf = P.lv[s - 1];
+              zoom_in_parameters(st.p, ttype, (double)nx, (double)ny, (double)Lf.nx, (double)Lf.ny, q);
+              for (int i = 0; i < n; ++i) st.p[i] = q[i];
+              st.scale = s - 1;
+              st.iter = 0;
+              st.lambda_it = P.lambda_cfg > 0.0 ? P.lambda_cfg : kLambda0;  // new call per scale (ica.py:223)
+            } else {
+              st.scale = -1;
+            }
+          }
         }
       }
     }
-    }  // !solved
-    }  // warp 0
+    __syncthreads();
+    if (!P.dbg_Hb && tid < kStateWords)
+      reinterpret_cast<unsigned long long*>(&P.state[pair])[tid] = reinterpret_cast<const unsigned long long*>(&s_st)[tid];
   }
   // ---- the last block builds the next work list
   __threadfence();
@@ -949,6 +942,34 @@ cudaError_t launch_iterate_t(const IterParams& P, int grid, cudaStream_t stream)
 }
 
 }  // namespace
+
+void build_assembly_table(int dh, AsmEntry* tab) {
+  const int hw = dh + 1, bwn = dh / 2 + 1, boff = 3 * hw;
+  for (int i = 0; i < 6 * 72; ++i) for (int q = 0; q < 4; ++q) { tab[i].idx[q] = 0; tab[i].coef[q] = 0.f; }
+  for (int ttype = TRANSLATION; ttype <= HOMOGRAPHY; ++ttype) {
+    if (moment_degree_of(ttype) > dh) continue;
+    Mono jx[ICA_MAX_PARAMS], jy[ICA_MAX_PARAMS];
+    jacobian_monomials(ttype, jx, jy);
+    const int n = nparams_of(ttype);
+    for (int k = 0; k < n; ++k) {
+      for (int l = 0; l < n; ++l) {
+        AsmEntry& e = tab[ttype * 72 + k * 8 + l];
+        const Mono* a[4] = {&jx[k], &jx[k], &jy[k], &jy[k]};
+        const Mono* b[4] = {&jx[l], &jy[l], &jx[l], &jy[l]};
+        const int ij[4] = {0, 1, 1, 2};
+        for (int q = 0; q < 4; ++q) {
+          if (a[q]->coef && b[q]->coef) {
+            e.coef[q] = (float)(a[q]->coef * b[q]->coef);
+            e.idx[q] = (ij[q] * hw + a[q]->a + b[q]->a) * kYPow + a[q]->b + b[q]->b;
+          }
+        }
+      }
+      AsmEntry& e = tab[ttype * 72 + 64 + k];
+      if (jx[k].coef) { e.coef[0] = (float)jx[k].coef; e.idx[0] = (boff + 0 * bwn + jx[k].a) * kYPow + jx[k].b; }
+      if (jy[k].coef) { e.coef[1] = (float)jy[k].coef; e.idx[1] = (boff + 1 * bwn + jy[k].a) * kYPow + jy[k].b; }
+    }
+  }
+}
 
 int iterate_tile_w() { return TW; }
 int iterate_tile_h() { return TH; }

@@ -4,6 +4,9 @@
 
 namespace ica {
 
+// H[k][l] (entry k*8+l) and b[k] (entry 64+k) as +-1 combinations of at most 4 moment sums
+struct AsmEntry { int idx[4]; float coef[4]; };
+
 struct IterParams {
   const float* I1_0;      // level-0 inputs [B][H][W][C]
   const float* I2_0;
@@ -22,6 +25,7 @@ struct IterParams {
   int* n_active;
   int* chunk_start;       // [B+1] work list of the current launch (ica_schedule_kernel)
   int* item_pair;         // [B*max_chunks] pair of each work item
+  const AsmEntry* asm_tab;      // [6 transform codes][72]
   unsigned int* solve_ticket;   // blocks of the solve kernel that are done (the last one schedules)
   int B;
   int max_chunks;         // partial slots per pair
@@ -36,6 +40,7 @@ struct IterParams {
   float ch_mult;          // 3 for a gray image standing for its RGB replication, else 1
 };
 
+void build_assembly_table(int dh, AsmEntry* tab /* [6*72] */);
 int iterate_tile_w();
 int iterate_tile_h();
 int iterate_blocks_per_sm();
