@@ -52,7 +52,8 @@ typedef enum {
 /* flags for ica_config.flags */
 #define ICA_FLAG_RECORD_TRAJECTORY 1u /* keep (scale, iter, |dp|, lambda, p) per iteration */
 #define ICA_FLAG_WRITE_DI_IW 2u       /* produce the DI / Iw images the reference returns */
-#define ICA_FLAG_GRAPH_LOOP 8u        /* iterate inside a CUDA-graph while node (no host polling) */
+#define ICA_FLAG_HOST_LOOP 8u         /* drive the iteration loop from the host (polling) instead of the
+                                         default CUDA-graph while node whose condition is set on the device */
 
 typedef struct ica_config {
   int32_t batch;          /* B independent image pairs per run */
@@ -135,8 +136,10 @@ ICA_API int ica_plan_get_level_device(ica_plan* plan, int32_t which, int32_t pai
                               const float** ptr_out, int32_t* pitch_out);
 /* number of kernels the last run launched (bench.py's gpu_launches) */
 ICA_API int64_t ica_plan_last_launch_count(const ica_plan* plan);
-/* CUDA-event time (ms) spent in the per-iteration kernel / pyramid kernels during the last run
-   (only measured when enabled; adds events, never a sync inside the run) */
+/* Time (ms) spent in the per-iteration kernel / pyramid kernels during the last run.  enable = 1: CUDA events
+   around the pyramid launches, the iterate kernel is timed by device-side %globaltimer stamps (first block start
+   to last block end of every launch) accumulated by the solve kernel, so it also works inside the graph loop;
+   enable = 2: host-driven loop with a CUDA-event pair around every iterate launch (cross-check). */
 ICA_API int ica_plan_enable_timing(ica_plan* plan, int32_t enable);
 ICA_API int ica_plan_get_timing(ica_plan* plan, float* iterate_ms, int32_t* iterate_launches,
                         float* pyramid_ms, int32_t* pyramid_launches);

@@ -322,7 +322,7 @@ class Plan:
         return int(lib().ica_plan_last_launch_count(self._h))
 
     def enable_timing(self, enable=True):
-        check(lib().ica_plan_enable_timing(self._h, 1 if enable else 0))
+        check(lib().ica_plan_enable_timing(self._h, int(enable)))
 
     def timing(self):
         a, b = C.c_float(), C.c_float()

@@ -1,6 +1,7 @@
 // C-ABI of libica_b200.so (see include/ica_b200.h): plan management and entry points.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <math.h>
 #include <algorithm>
@@ -40,6 +41,15 @@ struct ica_plan {
   int* chunk_start = nullptr;
   int* item_pair = nullptr;
   unsigned int* solve_ticket = nullptr;
+  int* loop_count = nullptr;
+  long long* tstamp = nullptr;      // [2] + kernel_ns [2]
+  int* h_loop = nullptr;            // pinned: {iterations, pad} and kernel ns copied after a run
+  long long* h_kns = nullptr;       // pinned [2]
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  const float *graph_I1 = nullptr, *graph_I2 = nullptr;
+  int graph_dh = -1;
+  int use_graph = 1;
   AsmEntry* asm_tab = nullptr;
   int asm_dh = -1;
   long long* dbg_time = nullptr;   // optional per-CTA timeline (ica_plan_debug_timeline)
@@ -164,6 +174,11 @@ void fill_iter_params(const ica_plan* pl, const float* I1, const float* I2, Iter
   P->item_pair = pl->item_pair;
   P->solve_ticket = pl->solve_ticket;
   P->asm_tab = pl->asm_tab;
+  P->cond_handle = 0;
+  P->loop_count = pl->loop_count;
+  P->max_launches = pl->nscales * pl->cfg.max_iter;
+  P->tstamp = pl->tstamp;
+  P->kernel_ns = pl->tstamp + 2;
   P->B = pl->B;
   P->max_chunks = pl->max_chunks;
   P->robust_type = pl->cfg.robust_type;
@@ -174,6 +189,41 @@ void fill_iter_params(const ica_plan* pl, const float* I1, const float* I2, Iter
   P->delta = pl->cfg.delta;
   P->frame = (pl->cfg.nanifoutside != 0 && pl->cfg.delta > 0) ? 1 : 0;
   P->ch_mult = (pl->C == 1 && pl->cfg.gray_as_rgb) ? 3.0f : 1.0f;
+}
+
+// CUDA graph of the iteration loop: one conditional WHILE node whose body is {iterate, solve}; the solve
+// kernel's scheduling block sets the condition on the device, so the whole coarse-to-fine loop of every
+// pair runs without a host round trip.  Rebuilt when the image pointers or the moment degree change.
+int ensure_loop_graph(ica_plan* pl, const float* I1, const float* I2) {
+  if (pl->graph_exec && pl->graph_I1 == I1 && pl->graph_I2 == I2 && pl->graph_dh == pl->dh) return ICA_OK;
+  if (pl->graph_exec) { cudaGraphExecDestroy(pl->graph_exec); pl->graph_exec = nullptr; }
+  if (pl->graph) { cudaGraphDestroy(pl->graph); pl->graph = nullptr; }
+  ICA_CUDA_CHECK(cudaGraphCreate(&pl->graph, 0));
+  cudaGraphConditionalHandle handle;
+  ICA_CUDA_CHECK(cudaGraphConditionalHandleCreate(&handle, pl->graph, 1, cudaGraphCondAssignDefault));
+  cudaGraphNodeParams cp = {};
+  cp.type = cudaGraphNodeTypeConditional;
+  cp.conditional.handle = handle;
+  cp.conditional.type = cudaGraphCondTypeWhile;
+  cp.conditional.size = 1;
+  cudaGraphNode_t node;
+  ICA_CUDA_CHECK(cudaGraphAddNode(&node, pl->graph, nullptr, 0, &cp));
+  cudaGraph_t body = cp.conditional.phGraph_out[0];
+  IterParams P;
+  fill_iter_params(pl, I1, I2, &P);
+  P.cond_handle = (unsigned long long)handle;
+  ICA_CUDA_CHECK(cudaStreamBeginCaptureToGraph(pl->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+  cudaError_t e1 = launch_iterate(P, pl->C, pl->dh, pl->grid, pl->stream);
+  cudaError_t e2 = launch_solve(P, pl->dh, pl->stream);
+  cudaGraph_t captured = nullptr;
+  cudaError_t e3 = cudaStreamEndCapture(pl->stream, &captured);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    set_error("building the loop graph failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    return ICA_ERR_CUDA;
+  }
+  ICA_CUDA_CHECK(cudaGraphInstantiate(&pl->graph_exec, pl->graph, 0));
+  pl->graph_I1 = I1; pl->graph_I2 = I2; pl->graph_dh = pl->dh;
+  return ICA_OK;
 }
 
 // minmax of level 0 and all pyramid levels of both images
@@ -241,7 +291,11 @@ int ica_plan_destroy(ica_plan* pl) {
   if (!pl) return ICA_OK;
   cudaFree(pl->pyr1); cudaFree(pl->pyr2); cudaFree(pl->tmp);
   for (int s = 0; s < ICA_MAX_SCALES; ++s) { free_resample(&pl->ry[s]); free_resample(&pl->rx[s]); }
-  cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->item_pair); cudaFree(pl->solve_ticket); cudaFree(pl->asm_tab); cudaFree(pl->dbg_time); cudaFree(pl->traj); cudaFree(pl->n_active);
+  cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->item_pair); cudaFree(pl->solve_ticket); cudaFree(pl->asm_tab); cudaFree(pl->loop_count); cudaFree(pl->tstamp);
+  if (pl->h_loop) cudaFreeHost(pl->h_loop);
+  if (pl->h_kns) cudaFreeHost(pl->h_kns);
+  if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
+  if (pl->graph) cudaGraphDestroy(pl->graph); cudaFree(pl->dbg_time); cudaFree(pl->traj); cudaFree(pl->n_active);
   if (pl->h_n_active) cudaFreeHost(pl->h_n_active);
   cudaFree(pl->ttypes_dev); cudaFree(pl->p_dev); cudaFree(pl->err_dev); cudaFree(pl->iters_dev);
   cudaFree(pl->in1_dev); cudaFree(pl->in2_dev); cudaFree(pl->raw_dev); cudaFree(pl->DI_dev); cudaFree(pl->Iw_dev);
@@ -318,6 +372,13 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   TRY(dev_alloc(pl, &pl->chunk_start, (size_t)pl->B + 1));
   TRY(dev_alloc(pl, &pl->item_pair, (size_t)pl->B * pl->max_chunks));
   TRY(dev_alloc(pl, &pl->solve_ticket, 1));
+  TRY(dev_alloc(pl, &pl->loop_count, 1));
+  TRY(dev_alloc(pl, &pl->tstamp, 4));
+  TRY_CUDA(cudaMemset(pl->tstamp, 0, 4 * sizeof(long long)));
+  TRY_CUDA(cudaMallocHost((void**)&pl->h_loop, 2 * sizeof(int)));
+  TRY_CUDA(cudaMallocHost((void**)&pl->h_kns, 2 * sizeof(long long)));
+  pl->h_loop[0] = 0; pl->h_kns[0] = 0; pl->h_kns[1] = 0;
+  pl->use_graph = (cfg->flags & ICA_FLAG_HOST_LOOP) ? 0 : (getenv("ICA_NO_GRAPH") ? 0 : 1);
   TRY(dev_alloc(pl, &pl->asm_tab, (size_t)6 * 72));
   TRY(upload_assembly(pl));
   TRY_CUDA(cudaMemset(pl->solve_ticket, 0, sizeof(unsigned int)));
@@ -365,11 +426,14 @@ int ica_plan_level_shapes(const ica_plan* pl, int32_t* nx_out, int32_t* ny_out) 
 }
 
 size_t ica_plan_device_bytes(const ica_plan* pl) { return pl ? pl->device_bytes : 0; }
-int64_t ica_plan_last_launch_count(const ica_plan* pl) { return pl ? pl->launches : 0; }
+int64_t ica_plan_last_launch_count(const ica_plan* pl) {
+  // valid once the run's stream work has completed (the iteration count is copied back asynchronously)
+  return pl ? pl->launches + 2ll * pl->h_loop[0] : 0;
+}
 
 int ica_plan_enable_timing(ica_plan* pl, int32_t enable) {
   if (!pl) return ICA_ERR_INVALID;
-  pl->timing = enable ? 1 : 0;
+  pl->timing = enable < 0 ? 0 : enable;   // 1: events around the pyramid launches; 2: also host loop + events per iterate launch
   if (enable && pl->ev_iter.empty()) {
     const int n_it = 2 * (pl->nscales * pl->cfg.max_iter + 8);
     const int n_py = 4 * pl->nscales * ((pl->B + std::max(1, pl->tmp_images) - 1) / std::max(1, pl->tmp_images)) + 8;
@@ -396,8 +460,11 @@ int ica_plan_get_timing(ica_plan* pl, float* iterate_ms, int32_t* iterate_launch
     ICA_CUDA_CHECK(cudaEventElapsedTime(&ms, pl->ev_pyr[i], pl->ev_pyr[i + 1]));
     py += ms;
   }
+  if (pl->n_ev_iter == 0) {   // graph loop: device-side %globaltimer span of every iterate launch
+    it = (float)(pl->h_kns[0] * 1e-6);
+    if (iterate_launches) *iterate_launches = (int)pl->h_kns[1];
+  } else if (iterate_launches) *iterate_launches = pl->n_ev_iter / 2;
   if (iterate_ms) *iterate_ms = it;
-  if (iterate_launches) *iterate_launches = pl->n_ev_iter / 2;
   if (pyramid_ms) *pyramid_ms = py;
   if (pyramid_launches) *pyramid_launches = pl->n_ev_pyr;  // two kernels per recorded pair
   return ICA_OK;
@@ -416,27 +483,35 @@ int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* 
   IterParams P;
   fill_iter_params(pl, I1, I2, &P);
   const int max_launches = pl->nscales * pl->cfg.max_iter;
-  const int poll_every = 8;
-  int done = 0;
-  // a pair needs at least one launch per scale, so the first poll can wait that long
-  int next_poll = std::max(pl->nscales, poll_every);
   ICA_LAUNCH_CHECK(launch_schedule(P, stream));   // work list of the first iteration
   pl->launches += 1;
-  for (int it = 0; it < max_launches && !done; ++it) {
-    const bool timed = pl->timing && pl->n_ev_iter + 2 <= (int)pl->ev_iter.size();
-    if (timed) cudaEventRecord(pl->ev_iter[pl->n_ev_iter++], stream);
-    ICA_LAUNCH_CHECK(launch_iterate(P, pl->C, pl->dh, pl->grid, stream));
-    if (timed) cudaEventRecord(pl->ev_iter[pl->n_ev_iter++], stream);
-    // per-pair solve / compose; its last block publishes the next work list and the number of unfinished pairs
-    ICA_LAUNCH_CHECK(launch_solve(P, pl->dh, stream));
-    pl->launches += 2;
-    if (it + 1 >= next_poll && it + 1 < max_launches) {
-      ICA_CUDA_CHECK(cudaMemcpyAsync(pl->h_n_active, pl->n_active, sizeof(int), cudaMemcpyDeviceToHost, stream));
-      ICA_CUDA_CHECK(cudaStreamSynchronize(stream));
-      if (*pl->h_n_active <= 0) done = 1;
-      next_poll = it + 1 + poll_every;
+  if (pl->use_graph && pl->timing < 2) {
+    // device-side loop: CUDA-graph while node, condition set by the solve kernel
+    if (int rc = ensure_loop_graph(pl, I1, I2)) return rc;
+    ICA_CUDA_CHECK(cudaGraphLaunch(pl->graph_exec, stream));
+  } else {
+    const int poll_every = 8;
+    int done = 0;
+    // a pair needs at least one launch per scale, so the first poll can wait that long
+    int next_poll = std::max(pl->nscales, poll_every);
+    for (int it = 0; it < max_launches && !done; ++it) {
+      const bool timed = pl->timing >= 2 && pl->n_ev_iter + 2 <= (int)pl->ev_iter.size();
+      if (timed) cudaEventRecord(pl->ev_iter[pl->n_ev_iter++], stream);
+      ICA_LAUNCH_CHECK(launch_iterate(P, pl->C, pl->dh, pl->grid, stream));
+      if (timed) cudaEventRecord(pl->ev_iter[pl->n_ev_iter++], stream);
+      // per-pair solve / compose; its last block publishes the next work list and the number of unfinished pairs
+      ICA_LAUNCH_CHECK(launch_solve(P, pl->dh, stream));
+      if (it + 1 >= next_poll && it + 1 < max_launches) {
+        ICA_CUDA_CHECK(cudaMemcpyAsync(pl->h_n_active, pl->n_active, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        ICA_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (*pl->h_n_active <= 0) done = 1;
+        next_poll = it + 1 + poll_every;
+      }
     }
   }
+  // iterations executed and time spent in the iterate kernel (device-side counters), read lazily by the getters
+  ICA_CUDA_CHECK(cudaMemcpyAsync(pl->h_loop, pl->loop_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  ICA_CUDA_CHECK(cudaMemcpyAsync(pl->h_kns, pl->tstamp + 2, 2 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
   ICA_LAUNCH_CHECK(launch_export_results(pl->state, pl->B, p_inout, pl->err_dev, pl->iters_dev, pl->nscales, stream));
   pl->launches += 1;
   if (pl->cfg.flags & ICA_FLAG_WRITE_DI_IW) {

@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   const int warp = tid >> 5;
   const int total_chunks = P.chunk_start[P.B];
   if ((int)blockIdx.x >= total_chunks) return;
+  if (tid == 0) atomicMin(reinterpret_cast<long long*>(&P.tstamp[0]), gtime());
 
   if (tid == 0) {
     mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
@@ -550,12 +551,13 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
     consumer_sync();   // every warp's shared accumulators may be reused by the CTA's next chunk
   }
   if (P.dbg_time && tid == 32) { P.dbg_time[blockIdx.x * 16 + 13] = gtime(); P.dbg_time[blockIdx.x * 16 + 14] = nitems; }
+  if (tid == 32) atomicMax(reinterpret_cast<long long*>(&P.tstamp[1]), gtime());
 }
 
 // Work list of the next launch: chunk_start[b] = exclusive prefix sum of chunks per pair,
 // chunk_start[B] = total, item_pair[i] = pair of work item i; also publishes the number of
 // unfinished pairs.  Executed by one whole block (any size that is a multiple of 32, <= 1024).
-__device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal) {
+__device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal, bool first) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthr = blockDim.x, nwarp = nthr >> 5;
   const int B = P.B;
@@ -592,13 +594,27 @@ __device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal) {
     if (tid == nthr - 1) s_scal[0] = excl + c;
     __syncthreads();
   }
-  if (tid == 0) { P.chunk_start[B] = s_scal[0]; *P.n_active = s_scal[1]; }
+  if (tid == 0) {
+    P.chunk_start[B] = s_scal[0];
+    *P.n_active = s_scal[1];
+    // device-side bookkeeping of the loop: iterations done, time spent in the iterate kernel, and the
+    // condition of the CUDA-graph while node (no host round trip until every pair has converged)
+    int cnt = 0;
+    if (first) { *P.loop_count = 0; P.kernel_ns[0] = 0; P.kernel_ns[1] = 0; }
+    else {
+      cnt = *P.loop_count + 1; *P.loop_count = cnt;
+      const long long t0 = P.tstamp[0], t1 = P.tstamp[1];
+      if (t1 > t0 && t1 > 0) { P.kernel_ns[0] += t1 - t0; P.kernel_ns[1] += 1; }
+    }
+    P.tstamp[0] = 0x7fffffffffffffffll; P.tstamp[1] = 0;
+    if (!first && P.cond_handle) cudaGraphSetConditional(P.cond_handle, (s_scal[1] > 0 && cnt < P.max_launches) ? 1u : 0u);
+  }
 }
 
 __global__ void __launch_bounds__(1024) ica_schedule_kernel(const IterParams P) {
   __shared__ int s_warp[32];
   __shared__ int s_scal[2];
-  schedule_block(P, s_warp, s_scal);
+  schedule_block(P, s_warp, s_scal, true);
 }
 
 
@@ -806,7 +822,7 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
   __syncthreads();
   if (s_ticket != gridDim.x - 1) return;
   __threadfence();
-  schedule_block(P, s_warp, s_scal);
+  schedule_block(P, s_warp, s_scal, false);
   if (tid == 0) *P.solve_ticket = 0;
 }
 

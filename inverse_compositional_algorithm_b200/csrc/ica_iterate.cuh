@@ -26,6 +26,11 @@ struct IterParams {
   int* chunk_start;       // [B+1] work list of the current launch (ica_schedule_kernel)
   int* item_pair;         // [B*max_chunks] pair of each work item
   const AsmEntry* asm_tab;      // [6 transform codes][72]
+  unsigned long long cond_handle;   // cudaGraphConditionalHandle of the while node (0 outside a graph)
+  int* loop_count;              // iterations executed in this run (device)
+  int max_launches;
+  long long* tstamp;            // [2] min start / max end (%globaltimer) of the current iterate launch
+  long long* kernel_ns;         // [2] accumulated iterate-kernel time (ns) and number of launches of this run
   unsigned int* solve_ticket;   // blocks of the solve kernel that are done (the last one schedules)
   int B;
   int max_chunks;         // partial slots per pair
