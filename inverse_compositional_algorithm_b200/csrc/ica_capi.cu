@@ -59,6 +59,7 @@ struct ica_plan {
   float* tmp = nullptr;
   long long tmp_stride = 0;
   int tmp_images = 0;
+  long long tmp_floats = 0;
   DeviceResample ry[ICA_MAX_SCALES], rx[ICA_MAX_SCALES];
   PairState* state = nullptr;
   MinMaxKeys* mm = nullptr;
@@ -233,7 +234,6 @@ int build_pyramids(ica_plan* pl, const float* I1, const float* I2, cudaStream_t 
   pl->launches += 1;
   const long long n0 = (long long)pl->H * pl->W * pl->C;
   const float* src[2] = {I1, I2};
-  float* pyr[2] = {pl->pyr1, pl->pyr2};
   for (int which = 0; which < 2; ++which) {
     ICA_LAUNCH_CHECK(launch_minmax(src[which], pl->in_stride, n0, B, pl->mm + which, ns * 2, stream));
     pl->launches += 1;
@@ -241,22 +241,25 @@ int build_pyramids(ica_plan* pl, const float* I1, const float* I2, cudaStream_t 
   for (int s = 0; s + 1 < ns; ++s) {
     const LevelDesc& Li = pl->lv[s];
     const LevelDesc& Lo = pl->lv[s + 1];
-    for (int which = 0; which < 2; ++which) {
-      for (int b0 = 0; b0 < B; b0 += pl->tmp_images) {
-        const int nimg = std::min(pl->tmp_images, B - b0);
-        const float* in0 = s == 0 ? src[which] + (long long)b0 * pl->in_stride
-                                  : pyr[which] + (long long)b0 * pl->pyr_stride + Li.offset;
-        const long long istr = s == 0 ? pl->in_stride : pl->pyr_stride;
-        float* out0 = pyr[which] + (long long)b0 * pl->pyr_stride + Lo.offset;
-        int nl = 0;
-        if (pl->timing && pl->n_ev_pyr + 2 <= (int)pl->ev_pyr.size()) cudaEventRecord(pl->ev_pyr[pl->n_ev_pyr++], stream);
-        ICA_LAUNCH_CHECK(launch_pyr_down(in0, istr, Li.pitch, Li.nx, Li.ny, pl->C, pl->ry[s], pl->rx[s], pl->tmp,
-                                         pl->tmp_stride, out0, pl->pyr_stride, Lo.pitch, nimg,
-                                         pl->mm + ((long long)b0 * ns + s) * 2 + which, ns * 2,
-                                         pl->mm + ((long long)b0 * ns + s + 1) * 2 + which, ns * 2, stream, &nl));
-        if (pl->timing && pl->n_ev_pyr + 1 <= (int)pl->ev_pyr.size()) cudaEventRecord(pl->ev_pyr[pl->n_ev_pyr++], stream);
-        pl->launches += nl;
-      }
+    // pairs per launch group: both images of a pair share the launch; the intermediate (vertical-pass) buffer of a
+    // group stays within the budget the plan allocated (L2-resident between the two passes for the big levels)
+    const long long tmp_per_img = (long long)Lo.ny * Li.nx * pl->C;
+    const int group = (int)std::max<long long>(1, std::min<long long>(B, pl->tmp_floats / std::max<long long>(1, 2 * tmp_per_img)));
+    for (int b0 = 0; b0 < B; b0 += group) {
+      const int nset = std::min(group, B - b0);
+      const float* ina = s == 0 ? I1 + (long long)b0 * pl->in_stride : pl->pyr1 + (long long)b0 * pl->pyr_stride + Li.offset;
+      const float* inb = s == 0 ? I2 + (long long)b0 * pl->in_stride : pl->pyr2 + (long long)b0 * pl->pyr_stride + Li.offset;
+      const long long istr = s == 0 ? pl->in_stride : pl->pyr_stride;
+      float* outa = pl->pyr1 + (long long)b0 * pl->pyr_stride + Lo.offset;
+      float* outb = pl->pyr2 + (long long)b0 * pl->pyr_stride + Lo.offset;
+      int nl = 0;
+      if (pl->timing && pl->n_ev_pyr + 2 <= (int)pl->ev_pyr.size()) cudaEventRecord(pl->ev_pyr[pl->n_ev_pyr++], stream);
+      ICA_LAUNCH_CHECK(launch_pyr_down(ina, inb, istr, Li.pitch, Li.nx, Li.ny, pl->C, pl->ry[s], pl->rx[s], pl->tmp,
+                                       tmp_per_img, outa, outb, pl->pyr_stride, Lo.pitch, nset,
+                                       pl->mm + ((long long)b0 * ns + s) * 2, pl->mm + ((long long)b0 * ns + s + 1) * 2,
+                                       ns * 2, stream, &nl));
+      if (pl->timing && pl->n_ev_pyr + 1 <= (int)pl->ev_pyr.size()) cudaEventRecord(pl->ev_pyr[pl->n_ev_pyr++], stream);
+      pl->launches += nl;
     }
   }
   return ICA_OK;
@@ -355,7 +358,9 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
     pl->tmp_stride = (long long)pl->lv[1].ny * pl->lv[0].nx * pl->C;
     const long long budget = 64ll << 20;
     pl->tmp_images = (int)std::max<long long>(1, std::min<long long>(pl->B, budget / std::max<long long>(1, pl->tmp_stride * 4)));
-    TRY(dev_alloc(pl, &pl->tmp, (size_t)pl->tmp_images * pl->tmp_stride));
+    pl->tmp_floats = std::max<long long>((long long)pl->tmp_images * pl->tmp_stride, 2 * pl->tmp_stride);
+    pl->tmp_floats = (pl->tmp_floats + 3) / 4 * 4;
+    TRY(dev_alloc(pl, &pl->tmp, (size_t)pl->tmp_floats));
     for (int s = 0; s + 1 < pl->nscales; ++s) {
       Resample1D r;
       build_resample_1d(pl->lv[s].ny, pl->lv[s + 1].ny, &r);

@@ -158,7 +158,8 @@ __device__ __forceinline__ int skip_range(int i, int lo, int hi) { return i < lo
 
 // ---- vertical pass, general rows: tmp[oy][j] = sum_k Wy[oy][k] * in[sy[oy]+k][j],  j over nx*C floats
 __global__ void __launch_bounds__(256) pyr_vertical_kernel(
-    const float* __restrict__ in0, long long in_stride, int in_pitch, int ncols, int ny_out, int skip_lo, int skip_hi,
+    const float* __restrict__ in0a, const float* __restrict__ in0b, int nset, long long in_stride, int in_pitch,
+    int ncols, int ny_out, int skip_lo, int skip_hi,
     const float* __restrict__ W, const int* __restrict__ start, int taps,
     float* __restrict__ tmp, long long tmp_stride) {
   __shared__ float sw[kVR][kMaxTaps];
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(256) pyr_vertical_kernel(
   int row_lo = sst[0], row_hi = sst[0] + taps;
 #pragma unroll
   for (int r = 1; r < kVR; ++r) { row_lo = min(row_lo, sst[r]); row_hi = max(row_hi, sst[r] + taps); }
-  const float* in = in0 + (long long)img * in_stride + j;
+  const float* in = (img < nset ? in0a + (long long)img * in_stride : in0b + (long long)(img - nset) * in_stride) + j;
   float acc[kVR];
 #pragma unroll
   for (int r = 0; r < kVR; ++r) acc[r] = 0.f;
@@ -210,13 +211,15 @@ __global__ void __launch_bounds__(256) pyr_vertical_kernel(
 // thread, every input row loaded once per thread (LDG.128), weights as constant-bank operands.
 template <int TP>
 __global__ void __launch_bounds__(128) pyr_vertical_fast_kernel(
-    const float* __restrict__ in0, long long in_stride, int in_pitch, int ncols4, int oy_lo, int ngroups, int s0,
+    const float* __restrict__ in0a, const float* __restrict__ in0b, int nset, long long in_stride, int in_pitch,
+    int ncols4, int oy_lo, int ngroups, int s0,
     const FastW fw, float* __restrict__ tmp, long long tmp_stride, int tmp_pitch) {
   const int img = blockIdx.z;
   const int j4 = blockIdx.x * blockDim.x + threadIdx.x;
   if (j4 >= ncols4 || (int)blockIdx.y >= ngroups) return;
   const int oy = oy_lo + blockIdx.y * kFR;
-  const float4* in = reinterpret_cast<const float4*>(in0 + (long long)img * in_stride + (long long)(2 * oy + s0) * in_pitch) + j4;
+  const float* inb = img < nset ? in0a + (long long)img * in_stride : in0b + (long long)(img - nset) * in_stride;
+  const float4* in = reinterpret_cast<const float4*>(inb + (long long)(2 * oy + s0) * in_pitch) + j4;
   const int p4 = in_pitch >> 2;
   float4 acc[kFR];
 #pragma unroll
@@ -263,14 +266,15 @@ template <int C>
 __global__ void __launch_bounds__(256) pyr_horizontal_kernel(
     const float* __restrict__ tmp, long long tmp_stride, int ncols_in, int nx_out, int ny_out, int skip_lo, int skip_hi,
     const float* __restrict__ Wt /* [taps][nx_out] */, const int* __restrict__ start, int taps,
-    float* __restrict__ out0, long long out_stride, int out_pitch,
-    const MinMaxKeys* __restrict__ mm_parent, int mm_parent_stride,
-    MinMaxKeys* __restrict__ mm_child, int mm_child_stride) {
+    float* __restrict__ out0a, float* __restrict__ out0b, int nset, long long out_stride, int out_pitch,
+    const MinMaxKeys* __restrict__ mm_parent, MinMaxKeys* __restrict__ mm_child, int mm_stride) {
   const int img = blockIdx.z;
   const int oy = blockIdx.y;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;   // logical flat index over the general columns
   const int ncol = nx_out - (skip_hi - skip_lo);
-  const MinMaxKeys pk = mm_parent[(long long)img * mm_parent_stride];
+  const int set = img < nset ? 0 : 1, pb = img - set * nset;
+  float* out0 = (set ? out0b : out0a) + (long long)pb * out_stride;
+  const MinMaxKeys pk = mm_parent[(long long)pb * mm_stride + set];
   const float lo = key_float(pk.lo), hi = key_float(pk.hi);
   float val = 0.f;
   const bool active = e < ncol * C;
@@ -282,22 +286,23 @@ __global__ void __launch_bounds__(256) pyr_horizontal_kernel(
     float acc = 0.f;
     for (int k = 0; k < taps; ++k) acc = fmaf(__ldg(Wt + (long long)k * nx_out + ox), __ldg(row + (st + k) * C), acc);
     val = fminf(fmaxf(acc, lo), hi);
-    out0[(long long)img * out_stride + (long long)oy * out_pitch + ox * C + c] = val;
+    out0[(long long)oy * out_pitch + ox * C + c] = val;
   }
-  block_minmax_atomic(val, active, mm_child + (long long)img * mm_child_stride);
+  block_minmax_atomic(val, active, mm_child + (long long)pb * mm_stride + set);
 }
 
 // ---- horizontal pass, uniform columns: kFR consecutive outputs per thread, inputs loaded once
 template <int C, int TP>
 __global__ void __launch_bounds__(128) pyr_horizontal_fast_kernel(
     const float* __restrict__ tmp, long long tmp_stride, int ncols_in, int ox_lo, int ngroups, int s0, const FastW fw,
-    float* __restrict__ out0, long long out_stride, int out_pitch,
-    const MinMaxKeys* __restrict__ mm_parent, int mm_parent_stride,
-    MinMaxKeys* __restrict__ mm_child, int mm_child_stride) {
+    float* __restrict__ out0a, float* __restrict__ out0b, int nset, long long out_stride, int out_pitch,
+    const MinMaxKeys* __restrict__ mm_parent, MinMaxKeys* __restrict__ mm_child, int mm_stride) {
   const int img = blockIdx.z;
   const int oy = blockIdx.y;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;   // (group of kFR columns) * C + channel
-  const MinMaxKeys pk = mm_parent[(long long)img * mm_parent_stride];
+  const int set = img < nset ? 0 : 1, pb = img - set * nset;
+  float* out0 = (set ? out0b : out0a) + (long long)pb * out_stride;
+  const MinMaxKeys pk = mm_parent[(long long)pb * mm_stride + set];
   const float lo = key_float(pk.lo), hi = key_float(pk.hi);
   const bool active = g < ngroups * C;
   float vmin = 0.f, vmax = 0.f;
@@ -317,7 +322,7 @@ __global__ void __launch_bounds__(128) pyr_horizontal_fast_kernel(
         if (k >= 0 && k < TP) acc[r] = fmaf(fw.w[k], v, acc[r]);
       }
     }
-    float* o = out0 + (long long)img * out_stride + (long long)oy * out_pitch + ox * C + c;
+    float* o = out0 + (long long)oy * out_pitch + ox * C + c;
     vmin = 3.4e38f; vmax = -3.4e38f;
 #pragma unroll
     for (int r = 0; r < kFR; ++r) {
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(128) pyr_horizontal_fast_kernel(
     __syncthreads();
     if (threadIdx.x == 0) {
       for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { kmin = min(kmin, smin[w]); kmax = max(kmax, smax[w]); }
-      MinMaxKeys* ck = mm_child + (long long)img * mm_child_stride;
+      MinMaxKeys* ck = mm_child + (long long)pb * mm_stride + set;
       if (kmin <= kmax) { atomicMin(&ck->lo, kmin); atomicMax(&ck->hi, kmax); }
     }
   }
@@ -357,10 +362,19 @@ __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ i
                                                       MinMaxKeys* __restrict__ mm, int mm_stride) {
   const float* img = img0 + (long long)blockIdx.y * stride;
   unsigned kmin = 0xffffffffu, kmax = 0u;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
-    const float v = __ldg(img + i);
-    if (v == v) { const unsigned k = float_key(v); kmin = min(kmin, k); kmax = max(kmax, k); }
+  const bool vec = ((reinterpret_cast<unsigned long long>(img) & 15ull) == 0);
+  const long long n4 = vec ? count / 4 : 0;
+  float fmin_ = 3.4e38f, fmax_ = -3.4e38f;       // NaNs are skipped by fminf/fmaxf (nanmin / nanmax)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(img) + i);
+    fmin_ = fminf(fminf(fmin_, v.x), fminf(v.y, fminf(v.z, v.w)));
+    fmax_ = fmaxf(fmaxf(fmax_, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
   }
+  for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const float v = __ldg(img + i);
+    fmin_ = fminf(fmin_, v); fmax_ = fmaxf(fmax_, v);
+  }
+  if (fmin_ <= fmax_) { kmin = float_key(fmin_); kmax = float_key(fmax_); }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) {
     kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
@@ -394,7 +408,7 @@ cudaError_t launch_minmax_reset(MinMaxKeys* mm, int count, cudaStream_t stream) 
 
 cudaError_t launch_minmax(const float* img0, long long stride, long long count, int nimg, MinMaxKeys* mm,
                           int mm_stride, cudaStream_t stream) {
-  int blocks = (int)std::min<long long>((count + 256 * 8 - 1) / (256 * 8), 64);
+  int blocks = (int)std::min<long long>((count + 256 * 16 - 1) / (256 * 16), 256);
   if (blocks < 1) blocks = 1;
   minmax_kernel<<<dim3(blocks, nimg), 256, 0, stream>>>(img0, stride, count, mm, mm_stride);
   return cudaGetLastError();
@@ -412,56 +426,57 @@ static void fast_groups(const FastRows& f, int n_in, int TP, int* lo, int* ngrou
 }
 
 template <int TP>
-static void launch_vfast(const float* in0, long long in_stride, int in_pitch, int ncols, const FastRows& f, int lo, int ngroups,
-                         float* tmp, long long tmp_stride, int nimg, cudaStream_t stream) {
+static void launch_vfast(const float* in0a, const float* in0b, int nset, long long in_stride, int in_pitch, int ncols,
+                         const FastRows& f, int lo, int ngroups, float* tmp, long long tmp_stride, cudaStream_t stream) {
   FastW fw;
   for (int k = 0; k < kFastTapsMax; ++k) fw.w[k] = f.w[k];
   const int ncols4 = ncols / 4;
-  dim3 grid((ncols4 + 127) / 128, ngroups, nimg);
-  pyr_vertical_fast_kernel<TP><<<grid, 128, 0, stream>>>(in0, in_stride, in_pitch, ncols4, lo, ngroups, f.s0, fw, tmp,
-                                                          tmp_stride, ncols);
+  dim3 grid((ncols4 + 127) / 128, ngroups, 2 * nset);
+  pyr_vertical_fast_kernel<TP><<<grid, 128, 0, stream>>>(in0a, in0b, nset, in_stride, in_pitch, ncols4, lo, ngroups, f.s0, fw,
+                                                          tmp, tmp_stride, ncols);
 }
 
 template <int C, int TP>
 static void launch_hfast(const float* tmp, long long tmp_stride, int ncols, const FastRows& f, int lo, int ngroups, int ny_out,
-                         float* out0, long long out_stride, int out_pitch, int nimg, const MinMaxKeys* mm_parent,
-                         int mm_parent_stride, MinMaxKeys* mm_child, int mm_child_stride, cudaStream_t stream) {
+                         float* out0a, float* out0b, int nset, long long out_stride, int out_pitch,
+                         const MinMaxKeys* mm_parent, MinMaxKeys* mm_child, int mm_stride, cudaStream_t stream) {
   FastW fw;
   for (int k = 0; k < kFastTapsMax; ++k) fw.w[k] = f.w[k];
-  dim3 grid((ngroups * C + 127) / 128, ny_out, nimg);
-  pyr_horizontal_fast_kernel<C, TP><<<grid, 128, 0, stream>>>(tmp, tmp_stride, ncols, lo, ngroups, f.s0, fw, out0, out_stride,
-                                                               out_pitch, mm_parent, mm_parent_stride, mm_child,
-                                                               mm_child_stride);
+  dim3 grid((ngroups * C + 127) / 128, ny_out, 2 * nset);
+  pyr_horizontal_fast_kernel<C, TP><<<grid, 128, 0, stream>>>(tmp, tmp_stride, ncols, lo, ngroups, f.s0, fw, out0a, out0b, nset,
+                                                               out_stride, out_pitch, mm_parent, mm_child, mm_stride);
 }
 
-cudaError_t launch_pyr_down(const float* in0, long long in_stride, int in_pitch, int nx_in, int ny_in, int channels,
-                            const DeviceResample& ry, const DeviceResample& rx, float* tmp, long long tmp_stride,
-                            float* out0, long long out_stride, int out_pitch, int nimg,
-                            const MinMaxKeys* mm_parent, int mm_parent_stride, MinMaxKeys* mm_child,
-                            int mm_child_stride, cudaStream_t stream, int* launches) {
+// One level for `nset` pairs: both image sets (a = I1, b = I2) in the same launches.  mm_parent / mm_child
+// point at the pair's (level, image 0) key of the parent / child level; image 1's key follows it.
+cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_stride, int in_pitch, int nx_in, int ny_in,
+                            int channels, const DeviceResample& ry, const DeviceResample& rx, float* tmp,
+                            long long tmp_stride, float* out0a, float* out0b, long long out_stride, int out_pitch, int nset,
+                            const MinMaxKeys* mm_parent, MinMaxKeys* mm_child, int mm_stride, cudaStream_t stream,
+                            int* launches) {
   const int ncols = nx_in * channels;
   const int ny_out = ry.n_out, nx_out = rx.n_out;
   int nl = 0;
   // ---- vertical pass: uniform interior rows through the fast kernel (needs 16-byte rows), the rest general
   int vlo = 0, vhi = 0;
-  const bool valign = (ncols % 4 == 0) && (in_pitch % 4 == 0) && (in_stride % 4 == 0) &&
-                      ((reinterpret_cast<unsigned long long>(in0) | reinterpret_cast<unsigned long long>(tmp)) & 15ull) == 0 &&
-                      (tmp_stride % 4 == 0);
+  const bool valign = (ncols % 4 == 0) && (in_pitch % 4 == 0) && (in_stride % 4 == 0) && (tmp_stride % 4 == 0) &&
+                      ((reinterpret_cast<unsigned long long>(in0a) | reinterpret_cast<unsigned long long>(in0b) |
+                        reinterpret_cast<unsigned long long>(tmp)) & 15ull) == 0;
   if (valign && ry.fast.hi - ry.fast.lo >= kFR) {
     const int TP = ry.fast.taps <= 32 ? 32 : kFastTapsMax;
     int lo = 0, ngroups = 0;
     fast_groups(ry.fast, ny_in, TP, &lo, &ngroups);
     if (ngroups > 0) {
       vlo = lo; vhi = vlo + ngroups * kFR;
-      if (TP == 32) launch_vfast<32>(in0, in_stride, in_pitch, ncols, ry.fast, lo, ngroups, tmp, tmp_stride, nimg, stream);
-      else launch_vfast<kFastTapsMax>(in0, in_stride, in_pitch, ncols, ry.fast, lo, ngroups, tmp, tmp_stride, nimg, stream);
+      if (TP == 32) launch_vfast<32>(in0a, in0b, nset, in_stride, in_pitch, ncols, ry.fast, lo, ngroups, tmp, tmp_stride, stream);
+      else launch_vfast<kFastTapsMax>(in0a, in0b, nset, in_stride, in_pitch, ncols, ry.fast, lo, ngroups, tmp, tmp_stride, stream);
       ++nl;
     }
   }
   if (ny_out - (vhi - vlo) > 0) {
-    dim3 grid((ncols + 255) / 256, (vlo + kVR - 1) / kVR + (ny_out - vhi + kVR - 1) / kVR, nimg);
-    pyr_vertical_kernel<<<grid, 256, 0, stream>>>(in0, in_stride, in_pitch, ncols, ny_out, vlo, vhi, ry.weights, ry.start,
-                                                   ry.taps, tmp, tmp_stride);
+    dim3 grid((ncols + 255) / 256, (vlo + kVR - 1) / kVR + (ny_out - vhi + kVR - 1) / kVR, 2 * nset);
+    pyr_vertical_kernel<<<grid, 256, 0, stream>>>(in0a, in0b, nset, in_stride, in_pitch, ncols, ny_out, vlo, vhi, ry.weights,
+                                                   ry.start, ry.taps, tmp, tmp_stride);
     ++nl;
   }
   cudaError_t e = cudaGetLastError();
@@ -474,7 +489,7 @@ cudaError_t launch_pyr_down(const float* in0, long long in_stride, int in_pitch,
     fast_groups(rx.fast, nx_in, TP, &lo, &ngroups);
     if (ngroups > 0) {
       hlo = lo; hhi = hlo + ngroups * kFR;
-#define ICA_HF(CC, TT) launch_hfast<CC, TT>(tmp, tmp_stride, ncols, rx.fast, lo, ngroups, ny_out, out0, out_stride, out_pitch, nimg, mm_parent, mm_parent_stride, mm_child, mm_child_stride, stream)
+#define ICA_HF(CC, TT) launch_hfast<CC, TT>(tmp, tmp_stride, ncols, rx.fast, lo, ngroups, ny_out, out0a, out0b, nset, out_stride, out_pitch, mm_parent, mm_child, mm_stride, stream)
       if (channels == 3) { if (TP == 32) ICA_HF(3, 32); else ICA_HF(3, kFastTapsMax); }
       else { if (TP == 32) ICA_HF(1, 32); else ICA_HF(1, kFastTapsMax); }
 #undef ICA_HF
@@ -484,15 +499,15 @@ cudaError_t launch_pyr_down(const float* in0, long long in_stride, int in_pitch,
   if (nx_out - (hhi - hlo) > 0) {
     const int ne = (nx_out - (hhi - hlo)) * channels;
     const int threads = ne >= 256 ? 256 : ((ne + 31) / 32) * 32;
-    dim3 grid((ne + threads - 1) / threads, ny_out, nimg);
+    dim3 grid((ne + threads - 1) / threads, ny_out, 2 * nset);
     if (channels == 3)
       pyr_horizontal_kernel<3><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, ny_out, hlo, hhi, rx.weights_t,
-                                                              rx.start, rx.taps, out0, out_stride, out_pitch, mm_parent,
-                                                              mm_parent_stride, mm_child, mm_child_stride);
+                                                              rx.start, rx.taps, out0a, out0b, nset, out_stride, out_pitch,
+                                                              mm_parent, mm_child, mm_stride);
     else
       pyr_horizontal_kernel<1><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, ny_out, hlo, hhi, rx.weights_t,
-                                                              rx.start, rx.taps, out0, out_stride, out_pitch, mm_parent,
-                                                              mm_parent_stride, mm_child, mm_child_stride);
+                                                              rx.start, rx.taps, out0a, out0b, nset, out_stride, out_pitch,
+                                                              mm_parent, mm_child, mm_stride);
     ++nl;
   }
   if (launches) *launches = nl;

@@ -34,12 +34,12 @@ int max_taps();
 cudaError_t launch_minmax_reset(MinMaxKeys* mm, int count, cudaStream_t stream);
 cudaError_t launch_minmax(const float* img0, long long stride, long long count, int nimg, MinMaxKeys* mm,
                           int mm_stride, cudaStream_t stream);
-// one level for `nimg` images laid out with the given strides; tmp holds ny_out x (nx_in*C) floats per image
-cudaError_t launch_pyr_down(const float* in0, long long in_stride, int in_pitch, int nx_in, int ny_in, int channels,
-                            const DeviceResample& ry, const DeviceResample& rx, float* tmp, long long tmp_stride,
-                            float* out0, long long out_stride, int out_pitch, int nimg,
-                            const MinMaxKeys* mm_parent, int mm_parent_stride, MinMaxKeys* mm_child,
-                            int mm_child_stride, cudaStream_t stream, int* launches = nullptr);
+// one level for `nset` pairs, both image sets per launch; tmp holds ny_out x (nx_in*C) floats per image (2*nset images)
+cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_stride, int in_pitch, int nx_in, int ny_in,
+                            int channels, const DeviceResample& ry, const DeviceResample& rx, float* tmp,
+                            long long tmp_stride, float* out0a, float* out0b, long long out_stride, int out_pitch, int nset,
+                            const MinMaxKeys* mm_parent, MinMaxKeys* mm_child, int mm_stride, cudaStream_t stream,
+                            int* launches = nullptr);
 cudaError_t launch_convert_u8(const unsigned char* in, float* out, long long n, cudaStream_t stream);
 cudaError_t launch_convert_f64(const double* in, float* out, long long n, cudaStream_t stream);
 
