@@ -5,6 +5,7 @@
 #include <string.h>
 #include <math.h>
 #include <algorithm>
+#include <mutex>
 #include <vector>
 #include "ica_common.cuh"
 #include "ica_transform.cuh"
@@ -84,7 +85,7 @@ struct ica_plan {
   long long launches = 0;
   // optional timing
   int timing = 0;
-  cudaEvent_t ev_host0 = nullptr, ev_host1 = nullptr;  // bracket ica_plan_run_host on its stream
+  cudaEvent_t ev_host0 = nullptr, ev_host1 = nullptr, ev_h2d_done = nullptr;  // bracket ica_plan_run_host on its stream
   std::vector<cudaEvent_t> ev_iter, ev_pyr;
   int n_ev_iter = 0, n_ev_pyr = 0;
 };
@@ -169,6 +170,7 @@ void fill_iter_params(const ica_plan* pl, const float* I1, const float* I2, Iter
   P->traj = (pl->cfg.flags & ICA_FLAG_RECORD_TRAJECTORY) ? pl->traj : nullptr;
   P->dbg_Hb = nullptr;
   P->dbg_time = pl->dbg_time;
+  P->dbg_row = pl->grid;
   P->n_active = pl->n_active;
   P->traj_cap = pl->traj_cap;
   P->chunk_start = pl->chunk_start;
@@ -306,6 +308,7 @@ int ica_plan_destroy(ica_plan* pl) {
   for (auto e : pl->ev_pyr) cudaEventDestroy(e);
   if (pl->ev_host0) cudaEventDestroy(pl->ev_host0);
   if (pl->ev_host1) cudaEventDestroy(pl->ev_host1);
+  if (pl->ev_h2d_done) cudaEventDestroy(pl->ev_h2d_done);
   if (pl->stream) cudaStreamDestroy(pl->stream);
   delete pl;
   return ICA_OK;
@@ -403,6 +406,7 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   TRY_CUDA(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
   TRY_CUDA(cudaEventCreate(&pl->ev_host0));
   TRY_CUDA(cudaEventCreate(&pl->ev_host1));
+  TRY_CUDA(cudaEventCreateWithFlags(&pl->ev_h2d_done, cudaEventDisableTiming));
   TRY_CUDA(cudaMemset(pl->state, 0, pl->B * sizeof(PairState)));
 #undef TRY
 #undef TRY_CUDA
@@ -527,6 +531,10 @@ int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* 
   return ICA_OK;
 }
 
+// Host->device copies of concurrent ica_plan_run_host calls (different plans, different threads) take turns on the
+// PCIe link: while one plan's kernels run, the next plan's inputs are copied, instead of all copies first.
+static std::mutex g_h2d_mutex;
+
 static int upload_images(ica_plan* pl, const void* host, int dtype, float* dst, cudaStream_t stream) {
   const long long n = (long long)pl->B * pl->in_stride;
   if (dtype == 0) {
@@ -560,12 +568,17 @@ int ica_plan_run_host(ica_plan* pl, const void* I1_host, const void* I2_host, in
     if (int rc = dev_alloc(pl, &pl->in1_dev, nimg)) return rc;
     if (int rc = dev_alloc(pl, &pl->in2_dev, nimg)) return rc;
   }
-  ICA_CUDA_CHECK(cudaEventRecord(pl->ev_host0, stream));
-  // the dtype staging buffer is reused for the second image only after the first conversion was enqueued
-  if (int rc = upload_images(pl, I1_host, dtype, pl->in1_dev, stream)) return rc;
-  if (int rc = upload_images(pl, I2_host, dtype, pl->in2_dev, stream)) return rc;
-  ICA_CUDA_CHECK(cudaMemcpyAsync(pl->p_dev, p_inout_host, (size_t)pl->B * ICA_MAX_PARAMS * sizeof(double),
-                                 cudaMemcpyHostToDevice, stream));
+  {
+    std::lock_guard<std::mutex> lock(g_h2d_mutex);
+    ICA_CUDA_CHECK(cudaEventRecord(pl->ev_host0, stream));
+    // the dtype staging buffer is reused for the second image only after the first conversion was enqueued
+    if (int rc = upload_images(pl, I1_host, dtype, pl->in1_dev, stream)) return rc;
+    if (int rc = upload_images(pl, I2_host, dtype, pl->in2_dev, stream)) return rc;
+    ICA_CUDA_CHECK(cudaMemcpyAsync(pl->p_dev, p_inout_host, (size_t)pl->B * ICA_MAX_PARAMS * sizeof(double),
+                                   cudaMemcpyHostToDevice, stream));
+    ICA_CUDA_CHECK(cudaEventRecord(pl->ev_h2d_done, stream));
+    ICA_CUDA_CHECK(cudaEventSynchronize(pl->ev_h2d_done));   // the link is free for the next caller
+  }
   const long long conv_launches = pl->launches;
   if (int rc = ica_plan_run_device(pl, pl->in1_dev, pl->in2_dev, pl->p_dev, stream)) return rc;
   pl->launches += (dtype == 0 ? 0 : 2);
@@ -590,7 +603,7 @@ int ica_plan_last_host_run_ms(ica_plan* pl, float* ms_out) {
 
 int ica_plan_debug_timeline(ica_plan* pl, long long* host_out, int32_t enable) {
   if (!pl) return ICA_ERR_INVALID;
-  const size_t n = (size_t)pl->grid * 16;
+  const size_t n = (size_t)(pl->grid + 1) * 16;
   if (enable && !pl->dbg_time) {
     if (int rc = dev_alloc(pl, &pl->dbg_time, n)) return rc;
     ICA_CUDA_CHECK(cudaMemset(pl->dbg_time, 0, n * sizeof(long long)));
@@ -600,7 +613,9 @@ int ica_plan_debug_timeline(ica_plan* pl, long long* host_out, int32_t enable) {
     ICA_CUDA_CHECK(cudaMemcpy(host_out, pl->dbg_time, n * sizeof(long long), cudaMemcpyDeviceToHost));
   }
   if (!enable && pl->dbg_time) { cudaFree(pl->dbg_time); pl->dbg_time = nullptr; }
-  return pl->grid;
+  // the loop graph bakes the kernel arguments: rebuild it next run
+  if (pl->graph_exec) { cudaGraphExecDestroy(pl->graph_exec); pl->graph_exec = nullptr; }
+  return pl->grid + 1;
 }
 
 int ica_plan_get_results(ica_plan* pl, double* p_out, double* err_out, int32_t* iters_out) {

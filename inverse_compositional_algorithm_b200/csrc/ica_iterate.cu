@@ -643,9 +643,12 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
   __shared__ unsigned int s_ticket;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pair = blockIdx.x;
+#define SOLVE_STAMP(slot) do { if (P.dbg_time && blockIdx.x == 0 && tid == 0) P.dbg_time[(long long)P.dbg_row * 16 + (slot)] = gtime(); } while (0)
+  SOLVE_STAMP(0);
   if (tid < kStateWords)
     reinterpret_cast<unsigned long long*>(&s_st)[tid] = __ldcg(reinterpret_cast<const unsigned long long*>(&P.state[pair]) + tid);
   __syncthreads();
+  SOLVE_STAMP(1);
   PairState& st = s_st;
   const int s = st.scale;
   const bool robust = P.robust_loop != 0;
@@ -695,6 +698,7 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
       }
       __syncthreads();
     }
+    SOLVE_STAMP(2);
     if (warp == 0) {   // the n x n part is one warp's job
       const int ttype = st.ttype;
       const int n = nparams_of(ttype);
@@ -712,6 +716,7 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
         }
       }
       __syncwarp();
+      SOLVE_STAMP(3);
       if (P.dbg_Hb) {  // parity hook (ica_hessian_b_host): export, leave the state untouched
         for (int e = lane; e < n * n; e += 32) P.dbg_Hb[e] = s_aug[e / n][e % n];
         if (lane < n) P.dbg_Hb[64 + lane] = s_vec[lane];
@@ -763,6 +768,7 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
           for (int e = lane; e < n * n; e += 32) st.hinv[e] = singular ? 0.0 : s_aug[e / n][n + e % n];
           __syncwarp();
         }
+        SOLVE_STAMP(4);
         if (lane < n) {                                    // io.parametric_solve (io.py:146-155)
           double a = 0.0;
           for (int j = 0; j < n; ++j) a += st.hinv[lane * n + j] * s_vec[j];
@@ -812,6 +818,7 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
       }
     }
     __syncthreads();
+    SOLVE_STAMP(5);
     if (!P.dbg_Hb && tid < kStateWords)
       reinterpret_cast<unsigned long long*>(&P.state[pair])[tid] = reinterpret_cast<const unsigned long long*>(&s_st)[tid];
   }
@@ -822,8 +829,10 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
   __syncthreads();
   if (s_ticket != gridDim.x - 1) return;
   __threadfence();
+  SOLVE_STAMP(6);
   schedule_block(P, s_warp, s_scal, false);
   if (tid == 0) *P.solve_ticket = 0;
+  SOLVE_STAMP(7);
 }
 
 // Resets the per-pair state at the start of a run (ica.py:319-337: ps[0] = p, ps[s>0] = 0;

@@ -20,6 +20,7 @@ struct IterParams {
   const MinMaxKeys* mm;   // [B][nscales][2]  (0 = I1, 1 = I2)
   double* partials;       // [B][max_chunks][kAccStride]
   double* traj;           // [B][traj_cap][ICA_TRAJ_STRIDE] or nullptr
+  int dbg_row;            // row of dbg_time the solve kernel (block 0) stamps
   long long* dbg_time;    // nullptr, or [grid][16] globaltimer stamps of each CTA's first item (profiling hook)
   double* dbg_Hb;         // nullptr, or 72 doubles: H (<=64) then b (8); state left untouched
   int* n_active;

@@ -19,6 +19,7 @@ plan.debug_timeline(True)
 plan.run_host(I1, I2)
 plan.run_host(I1, I2)
 tl = plan.debug_timeline(True, fetch=True)
+solve_row = tl[-1]; tl = tl[:-1]
 act = tl[tl[:, 0] > 0]
 t0 = act[:, 0].min()
 names = ["start", "first_tile_ready", "tiles_done", "partial_written", "ticket", "sums_done", "assembled", "gj_done", "end", "P:decoded", "P:planned", "P:issued", "P:filled", "block_end"]
@@ -32,3 +33,7 @@ for i, nm in enumerate(names):
 end = act[:, 13]; end = end[end > 0] - t0
 print("block_end percentiles (us):", [round(float(np.percentile(end, q)) / 1e3, 1) for q in (0, 10, 25, 50, 75, 90, 99, 100)])
 print("items per block:", np.unique(act[:, 14], return_counts=True))
+
+sr = solve_row
+print("solve kernel block 0 (us since its start): staged %.2f sums %.2f assembled %.2f gj %.2f updated %.2f ticket %.2f scheduled %.2f" % tuple((sr[i] - sr[0]) / 1e3 for i in range(1, 8)))
+print("iterate max end -> solve start: %.2f us" % ((sr[0] - act[:, 13].max()) / 1e3))
