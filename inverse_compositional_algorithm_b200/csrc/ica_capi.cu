@@ -179,6 +179,7 @@ void fill_iter_params(const ica_plan* pl, const float* I1, const float* I2, Iter
   P->asm_tab = pl->asm_tab;
   P->cond_handle = 0;
   P->loop_count = pl->loop_count;
+  P->work_counter = pl->loop_count + 1;
   P->max_launches = pl->nscales * pl->cfg.max_iter;
   P->tstamp = pl->tstamp;
   P->kernel_ns = pl->tstamp + 2;
@@ -380,7 +381,7 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   TRY(dev_alloc(pl, &pl->chunk_start, (size_t)pl->B + 1));
   TRY(dev_alloc(pl, &pl->item_pair, (size_t)pl->B * pl->max_chunks));
   TRY(dev_alloc(pl, &pl->solve_ticket, 1));
-  TRY(dev_alloc(pl, &pl->loop_count, 1));
+  TRY(dev_alloc(pl, &pl->loop_count, 2));
   TRY(dev_alloc(pl, &pl->tstamp, 4));
   TRY_CUDA(cudaMemset(pl->tstamp, 0, 4 * sizeof(long long)));
   TRY_CUDA(cudaMallocHost((void**)&pl->h_loop, 2 * sizeof(int)));

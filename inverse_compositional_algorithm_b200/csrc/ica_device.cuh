@@ -35,7 +35,7 @@ __device__ __forceinline__ bool project_px(const WarpCoef& k, const double* m64,
   float nx_ = fmaf(k.d00, fx, fmaf(k.m01, fy, k.m02)) - fx * zm1;
   float ny_ = fmaf(k.m10, fx, fmaf(k.d11, fy, k.m12)) - fy * zm1;
   float z = 1.0f + zm1;
-  float rz = 1.0f / z;
+  float rz = __frcp_rn(z);     // correctly rounded reciprocal, no slow-path branch
   float dx = nx_ * rz, dy = ny_ * rz;
   bool ok = (z > 0.0f) && (fabsf(dx) < 1.0e6f) && (fabsf(dy) < 1.0e6f);  // false for NaN too
   dx = ok ? dx : 0.0f; dy = ok ? dy : 0.0f;
@@ -72,8 +72,8 @@ __device__ __forceinline__ void keys_weights(float t, float& w0, float& w1, floa
 __device__ __forceinline__ float rho_prime(float t2, float lambda2, int rtype) {
   switch (rtype) {
     case TRUNCATED_QUADRATIC: return t2 < lambda2 ? 1.0f : 0.0f;
-    case GERMAN_MCCLURE: { float d = lambda2 + t2; return lambda2 / (d * d); }
-    case LORENTZIAN: return 1.0f / (lambda2 + t2);
+    case GERMAN_MCCLURE: { float d = lambda2 + t2; return lambda2 * __frcp_rn(d * d); }
+    case LORENTZIAN: return __frcp_rn(lambda2 + t2);
     case CHARBONNIER: return rsqrtf(t2 + lambda2);
     default: return 1.0f;
   }

@@ -69,7 +69,7 @@ struct TileCtl {
   int x0, y0;
   int bx0, by0, bw, bh, fits;
   int nx, ny, pitch;
-  int fill, bulk_ok;
+  int fill, bulk_ok, stop;
   const float* I2;
   const float* I1;
 };
@@ -181,7 +181,12 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
                                               double* pm64, int total_chunks, int lane) {
   constexpr int S1W = Stage<C>::S1W, S2W = Stage<C>::S2W;
   unsigned k = 0;   // tiles staged so far by this CTA
-  for (int item = blockIdx.x; item < total_chunks; item += gridDim.x) {
+  for (;;) {
+    // dynamic work distribution: chunks are handed out by an atomic counter (reset by the scheduler)
+    int item = 0;
+    if (lane == 0) item = atomicAdd(P.work_counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total_chunks) break;
     const int pair = __ldg(P.item_pair + item);
     const int chunk = item - __ldg(P.chunk_start + pair);
     const PairState& st = P.state[pair];
@@ -240,7 +245,7 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
         tc.pair = pair; tc.chunk = chunk; tc.nch = nch; tc.scale = s;
         tc.need_h = need_h; tc.first = tile == t_begin; tc.last = tile + 1 == t_end;
         tc.x0 = x0; tc.y0 = y0; tc.bx0 = bx0; tc.by0 = by0; tc.bw = bw; tc.bh = bh; tc.fits = fits ? 1 : 0;
-        tc.nx = nx; tc.ny = ny; tc.pitch = pitch; tc.I2 = I2; tc.I1 = I1; tc.bulk_ok = bulk_ok ? 1 : 0;
+        tc.nx = nx; tc.ny = ny; tc.pitch = pitch; tc.I2 = I2; tc.I1 = I1; tc.bulk_ok = bulk_ok ? 1 : 0; tc.stop = 0;
         // anything the bulk copies cannot deliver (image borders, ragged ends) is filled by the consumers
         const bool in2 = !fits || (bx0 >= 0 && bx0 + bw <= nx && by0 >= 0 && by0 + bh <= ny);
         const bool in1 = xa1_ >= 0 && xa1_ + S1PX <= nx && y0 - 1 >= 0 && y0 - 1 + S1ROWS <= ny;
@@ -264,6 +269,13 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
       __syncwarp();                       // every lane's ordinary stores precede the arrival
       if (lane == 0) mbar_arrive(bar);    // release; the phase completes when the bulk bytes have landed too
     }
+  }
+  // no more work: hand the consumers a stop marker through the next stage
+  {
+    const int sidx = k & 1;
+    const unsigned use = k >> 1;
+    if (use >= 1) mbar_wait(&empty[sidx], (use - 1) & 1);
+    if (lane == 0) { tctl[sidx].stop = 1; tctl[sidx].fill = 0; mbar_arrive(&full[sidx]); }
   }
 }
 
@@ -314,11 +326,11 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   float* const sc = scratch + warp * SCR;
   double* const accs = reinterpret_cast<double*>(scratch + kConsumerWarps * SCR);   // [kConsumerWarps][K][kYPow]
   double* const myacc = accs + (warp * K + (lane < K ? lane : 0)) * kYPow;
-  const int nitems = (total_chunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   unsigned k = 0;
+  int nitems = 0;
 
   if (P.dbg_time && tid == 0) P.dbg_time[blockIdx.x * 16 + 0] = gtime();
-  for (int it = 0; it < nitems; ++it) {
+  for (int it = 0;; ++it) {
     if (lane < K) {
 #pragma unroll
       for (int b = 0; b < kYPow; ++b) myacc[b] = 0.0;
@@ -326,9 +338,11 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
     int pair, chunk, nch, s, nx, ny;
     bool need_h;
     bool last;
+    bool stop = false;
     do {
       const int sidx = k & 1;
       mbar_wait(&s_full[sidx], (k >> 1) & 1);
+      if (tctl[sidx].stop) { stop = true; break; }   // uniform: the producer ran out of work
       if (k == 0) ICA_STAMP(1);
       // Tile constants stay in shared memory and are re-read (volatile) where they are used: the
       // register file is the scarce resource of this kernel, it must hold the tap loads in flight.
@@ -535,6 +549,8 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
       if (lane == 0) mbar_arrive(&s_empty[sidx]);   // this warp is done with the stage (and its TileCtl)
       ++k;
     } while (!last);
+    if (stop) break;
+    ++nitems;
     ICA_STAMP(2);
 
     // ---------------- chunk partial: [K][kYPow] doubles, warps summed in fixed order
@@ -607,6 +623,7 @@ __device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal, bo
       if (t1 > t0 && t1 > 0) { P.kernel_ns[0] += t1 - t0; P.kernel_ns[1] += 1; }
     }
     P.tstamp[0] = 0x7fffffffffffffffll; P.tstamp[1] = 0;
+    *P.work_counter = 0;
     if (!first && P.cond_handle) cudaGraphSetConditional(P.cond_handle, (s_scal[1] > 0 && cnt < P.max_launches) ? 1u : 0u);
   }
 }

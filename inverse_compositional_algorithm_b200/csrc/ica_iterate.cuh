@@ -29,6 +29,7 @@ struct IterParams {
   const AsmEntry* asm_tab;      // [6 transform codes][72]
   unsigned long long cond_handle;   // cudaGraphConditionalHandle of the while node (0 outside a graph)
   int* loop_count;              // iterations executed in this run (device)
+  int* work_counter;            // next unclaimed work item of the current iterate launch
   int max_launches;
   long long* tstamp;            // [2] min start / max end (%globaltimer) of the current iterate launch
   long long* kernel_ns;         // [2] accumulated iterate-kernel time (ns) and number of launches of this run
