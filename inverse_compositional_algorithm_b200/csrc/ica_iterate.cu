@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(1024) ica_schedule_kernel(const IterParams P) 
 // lambda schedule, the stopping rule and zm.zoom_in_parameters at a scale change
 // (ica.py:223-259, 102-131).  The last block to finish builds the work list of the next
 // iteration (what ica_schedule_kernel does for the first one), so an iteration is two launches.
-constexpr int kSolveThreads = 256;
+constexpr int kSolveThreads = 512;
 constexpr int kSolveWarps = kSolveThreads / 32;
 
 template <int DH>
@@ -675,12 +675,20 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
     const int ntiles = L.tiles_x * L.tiles_y;
     const int nch = ntiles < P.max_chunks ? ntiles : P.max_chunks;
     const bool need_h = P.robust_loop || st.iter == 0;
+    const int ttype = st.ttype;
+    const int n = nparams_of(ttype);
+    // warp 0 fetches its rows of the assembly table now; the latency hides behind the partial sums
+    AsmEntry asm_e[3];
+    if (warp == 0) {
+#pragma unroll
+      for (int m = 0; m < 3; ++m) { const int e = lane + 32 * m; if (e < 72) asm_e[m] = P.asm_tab[ttype * 72 + e]; }
+    }
     {
       // fixed summation order: warp w sums its contiguous range of chunks, then warps in order
       const int c0 = (int)((long long)warp * nch / kSolveWarps), c1 = (int)((long long)(warp + 1) * nch / kSolveWarps);
       const double* src = P.partials + (long long)pair * P.max_chunks * kAccStride;
       constexpr int NJ = (NENT + 31) / 32;
-      constexpr int UN = 4;                                    // chunks in flight per lane
+      constexpr int UN = 8;                                    // chunks in flight per lane
       double sum[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) sum[j] = 0.0;
@@ -717,19 +725,20 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
     }
     SOLVE_STAMP(2);
     if (warp == 0) {   // the n x n part is one warp's job
-      const int ttype = st.ttype;
-      const int n = nparams_of(ttype);
       // assemble H (n x n) and b (n): every entry is a fixed +-1 combination of at most 4 moments
       // (table built on the host from the Jacobian monomials, ica_transform.cuh: assemble_system)
-      for (int e = lane; e < 72; e += 32) {
-        const int kk = e < 64 ? e >> 3 : e - 64, l = e < 64 ? e & 7 : 0;
-        if (kk < n && l < n) {
-          const AsmEntry t = P.asm_tab[ttype * 72 + e];
-          double sum = 0.0;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) if (t.coef[q] != 0.0f) sum += (double)t.coef[q] * s_mom[t.idx[q]];
-          if (e < 64) { s_aug[kk][l] = sum; s_aug[kk][n + l] = (kk == l) ? 1.0 : 0.0; }
-          else s_vec[kk] = sum;
+      for (int m = 0; m < 3; ++m) {
+        const int e = lane + 32 * m;
+        if (e < 72) {
+          const int kk = e < 64 ? e >> 3 : e - 64, l = e < 64 ? e & 7 : 0;
+          double sum = 0.0;
+          if (kk < n && l < n) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (asm_e[m].coef[q] != 0.0f) sum += (double)asm_e[m].coef[q] * s_mom[asm_e[m].idx[q]];
+          }
+          if (e < 64) s_aug[kk][l] = (kk < n && l < n) ? sum : (kk == l ? 1.0 : 0.0);   // identity padding up to 8 x 8
+          else s_vec[kk] = kk < n ? sum : 0.0;
         }
       }
       __syncwarp();
@@ -738,51 +747,44 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
         for (int e = lane; e < n * n; e += 32) P.dbg_Hb[e] = s_aug[e / n][e % n];
         if (lane < n) P.dbg_Hb[64 + lane] = s_vec[lane];
       } else {
-        // de.inverse_hessian: Gauss-Jordan with partial pivoting on [H | I] in shared memory, 4 entries per
-        // lane (element by element the arithmetic of ica_transform.cuh: inverse_hessian); zero matrix when a
-        // pivot is exactly zero (np.linalg.LinAlgError branch, derivatives.py:127-129)
+        // de.inverse_hessian: Gauss-Jordan with partial pivoting on the 8 x 16 matrix [H (+) I | I], lane j
+        // keeps column j in registers: pivot search and row swaps are register-local, each step needs one
+        // broadcast of the pivot column (element by element the arithmetic of ica_transform.cuh:
+        // inverse_hessian; the identity padding leaves the n x n block untouched).  Zero matrix when a pivot
+        // is exactly zero (np.linalg.LinAlgError branch, derivatives.py:127-129).
         if (need_h) {
+          const int j = lane & 15;
+          double a[ICA_MAX_PARAMS];
+#pragma unroll
+          for (int r = 0; r < ICA_MAX_PARAMS; ++r) a[r] = j < ICA_MAX_PARAMS ? s_aug[r][j] : (r == j - ICA_MAX_PARAMS ? 1.0 : 0.0);
           bool singular = false;
-          for (int kk = 0; kk < n; ++kk) {
-            // pivot: largest |a[r][kk]|, r >= kk, first one on ties (lanes 0..7 hold the candidates)
-            double best = (lane >= kk && lane < n) ? fabs(s_aug[lane][kk]) : -1.0;
-            int piv = lane;
 #pragma unroll
-            for (int o = 4; o >= 1; o >>= 1) {
-              const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-              const int op = __shfl_xor_sync(0xffffffffu, piv, o);
-              if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
-            }
-            best = __shfl_sync(0xffffffffu, best, 0); piv = __shfl_sync(0xffffffffu, piv, 0);
+          for (int kk = 0; kk < ICA_MAX_PARAMS; ++kk) {
+            // the lane that holds column kk finds the pivot row (largest |a[r][kk]|, r >= kk, first on ties)
+            int piv = kk;
+            double best = fabs(a[kk]);
+#pragma unroll
+            for (int r = kk + 1; r < ICA_MAX_PARAMS; ++r) { const double vv = fabs(a[r]); if (vv > best) { best = vv; piv = r; } }
+            piv = __shfl_sync(0xffffffffu, piv, kk);
+            best = __shfl_sync(0xffffffffu, best, kk);
             if (!(best > 0.0)) { singular = true; break; }
-            if (piv != kk) {
-              double t0 = 0.0, t1 = 0.0;
-              if (lane < 2 * n) { t0 = s_aug[kk][lane]; t1 = s_aug[piv][lane]; }
-              __syncwarp();
-              if (lane < 2 * n) { s_aug[kk][lane] = t1; s_aug[piv][lane] = t0; }
-              __syncwarp();
-            }
-            const double inv = 1.0 / s_aug[kk][kk];
-            __syncwarp();
-            if (lane < 2 * n) s_aug[kk][lane] *= inv;
-            __syncwarp();
-            double f[4], pk[4];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              const int e = lane + 32 * m, i = e >> 4, j = e & 15;
-              const bool act = i < n && j < 2 * n;
-              f[m] = act ? s_aug[i][kk] : 0.0;
-              pk[m] = act ? s_aug[kk][j] : 0.0;
-            }
-            __syncwarp();
+            for (int r = kk + 1; r < ICA_MAX_PARAMS; ++r) if (r == piv) { const double t = a[kk]; a[kk] = a[r]; a[r] = t; }
+            const double pivval = __shfl_sync(0xffffffffu, a[kk], kk);
+            const double inv = 1.0 / pivval;
+            a[kk] *= inv;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              const int e = lane + 32 * m, i = e >> 4, j = e & 15;
-              if (i < n && j < 2 * n && i != kk && f[m] != 0.0) s_aug[i][j] -= f[m] * pk[m];
+            for (int r = 0; r < ICA_MAX_PARAMS; ++r) {
+              if (r == kk) continue;
+              const double f = __shfl_sync(0xffffffffu, a[r], kk);   // a[r][kk] (column kk is not rescaled except row kk)
+              if (f != 0.0) a[r] -= f * a[kk];
             }
-            __syncwarp();
           }
-          for (int e = lane; e < n * n; e += 32) st.hinv[e] = singular ? 0.0 : s_aug[e / n][n + e % n];
+          if (lane >= ICA_MAX_PARAMS && lane < 2 * ICA_MAX_PARAMS) {
+            const int jc = lane - ICA_MAX_PARAMS;   // column of the inverse
+#pragma unroll
+            for (int r = 0; r < ICA_MAX_PARAMS; ++r) if (r < n && jc < n) st.hinv[r * n + jc] = singular ? 0.0 : a[r];
+          }
           __syncwarp();
         }
         SOLVE_STAMP(4);
