@@ -106,6 +106,29 @@ ICA_API size_t ica_plan_device_bytes(const ica_plan* plan);
 ICA_API int ica_plan_run_device(ica_plan* plan, const float* I1_dev, const float* I2_dev,
                         double* p_inout_dev, void* stream);
 
+/* ---- Row-sharded mode: ONE large pair split across ranks by bands of rows (BASELINE.json configs[4],
+   SURVEY.md 8e).  The sums over pixels of ica.py:95-99 (H) and :101,240-246 (b) are the only global
+   operation of an iteration; they are linear in the pixels, so each rank gathers the moment sums of its
+   band and the caller adds them over ranks (NCCL allreduce of ica_moment_stride() doubles per pair).
+   Every rank holds both full images (pyramid and warps need neighbours across the band edge), performs
+   the identical solve on the identical reduced moments and therefore keeps identical parameters.
+     ica_plan_set_row_shard(plan, rank, nranks)
+     ica_plan_shard_begin(plan, I1, I2, p_in, stream)          pyramids, state, first work list
+     loop: ica_plan_shard_partial(plan, moments, stream)       K2 on this rank's band -> moments[B][stride]
+           <allreduce(moments, SUM) by the caller on the same stream>
+           ica_plan_shard_solve(plan, moments, &n_active, stream)   K3; n_active == 0 ends the loop
+     ica_plan_shard_finish(plan, p_out, stream)                results (and DI/Iw with the flag)          */
+ICA_API int ica_moment_stride(void);
+/* band of tile rows [ty0, ty1) that rank owns at a level with tiles_y rows of tiles (no device needed) */
+ICA_API int ica_row_band(int32_t tiles_y, int32_t rank, int32_t nranks, int32_t* ty0, int32_t* ty1);
+ICA_API int ica_plan_set_row_shard(ica_plan* plan, int32_t rank, int32_t nranks);
+ICA_API int ica_plan_shard_begin(ica_plan* plan, const float* I1_dev, const float* I2_dev,
+                                 const double* p_in_dev, void* stream);
+ICA_API int ica_plan_shard_partial(ica_plan* plan, double* moments_dev, void* stream);
+/* n_active_out may be NULL (no synchronisation); otherwise the stream is synchronised */
+ICA_API int ica_plan_shard_solve(ica_plan* plan, const double* moments_dev, int32_t* n_active_out, void* stream);
+ICA_API int ica_plan_shard_finish(ica_plan* plan, double* p_out_dev, void* stream);
+
 /* Same, from HOST buffers (what the Python drop-in calls): copies inputs host->device, runs,
    copies results back, synchronises.  dtype: 0 = float32, 1 = uint8, 2 = float64 (converted
    to float32 on the device).  Optional outputs may be NULL.

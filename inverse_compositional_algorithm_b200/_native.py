@@ -54,6 +54,13 @@ SIGNATURES = {
     "ica_plan_level_shapes": (C.c_int, [_P, _PI, _PI]),
     "ica_plan_device_bytes": (C.c_size_t, [_P]),
     "ica_plan_run_device": (C.c_int, [_P, _P, _P, _P, _P]),
+    "ica_moment_stride": (C.c_int, []),
+    "ica_row_band": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _PI, _PI]),
+    "ica_plan_set_row_shard": (C.c_int, [_P, C.c_int32, C.c_int32]),
+    "ica_plan_shard_begin": (C.c_int, [_P, _P, _P, _P, _P]),
+    "ica_plan_shard_partial": (C.c_int, [_P, _P, _P]),
+    "ica_plan_shard_solve": (C.c_int, [_P, _P, _PI, _P]),
+    "ica_plan_shard_finish": (C.c_int, [_P, _P, _P]),
     "ica_plan_run_host": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "ica_plan_last_host_run_ms": (C.c_int, [_P, _PF]),
     "ica_plan_debug_timeline": (C.c_int, [_P, _P, C.c_int32]),
@@ -334,6 +341,24 @@ class Plan:
     def run_device(self, I1_ptr: int, I2_ptr: int, p_ptr: int, stream: int = 0):
         """Device pointers (ints): float32 [B][H][W][C] x2, double [B][8]."""
         check(lib().ica_plan_run_device(self._h, _P(I1_ptr), _P(I2_ptr), _P(p_ptr), _P(stream)))
+
+    # ---- row-sharded mode (one large pair over several ranks; include/ica_b200.h)
+    def set_row_shard(self, rank: int, nranks: int):
+        check(lib().ica_plan_set_row_shard(self._h, int(rank), int(nranks)))
+
+    def shard_begin(self, I1_ptr: int, I2_ptr: int, p_ptr: int, stream: int = 0):
+        check(lib().ica_plan_shard_begin(self._h, _P(I1_ptr), _P(I2_ptr), _P(p_ptr), _P(stream)))
+
+    def shard_partial(self, moments_ptr: int, stream: int = 0):
+        check(lib().ica_plan_shard_partial(self._h, _P(moments_ptr), _P(stream)))
+
+    def shard_solve(self, moments_ptr: int, stream: int = 0, poll: bool = True) -> int:
+        n = C.c_int32(-1)
+        check(lib().ica_plan_shard_solve(self._h, _P(moments_ptr), C.byref(n) if poll else None, _P(stream)))
+        return n.value
+
+    def shard_finish(self, p_ptr: int, stream: int = 0):
+        check(lib().ica_plan_shard_finish(self._h, _P(p_ptr), _P(stream)))
 
     def results(self):
         p = np.zeros((self.batch, MAX_PARAMS))

@@ -39,6 +39,7 @@ struct ica_plan {
   ica_config cfg;
   int B, H, W, C, nscales, dh;
   int max_chunks = 0, grid = 0;
+  int shard_rank = 0, shard_n = 1;   // row-sharded mode (ica_plan_set_row_shard)
   int* chunk_start = nullptr;
   int* item_pair = nullptr;
   unsigned int* solve_ticket = nullptr;
@@ -183,6 +184,8 @@ void fill_iter_params(const ica_plan* pl, const float* I1, const float* I2, Iter
   P->max_launches = pl->nscales * pl->cfg.max_iter;
   P->tstamp = pl->tstamp;
   P->kernel_ns = pl->tstamp + 2;
+  P->shard_rank = pl->shard_rank; P->shard_n = pl->shard_n;
+  P->solve_mode = 0; P->ext_moments = nullptr;
   P->B = pl->B;
   P->max_chunks = pl->max_chunks;
   P->robust_type = pl->cfg.robust_type;
@@ -480,8 +483,85 @@ int ica_plan_get_timing(ica_plan* pl, float* iterate_ms, int32_t* iterate_launch
   return ICA_OK;
 }
 
+// ---- row-sharded mode: one (large) pair per plan entry, split by bands of tile rows across ranks.  Every rank
+// holds both full images and runs the whole pipeline except that K2 only visits its band; the caller sums the
+// per-pair moment vectors over ranks (NCCL allreduce) between ica_plan_shard_partial and ica_plan_shard_solve,
+// after which every rank performs the identical solve and keeps an identical state.
+int ica_moment_stride(void) { return kAccStride; }
+
+int ica_row_band(int32_t tiles_y, int32_t rank, int32_t nranks, int32_t* ty0, int32_t* ty1) {
+  if (tiles_y < 0 || nranks < 1 || rank < 0 || rank >= nranks) { set_error("invalid band request"); return ICA_ERR_INVALID; }
+  if (ty0) *ty0 = (int)((long long)rank * tiles_y / nranks);
+  if (ty1) *ty1 = (int)((long long)(rank + 1) * tiles_y / nranks);
+  return ICA_OK;
+}
+
+int ica_plan_set_row_shard(ica_plan* pl, int32_t rank, int32_t nranks) {
+  if (!pl || nranks < 1 || rank < 0 || rank >= nranks) { set_error("invalid row shard (rank %d of %d)", rank, nranks); return ICA_ERR_INVALID; }
+  pl->shard_rank = rank; pl->shard_n = nranks;
+  if (pl->graph_exec) { cudaGraphExecDestroy(pl->graph_exec); pl->graph_exec = nullptr; }   // kernel arguments are baked in
+  return ICA_OK;
+}
+
+int ica_plan_shard_begin(ica_plan* pl, const float* I1, const float* I2, const double* p_in, void* stream_) {
+  if (!pl || !I1 || !I2 || !p_in) { set_error("NULL argument"); return ICA_ERR_INVALID; }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  pl->launches = 0; pl->n_ev_iter = 0; pl->n_ev_pyr = 0;
+  pl->last_I1 = I1; pl->last_I2 = I2;
+  if (int rc = build_pyramids(pl, I1, I2, stream)) return rc;
+  ICA_LAUNCH_CHECK(launch_init_state(pl->state, p_in, pl->ttypes_dev, pl->B, pl->nscales, pl->cfg.lambda_, pl->n_active, stream));
+  IterParams P;
+  fill_iter_params(pl, I1, I2, &P);
+  ICA_LAUNCH_CHECK(launch_schedule(P, stream));
+  pl->launches += 2;
+  return ICA_OK;
+}
+
+int ica_plan_shard_partial(ica_plan* pl, double* moments, void* stream_) {
+  if (!pl || !moments || !pl->last_I1) { set_error("ica_plan_shard_begin must be called first"); return ICA_ERR_INVALID; }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IterParams P;
+  fill_iter_params(pl, pl->last_I1, pl->last_I2, &P);
+  P.solve_mode = 1; P.ext_moments = moments;
+  ICA_LAUNCH_CHECK(launch_iterate(P, pl->C, pl->dh, pl->grid, stream));
+  ICA_LAUNCH_CHECK(launch_solve(P, pl->dh, stream));
+  pl->launches += 2;
+  return ICA_OK;
+}
+
+int ica_plan_shard_solve(ica_plan* pl, const double* moments, int32_t* n_active_out, void* stream_) {
+  if (!pl || !moments || !pl->last_I1) { set_error("ica_plan_shard_begin must be called first"); return ICA_ERR_INVALID; }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IterParams P;
+  fill_iter_params(pl, pl->last_I1, pl->last_I2, &P);
+  P.solve_mode = 2; P.ext_moments = const_cast<double*>(moments);
+  ICA_LAUNCH_CHECK(launch_solve(P, pl->dh, stream));
+  pl->launches += 1;
+  if (n_active_out) {
+    ICA_CUDA_CHECK(cudaMemcpyAsync(pl->h_n_active, pl->n_active, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    ICA_CUDA_CHECK(cudaStreamSynchronize(stream));
+    *n_active_out = *pl->h_n_active;
+  }
+  return ICA_OK;
+}
+
+int ica_plan_shard_finish(ica_plan* pl, double* p_out, void* stream_) {
+  if (!pl || !p_out || !pl->last_I1) { set_error("ica_plan_shard_begin must be called first"); return ICA_ERR_INVALID; }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ICA_CUDA_CHECK(cudaMemcpyAsync(pl->h_loop, pl->loop_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  ICA_LAUNCH_CHECK(launch_export_results(pl->state, pl->B, p_out, pl->err_dev, pl->iters_dev, pl->nscales, stream));
+  pl->launches += 1;
+  if (pl->cfg.flags & ICA_FLAG_WRITE_DI_IW) {
+    ICA_LAUNCH_CHECK(launch_warp_out(pl->last_I1, pl->last_I2, pl->in_stride, pl->W, pl->H, pl->C, pl->state, pl->mm, pl->nscales,
+                                     pl->B, pl->Iw_dev, pl->DI_dev, stream));
+    pl->launches += 1;
+  }
+  return ICA_OK;
+}
+
 int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* p_inout, void* stream_) {
   if (!pl || !I1 || !I2 || !p_inout) { set_error("NULL argument"); return ICA_ERR_INVALID; }
+  if (pl->shard_n != 1) { set_error("the plan is row-sharded: use ica_plan_shard_begin/partial/solve/finish"); return ICA_ERR_INVALID; }
   cudaStream_t stream = (cudaStream_t)stream_;
   pl->launches = 0;
   pl->n_ev_iter = 0; pl->n_ev_pyr = 0;

@@ -40,6 +40,14 @@ struct LevelDesc {
   int tiles_x, tiles_y; // tiling used by the per-iteration kernel
 };
 
+// Row-sharded mode (one large pair split across ranks): rank r of n owns the tile rows [ty0, ty1) of every
+// level; first = index of its first tile, return value = number of its tiles (n = 1: the whole level).
+__host__ __device__ inline int band_tiles(const LevelDesc& L, int rank, int n, int* first) {
+  const int ty0 = (int)((long long)rank * L.tiles_y / n), ty1 = (int)((long long)(rank + 1) * L.tiles_y / n);
+  *first = ty0 * L.tiles_x;
+  return (ty1 - ty0) * L.tiles_x;
+}
+
 // Device-side state of one image pair (one "registration").
 struct PairState {
   double p[ICA_MAX_PARAMS];       // current parameters at `scale`

@@ -205,10 +205,11 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
     const float* __restrict__ I2 = s == 0 ? P.I2_0 + (long long)pair * P.in_stride
                                           : P.pyr2 + (long long)pair * P.pyr_stride + L.offset;
     const bool bulk_ok = (pitch & 3) == 0 && ((((unsigned long long)I1) | ((unsigned long long)I2)) & 15ull) == 0;
-    const int ntiles = L.tiles_x * L.tiles_y;
+    int t_first;
+    const int ntiles = band_tiles(L, P.shard_rank, P.shard_n, &t_first);
     const int nch = ntiles < P.max_chunks ? ntiles : P.max_chunks;
-    const int t_begin = (int)((long long)chunk * ntiles / nch);
-    const int t_end = (int)((long long)(chunk + 1) * ntiles / nch);
+    const int t_begin = t_first + (int)((long long)chunk * ntiles / nch);
+    const int t_end = t_first + (int)((long long)(chunk + 1) * ntiles / nch);
 
     if (P.dbg_time && k == 0 && lane == 0) P.dbg_time[blockIdx.x * 16 + 9] = gtime();
     for (int tile = t_begin; tile < t_end; ++tile, ++k) {
@@ -582,11 +583,13 @@ __device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal, bo
   for (int base = 0; base < B; base += nthr) {
     const int b = base + tid;
     int c = 0;
+    bool act = false;   // a rank whose band is empty at a coarse level still counts the pair as unfinished
     if (b < B) {
       const int s = __ldcg(&P.state[b].scale);
-      if (s >= 0) { const int nt = P.lv[s].tiles_x * P.lv[s].tiles_y; c = nt < P.max_chunks ? nt : P.max_chunks; }
+      if (s >= 0) { int tf; const int nt = band_tiles(P.lv[s], P.shard_rank, P.shard_n, &tf); c = nt < P.max_chunks ? nt : P.max_chunks; }
+      act = s >= 0;
     }
-    const unsigned actmask = __ballot_sync(0xffffffffu, c > 0);
+    const unsigned actmask = __ballot_sync(0xffffffffu, act);
     int incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -672,7 +675,8 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
   if (s >= 0) {   // the pair took part in the iteration that just ran
     const LevelDesc L = P.lv[s];
     const int nx = L.nx, ny = L.ny;
-    const int ntiles = L.tiles_x * L.tiles_y;
+    int t_first;
+    const int ntiles = band_tiles(L, P.shard_rank, P.shard_n, &t_first);
     const int nch = ntiles < P.max_chunks ? ntiles : P.max_chunks;
     const bool need_h = P.robust_loop || st.iter == 0;
     const int ttype = st.ttype;
@@ -683,7 +687,10 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
 #pragma unroll
       for (int m = 0; m < 3; ++m) { const int e = lane + 32 * m; if (e < 72) asm_e[m] = P.asm_tab[ttype * 72 + e]; }
     }
-    {
+    if (P.solve_mode == 2) {   // row-sharded: the moments were summed over ranks by the caller's allreduce
+      if (tid < NENT) s_mom[tid] = P.ext_moments[(long long)pair * kAccStride + tid];
+      __syncthreads();
+    } else {
       // fixed summation order: warp w sums its contiguous range of chunks, then warps in order
       const int c0 = (int)((long long)warp * nch / kSolveWarps), c1 = (int)((long long)(warp + 1) * nch / kSolveWarps);
       const double* src = P.partials + (long long)pair * P.max_chunks * kAccStride;
@@ -724,6 +731,10 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
       __syncthreads();
     }
     SOLVE_STAMP(2);
+    if (P.solve_mode == 1) {   // row-sharded: publish this rank's moment sums and stop
+      if (tid < kAccStride) P.ext_moments[(long long)pair * kAccStride + tid] = tid < NENT ? s_mom[tid] : 0.0;
+      return;
+    }
     if (warp == 0) {   // the n x n part is one warp's job
       // assemble H (n x n) and b (n): every entry is a fixed +-1 combination of at most 4 moments
       // (table built on the host from the Jacobian monomials, ica_transform.cuh: assemble_system)
@@ -840,6 +851,10 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
     SOLVE_STAMP(5);
     if (!P.dbg_Hb && tid < kStateWords)
       reinterpret_cast<unsigned long long*>(&P.state[pair])[tid] = reinterpret_cast<const unsigned long long*>(&s_st)[tid];
+  }
+  else if (P.solve_mode == 1) {
+    if (tid < kAccStride) P.ext_moments[(long long)pair * kAccStride + tid] = 0.0;
+    return;
   }
   // ---- the last block builds the next work list
   __threadfence();

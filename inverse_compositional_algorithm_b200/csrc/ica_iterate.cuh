@@ -34,6 +34,9 @@ struct IterParams {
   long long* tstamp;            // [2] min start / max end (%globaltimer) of the current iterate launch
   long long* kernel_ns;         // [2] accumulated iterate-kernel time (ns) and number of launches of this run
   unsigned int* solve_ticket;   // blocks of the solve kernel that are done (the last one schedules)
+  int shard_rank, shard_n;      // row-sharded mode: this rank's band of tile rows (0, 1 = whole image)
+  int solve_mode;               // 0: sum partials + solve; 1: sum partials -> ext_moments only; 2: solve from ext_moments
+  double* ext_moments;          // [B][kAccStride] moment sums exchanged between ranks (row-sharded mode)
   int B;
   int max_chunks;         // partial slots per pair
   int traj_cap;

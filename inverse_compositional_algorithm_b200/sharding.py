@@ -48,3 +48,112 @@ def register_sharded(I1, I2, transform_types, register_fn, *, group=None):
     dist.all_gather(out, buf, group=group)
     full = np.concatenate([o.cpu().numpy()[:b - a] for o, (a, b) in zip(out, sizes)])
     return full[:, :8], full[:, 8], full[:, 9:].astype(np.int32)
+
+
+# ---------------------------------------------------------------------------------------------
+# Row-sharded registration of ONE large pair (BASELINE.json configs[4]).
+# The reference sums H (ica.py:95-99) and b (ica.py:101, 240-246) over all pixels; that sum is the only
+# global step of an iteration.  Each rank gathers the moment sums of its band of rows on its own GPU, the
+# ranks add them with one allreduce (NCCL: 105 doubles per pair), and every rank performs the identical
+# solve / update on the identical sums.  Both full images live on every rank.
+# ---------------------------------------------------------------------------------------------
+_ROW_PLANS = {}   # plans of register_row_sharded, reused between calls (device buffers, pyramid operators)
+
+
+def row_band(tiles_y: int, rank: int, nranks: int):
+    """Band ``[ty0, ty1)`` of tile rows that ``rank`` owns (same arithmetic as the kernels)."""
+    import ctypes as C
+    from . import _native
+    a, b = C.c_int32(), C.c_int32()
+    _native.check(_native.lib().ica_row_band(int(tiles_y), int(rank), int(nranks), C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def register_row_sharded(I1, I2, transform_type, *, nscales=5, nu=0.5, robust_type=0, robust_loop=None,
+                         lambda_=0.0, tol=1e-3, max_iter=30, delta=5, nanifoutside=True,
+                         gray_as_rgb=True, p0=None, group=None, emulate_ranks=None, stats=None):
+    """Registers one image pair with the pixels of every iteration split by rows over the ranks of
+    ``group`` (``torch.distributed``, NCCL).  ``I1``/``I2``: float32 CUDA tensors ``[H, W, C]`` (the full
+    images, on every rank).  Returns ``(p [8], err, iters [nscales])``, identical on all ranks.
+
+    ``emulate_ranks=W`` runs W bands one after the other on the current GPU and adds their moments
+    locally -- the same kernels and band arithmetic without a process group (used by the tests).
+    ``stats`` (a dict) receives ``iterations`` and, when timing was requested through
+    ``stats={"time": True}``, the CUDA-event time of every allreduce in ms (``allreduce_ms``)."""
+    import torch
+    import torch.distributed as dist
+    from . import _native
+    from .image_optimisation import RobustErrorFunctionType
+
+    if I1.dim() != 3 or I1.shape != I2.shape or I1.dtype != torch.float32 or not I1.is_cuda:
+        raise ValueError("I1 and I2 must be float32 CUDA tensors of the same [H, W, C] shape")
+    I1, I2 = I1.contiguous(), I2.contiguous()
+    H, W, Cn = (int(v) for v in I1.shape)
+    rt = RobustErrorFunctionType(getattr(robust_type, "value", robust_type)).value
+    if robust_loop is None:
+        robust_loop = rt != 0
+    if emulate_ranks:
+        world, ranks = int(emulate_ranks), list(range(int(emulate_ranks)))
+    else:
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        ranks = [dist.get_rank(group) if dist.is_initialized() else 0]
+    plans = []
+    for r in ranks:
+        key = (torch.cuda.current_device(), H, W, Cn, nscales, nu, int(getattr(transform_type, "value", transform_type)),
+               rt, bool(robust_loop), lambda_, tol, max_iter, delta, bool(nanifoutside), bool(gray_as_rgb), r, world)
+        if key in _ROW_PLANS:
+            plans.append(_ROW_PLANS[key])
+            continue
+        pl = _native.Plan(batch=1, height=H, width=W, channels=Cn, nscales=nscales, nu=nu,
+                          transform_type=int(getattr(transform_type, "value", transform_type)), robust_type=rt, robust_loop=bool(robust_loop),
+                          lambda_=lambda_, tol=tol, max_iter=max_iter, delta=delta,
+                          nanifoutside=nanifoutside, gray_as_rgb=bool(gray_as_rgb) and Cn == 1)
+        pl.set_row_shard(r, world)
+        if len(_ROW_PLANS) >= 16:
+            _ROW_PLANS.pop(next(iter(_ROW_PLANS))).close()
+        _ROW_PLANS[key] = pl
+        plans.append(pl)
+    dev = I1.device
+    stride = int(_native.lib().ica_moment_stride())
+    p_dev = torch.zeros((1, 8), dtype=torch.float64, device=dev)
+    if p0 is not None:
+        p0 = np.asarray(p0, dtype=np.float64)
+        p_dev[0, :p0.size] = torch.from_numpy(p0).to(dev)
+    moments = [torch.zeros((1, stride), dtype=torch.float64, device=dev) for _ in plans]
+    stream = torch.cuda.current_stream().cuda_stream
+    want_time = bool(stats is not None and stats.get("time"))
+    ar_events = []
+    for pl in plans:
+        pl.shard_begin(I1.data_ptr(), I2.data_ptr(), p_dev.data_ptr(), stream)
+    n_active, it = 1, 0
+    while n_active > 0 and it < nscales * max_iter:
+        for pl, m in zip(plans, moments):
+            pl.shard_partial(m.data_ptr(), stream)
+        if want_time:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        if emulate_ranks:
+            total = moments[0]
+            for m in moments[1:]:
+                total = total + m          # fixed order, like a ring over ranks 0..W-1
+        else:
+            total = moments[0]
+            if world > 1:
+                dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        if want_time:
+            e1.record()
+            ar_events.append((e0, e1))
+        for pl in plans:
+            n_active = pl.shard_solve(total.data_ptr(), stream)
+        it += 1
+    out = torch.zeros((1, 8), dtype=torch.float64, device=dev)
+    for pl in plans:
+        pl.shard_finish(out.data_ptr(), stream)
+    torch.cuda.current_stream().synchronize()
+    p, err, iters = plans[0].results()
+    if stats is not None:
+        stats["iterations"] = it
+        stats["world"] = world
+        if want_time:
+            stats["allreduce_ms"] = [a.elapsed_time(b) for a, b in ar_events]
+    return p[0], float(err[0]), iters[0]

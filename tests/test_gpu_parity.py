@@ -339,3 +339,80 @@ def test_full_size_c2_properties(nat):
     assert _epe(a[0][0], p_gt, t.value, 1024, 1024) <= 0.05
     c = register_batch(I2[None], I2[None], t, nscales=5, robust_type=3, delta=10)
     assert _epe(c[0][0], np.zeros(8), t.value, 1024, 1024) <= 1e-6
+
+
+# ------------------------------------------------------------------ row-sharded single pair (BASELINE config 5)
+@pytest.mark.parametrize("shape,channels,world,rtype", [((200, 256), 3, 3, 3), ((96, 128), 1, 8, 0),
+                                                        ((300, 200), 1, 2, 2)])
+def test_row_sharded_equals_unsharded(nat, shape, channels, world, rtype):
+    """One pair split by bands of rows over `world` ranks (emulated one after the other on this GPU, same
+    kernels and band arithmetic as the NCCL path): the moments summed over bands equal the unsharded sums up
+    to fp64 regrouping, so iteration counts are identical and the motion agrees to far below the parity bar.  world = 8 on a
+    small image leaves some ranks without tiles at the coarse levels."""
+    import torch
+    from inverse_compositional_algorithm_b200 import synthetic
+    from inverse_compositional_algorithm_b200.inverse_compositional_algorithm import register_batch
+    from inverse_compositional_algorithm_b200.sharding import register_row_sharded
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    t = TransformType.HOMOGRAPHY
+    h, w = shape
+    I1, I2, p_gt = synthetic.make_pair(500 + world, h, w, channels, t, max_shift=3.0, margin=32)
+    ref_p, ref_err, ref_it = register_batch(I1[None], I2[None], t, nscales=3, robust_type=rtype, delta=5)
+    stats = {}
+    p, err, iters = register_row_sharded(torch.from_numpy(I1).cuda(), torch.from_numpy(I2).cuda(), t, nscales=3,
+                                         robust_type=rtype, delta=5, emulate_ranks=world, stats=stats)
+    assert np.array_equal(iters, ref_it[0])
+    assert stats["iterations"] == int(ref_it[0].sum())
+    epe = _epe(p, ref_p[0], t.value, w, h)
+    assert epe <= 1e-6, epe          # fp64 regrouping of the sums, amplified by cond(H) of a homography
+    assert abs(err - ref_err[0]) <= 1e-6
+
+
+_NCCL_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch
+import torch.distributed as dist
+from inverse_compositional_algorithm_b200 import synthetic
+from inverse_compositional_algorithm_b200.sharding import register_row_sharded
+from inverse_compositional_algorithm_b200.transformation import TransformType
+rank = int(sys.argv[3])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=rank, world_size=2)
+t = TransformType.HOMOGRAPHY
+I1, I2, _ = synthetic.make_pair(901, 384, 512, 1, t, max_shift=3.0, margin=32)
+p, err, iters = register_row_sharded(torch.from_numpy(I1).cuda(), torch.from_numpy(I2).cuda(), t, nscales=3,
+                                     robust_type=3, delta=5)
+np.savez(sys.argv[4] % rank, p=p, err=err, iters=iters)
+dist.barrier(); dist.destroy_process_group()
+print("ok")
+"""
+
+
+def test_row_sharded_nccl_two_gpus(nat, tmp_path):
+    """The real thing on two GPUs: per-iteration NCCL allreduce of the moment sums; both ranks end with
+    identical parameters, equal to the single-GPU run."""
+    import os, subprocess, sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from inverse_compositional_algorithm_b200 import synthetic
+    from inverse_compositional_algorithm_b200.inverse_compositional_algorithm import register_batch
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(_NCCL_WORKER)
+    out = str(tmp_path / "rank%d.npz")
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), root, port, str(r), out], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "ok" in o, o
+    r0, r1 = np.load(out % 0), np.load(out % 1)
+    assert np.array_equal(r0["p"], r1["p"]) and np.array_equal(r0["iters"], r1["iters"])
+    t = TransformType.HOMOGRAPHY
+    I1, I2, _ = synthetic.make_pair(901, 384, 512, 1, t, max_shift=3.0, margin=32)
+    ref_p, _, ref_it = register_batch(I1[None], I2[None], t, nscales=3, robust_type=3, delta=5)
+    assert np.array_equal(r0["iters"], ref_it[0])
+    assert _epe(r0["p"], ref_p[0], t.value, 512, 384) <= 1e-6

@@ -159,6 +159,21 @@ def test_shard_range_partitions():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_row_band_partitions():
+    """Row-sharded mode: the bands of tile rows of the ranks tile [0, tiles_y) without overlap (some may be
+    empty when there are fewer tile rows than ranks)."""
+    from inverse_compositional_algorithm_b200.sharding import row_band
+    for tiles_y in (0, 1, 5, 74, 586):
+        for w in (1, 2, 3, 8):
+            bands = [row_band(tiles_y, r, w) for r in range(w)]
+            assert bands[0][0] == 0 and bands[-1][1] == tiles_y
+            assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+            sizes = [b - a for a, b in bands]
+            assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        row_band(4, 2, 2)
+
+
 _GLOO_WORKER = r'''
 import os, sys
 sys.path.insert(0, sys.argv[1])
