@@ -224,28 +224,33 @@ def run_ours(args, wl):
         sp.set_transform_types([t.value for t in types[lo_:hi_]])
         subs.append(dict(plan=sp, stream=torch.cuda.Stream(device=dev), i1=I1[lo_:hi_], i2=I2[lo_:hi_], p=p_dev[lo_:hi_]))
 
-    def step_streams():
-        p_dev.zero_()
+    def run_steps(nsteps):
+        """Enqueues `nsteps` passes over the batch.  Each sub-batch advances through its steps on its own stream
+        (in-order per stream, no join between steps), so a straggling pair of one sub-batch overlaps the other
+        sub-batches' next step instead of idling the GPU; all streams are joined at the end."""
         fork = torch.cuda.Event()
         fork.record(stream)
         for sub in subs:
             sub["stream"].wait_event(fork)
-            sub["plan"].run_device(sub["i1"].data_ptr(), sub["i2"].data_ptr(), sub["p"].data_ptr(),
-                                   sub["stream"].cuda_stream)
+        for _ in range(nsteps):
+            for sub in subs:
+                with torch.cuda.stream(sub["stream"]):
+                    sub["p"].zero_()
+                sub["plan"].run_device(sub["i1"].data_ptr(), sub["i2"].data_ptr(), sub["p"].data_ptr(),
+                                       sub["stream"].cuda_stream)
+        for sub in subs:
             join = torch.cuda.Event()
             join.record(sub["stream"])
             stream.wait_event(join)
 
-    for _ in range(args.warmup):
-        step_streams()
+    run_steps(args.warmup)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    for _ in range(args.steps):
-        step_streams()
+    run_steps(args.steps)
     ev1.record(stream)
     barrier()
     launches = sum(sub["plan"].last_launch_count() for sub in subs) * args.steps   # identical inputs every step
@@ -403,10 +408,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=32, help="image pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=128, help="image pairs per step per GPU")
     ap.add_argument("--input-dtype", default="u8", choices=["u8", "f32"],
                     help="dtype of the host images on the e2e leg (values are identical on the device-resident leg)")
-    ap.add_argument("--streams", type=int, default=2, help="independent sub-batches (plan + CUDA stream each) per GPU")
+    ap.add_argument("--streams", type=int, default=4, help="independent sub-batches (plan + CUDA stream each) per GPU")
     ap.add_argument("--e2e-plans", type=int, default=4, help="sub-batch plans (one host thread each) on the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")

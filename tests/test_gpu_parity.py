@@ -416,3 +416,43 @@ def test_row_sharded_nccl_two_gpus(nat, tmp_path):
     ref_p, _, ref_it = register_batch(I1[None], I2[None], t, nscales=3, robust_type=3, delta=5)
     assert np.array_equal(r0["iters"], ref_it[0])
     assert _epe(r0["p"], ref_p[0], t.value, 512, 384) <= 1e-6
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("ICA_SLOW_TESTS"), reason="minutes of CPU oracle time (set ICA_SLOW_TESTS=1)")
+def test_non_converging_pair_matches_oracle(nat):
+    """A pair of the bench workload on which the algorithm does NOT converge (30 iterations at every scale,
+    final motion far from the ground truth): the CUDA path must fail the same way as the oracle, iteration for
+    iteration, until chaos takes over -- compare the trajectories scale by scale."""
+    import torch
+    from inverse_compositional_algorithm_b200 import _native, synthetic
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    t = TransformType.HOMOGRAPHY
+    B = 32
+    I1, I2, p_gt = synthetic.make_batch_torch(B, 1024, 1024, 3, [t] * B, seed=1001, device="cuda")
+    I1 = I1.round_().clamp_(0, 255); I2 = I2.round_().clamp_(0, 255)
+    plan = _native.Plan(batch=B, height=1024, width=1024, channels=3, nscales=5, nu=0.5, transform_type=t.value,
+                        robust_type=3, robust_loop=True, lambda_=0.0, tol=1e-3, max_iter=30, delta=10,
+                        nanifoutside=True, gray_as_rgb=False)
+    p = torch.zeros((B, 8), dtype=torch.float64, device="cuda")
+    plan.run_device(I1.data_ptr(), I2.data_ptr(), p.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    pr, err, iters = plan.results()
+    bad = int(np.argmax(iters.sum(1)))
+    assert iters[bad].min() == 30
+    single = _native.Plan(batch=1, height=1024, width=1024, channels=3, nscales=5, nu=0.5, transform_type=t.value,
+                          robust_type=3, robust_loop=True, lambda_=0.0, tol=1e-3, max_iter=30, delta=10,
+                          nanifoutside=True, gray_as_rgb=False, record_trajectory=True)
+    p1 = torch.zeros((1, 8), dtype=torch.float64, device="cuda")
+    a, b = I1[bad:bad + 1].contiguous(), I2[bad:bad + 1].contiguous()
+    single.run_device(a.data_ptr(), b.data_ptr(), p1.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    traj = single.trajectory()[0]
+    trace = []
+    po, eo, _, _ = orc.ica_pyramidal(a[0].cpu().numpy().astype(np.float64), b[0].cpu().numpy().astype(np.float64),
+                                     np.zeros(8), t.value, 5, 0.5, 1e-3, orc.LORENTZIAN, 0.0, True, 10, trace=trace)
+    assert len(traj) == len(trace) == 150
+    # per-iteration |dp| of the coarsest scale (first 30 entries): same path while the iteration is stable
+    g = traj[:30, 2]
+    o = np.array([tr[2] for tr in trace[:30]])
+    print("gpu |dp|", g[:8], "oracle |dp|", o[:8], "final epe gpu-vs-oracle", _epe(pr[bad], po, t.value, 1024, 1024))
+    assert np.allclose(g[:5], o[:5], rtol=1e-3)
