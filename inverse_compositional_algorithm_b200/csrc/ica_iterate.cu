@@ -533,9 +533,11 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
         __syncwarp();
         if (lane < K && y < ny) {
           const float4* r4 = reinterpret_cast<const float4*>(sc + lane * SCR_PITCH);
-          float tot = 0.0f;
+          // four independent partial sums (fixed order): a single chain of 32 dependent adds was pure latency
+          float4 t4 = r4[0];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { const float4 q4 = r4[j]; tot += q4.x; tot += q4.y; tot += q4.z; tot += q4.w; }
+          for (int j = 1; j < 8; ++j) { const float4 q4 = r4[j]; t4.x += q4.x; t4.y += q4.y; t4.z += q4.z; t4.w += q4.w; }
+          const float tot = (t4.x + t4.y) + (t4.z + t4.w);
           // fold in y^b in fp64; the per-lane accumulators live in shared memory
           const double yd = (double)y, t = (double)tot;
           double yp = 1.0;
