@@ -36,18 +36,19 @@ namespace ica {
 
 namespace {
 
-constexpr int kBlocksPerSM = 2;      // 2 CTAs x 8 warps per SM at 128 registers per thread
-constexpr int kConsumerWarps = 7;    // + 1 producer warp = 8 warps: warps are allocated in groups of 4
+constexpr int kBlocksPerSM = 2;      // 2 CTAs x 12 warps per SM at 80 registers per thread
+constexpr int kConsumerWarps = 11;   // + 1 producer warp = 12 warps: warps are allocated in groups of 4
+constexpr int kRowsPerWarp = 1;      // rows of a tile per consumer warp
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = kConsumerThreads + 32;   // + one producer warp
 constexpr int TW = 64;            // tile width  (2 pixels per lane: x0+lane, x0+32+lane)
-constexpr int TH = 2 * kConsumerWarps;   // tile height 14 (2 rows per consumer warp: y0+warp, y0+7+warp)
+constexpr int TH = kRowsPerWarp * kConsumerWarps;   // tile height (row y0 + warp + rr * kConsumerWarps for warp, rr)
 constexpr int HALO = 4;           // I1 patch starts at x0-4 so that row starts are 16-byte aligned
 constexpr int S1PX = TW + 2 * HALO;
 constexpr int S1ROWS = TH + 2;
 constexpr int BW_MAX = 96;        // staged I2 window; 96*C floats per row == 0 (mod 32 banks): lanes of a
                                   // warp that sit on different window rows never collide
-constexpr int BH_MAX = 24;        // larger windows (strong rotation / zoom) take the global-memory path
+constexpr int BH_MAX = 20;        // larger windows (strong rotation / zoom) take the global-memory path
 constexpr int SCR_PITCH = 36;     // floats per row of the per-warp transposition scratch
 
 template <int DH> struct RowVals { static constexpr int K = 3 * (DH + 1) + 2 * (DH / 2 + 1); };
@@ -181,8 +182,11 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
                                               double* pm64, int total_chunks, int lane) {
   constexpr int S1W = Stage<C>::S1W, S2W = Stage<C>::S2W;
   unsigned k = 0;   // tiles staged so far by this CTA
+  const bool pdbg = P.dbg_time != nullptr && lane == 0;   // profiling hook: cycles spent fetching work / waiting for a free stage
+  long long pd_fetch = 0, pd_empty = 0, pd_proj = 0, pd_ctl = 0, pd_issue = 0;
   for (;;) {
     // dynamic work distribution: chunks are handed out by an atomic counter (reset by the scheduler)
+    const long long pf0 = pdbg ? clock64() : 0;
     int item = 0;
     if (lane == 0) item = atomicAdd(P.work_counter, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
@@ -212,10 +216,14 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
     const int t_end = t_first + (int)((long long)(chunk + 1) * ntiles / nch);
 
     if (P.dbg_time && k == 0 && lane == 0) P.dbg_time[blockIdx.x * 16 + 9] = gtime();
+    if (pdbg) pd_fetch += clock64() - pf0;
     for (int tile = t_begin; tile < t_end; ++tile, ++k) {
       const int sidx = k & 1;
       const unsigned use = k >> 1;
+      const long long pe0 = pdbg ? clock64() : 0;
       if (use >= 1) mbar_wait(&empty[sidx], (use - 1) & 1);   // consumers released the previous use
+      const long long pt1 = pdbg ? clock64() : 0;
+      if (pdbg) pd_empty += pt1 - pe0;
       float* s2 = sidx ? stage1 : stage0;
       float* s1 = s2 + BH_MAX * S2W;
       unsigned long long* bar = &full[sidx];
@@ -240,6 +248,7 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
       const int bh = mxy + 3 - by0 + 1;
       const bool fits = okall && bw <= BW_MAX && bh <= BH_MAX && bw > 0 && bh > 0;
       const int xa1_ = x0 - HALO;
+      const long long pt2 = pdbg ? clock64() : 0;
       if (lane < 9) tc.m64[lane] = pm64[lane];
       if (lane == 0) {
         tc.coef = coef; tc.lo = lo; tc.hi = hi; tc.lambda2 = lambda2;
@@ -253,6 +262,7 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
         tc.fill = (bulk_ok && in1 && in2) ? 0 : 1;
       }
       const int xa1 = x0 - HALO;
+      const long long pt3 = pdbg ? clock64() : 0;
       RowPlan r2; r2.xs = bx0; r2.xe4 = bx0; r2.bytes = 0;
       if (fits && lane < bh) r2 = plan_row<C>(by0 + lane, bx0, bw, nx, ny, bulk_ok);
       RowPlan r1; r1.xs = xa1; r1.xe4 = xa1; r1.bytes = 0;
@@ -262,14 +272,16 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
       for (int o = 16; o >= 1; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
       if (lane == 0) { fence_proxy_async(); mbar_expect_tx(bar, tot); }
       __syncwarp();
-      if (P.dbg_time && k == 0 && lane == 0) P.dbg_time[blockIdx.x * 16 + 10] = gtime();
       if (r2.bytes) bulk_g2s(s2 + lane * S2W + (r2.xs - bx0) * C, I2 + (long long)(by0 + lane) * pitch + (long long)r2.xs * C, r2.bytes, bar);
       if (r1.bytes) bulk_g2s(s1 + lane * S1W + (r1.xs - xa1) * C, I1 + (long long)(y0 - 1 + lane) * pitch + (long long)r1.xs * C, r1.bytes, bar);
-      if (P.dbg_time && k == 0 && lane == 0) P.dbg_time[blockIdx.x * 16 + 11] = gtime();
-      if (P.dbg_time && k == 0 && lane == 0) P.dbg_time[blockIdx.x * 16 + 12] = gtime();
       __syncwarp();                       // every lane's ordinary stores precede the arrival
       if (lane == 0) mbar_arrive(bar);    // release; the phase completes when the bulk bytes have landed too
+      if (pdbg) { const long long pt4 = clock64(); pd_proj += pt2 - pt1; pd_ctl += pt3 - pt2; pd_issue += pt4 - pt3; }
     }
+  }
+  if (pdbg) {
+    long long* d = P.dbg_time + blockIdx.x * 16;
+    d[7] = pd_fetch; d[8] = pd_empty; d[10] = pd_proj; d[11] = pd_ctl; d[12] = pd_issue;
   }
   // no more work: hand the consumers a stop marker through the next stage
   {
@@ -329,6 +341,9 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   double* const myacc = accs + (warp * K + (lane < K ? lane : 0)) * kYPow;
   unsigned k = 0;
   int nitems = 0;
+  const bool dbg = P.dbg_time != nullptr && tid == 0;       // profiling hook: cycles warp 0 spends waiting / in chunk epilogues
+  long long dbg_wait = 0, dbg_epi = 0, dbg_fill = 0;
+  const long long dbg_t0 = dbg ? clock64() : 0;
 
   if (P.dbg_time && tid == 0) P.dbg_time[blockIdx.x * 16 + 0] = gtime();
   for (int it = 0;; ++it) {
@@ -342,7 +357,9 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
     bool stop = false;
     do {
       const int sidx = k & 1;
+      const long long w0 = dbg ? clock64() : 0;
       mbar_wait(&s_full[sidx], (k >> 1) & 1);
+      if (dbg) dbg_wait += clock64() - w0;
       if (tctl[sidx].stop) { stop = true; break; }   // uniform: the producer ran out of work
       if (k == 0) ICA_STAMP(1);
       // Tile constants stay in shared memory and are re-read (volatile) where they are used: the
@@ -351,6 +368,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
       const float* s2 = sidx ? stage1 : stage0;
       const float* s1 = s2 + BH_MAX * S2W;
       if (tcv->fill) {   // uniform over the consumers: border tile
+        const long long f0 = dbg ? clock64() : 0;
         const TileCtl& tc = tctl[sidx];
         float* w2 = sidx ? stage1 : stage0;
         float* w1 = w2 + BH_MAX * S2W;
@@ -359,6 +377,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
         fill_window<C>(w1, S1W, tc.I1, tc.pitch, tc.x0 - HALO, S1PX, tc.y0 - 1, S1ROWS, tc.nx, tc.ny, 0.0f, tc.bulk_ok != 0,
                        lane, warp, kConsumerWarps);
         consumer_sync();
+        if (dbg) dbg_fill += clock64() - f0;
       }
 
 #pragma unroll 1
@@ -555,6 +574,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
     if (stop) break;
     ++nitems;
     ICA_STAMP(2);
+    const long long e0 = dbg ? clock64() : 0;
 
     // ---------------- chunk partial: [K][kYPow] doubles, warps summed in fixed order
     consumer_sync();
@@ -568,6 +588,11 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
       }
     }
     consumer_sync();   // every warp's shared accumulators may be reused by the CTA's next chunk
+    if (dbg) dbg_epi += clock64() - e0;
+  }
+  if (dbg) {
+    long long* d = P.dbg_time + blockIdx.x * 16;
+    d[3] = dbg_wait; d[4] = dbg_epi; d[5] = dbg_fill; d[6] = clock64() - dbg_t0; d[15] = k;
   }
   if (P.dbg_time && tid == 32) { P.dbg_time[blockIdx.x * 16 + 13] = gtime(); P.dbg_time[blockIdx.x * 16 + 14] = nitems; }
   if (tid == 32) atomicMax(reinterpret_cast<long long*>(&P.tstamp[1]), gtime());

@@ -149,7 +149,8 @@ namespace {
 
 constexpr int kVR = 4;        // output rows per thread in the vertical pass
 constexpr int kMaxTaps = 64;
-constexpr int kFR = 4;        // outputs per thread along the filtered axis in the uniform (fast) kernels
+constexpr int kFR = 8;        // outputs per thread along the filtered axis in the uniform (fast) horizontal kernel
+constexpr int kFRV = 8;       // output rows per thread in the uniform vertical kernel (each input row is read (TP+14)/16 times)
 
 struct FastW { float w[kFastTapsMax]; };
 
@@ -194,12 +195,18 @@ __global__ void __launch_bounds__(256) pyr_vertical_kernel(
   float acc[kVR];
 #pragma unroll
   for (int r = 0; r < kVR; ++r) acc[r] = 0.f;
-  for (int row = row_lo; row < row_hi; ++row) {
-    const float v = __ldg(in + (long long)row * in_pitch);
+  // batches of 8 independent loads in flight: the border rows are few, so this kernel is pure load latency
+  for (int row0 = row_lo; row0 < row_hi; row0 += 8) {
+    float v[8];
 #pragma unroll
-    for (int r = 0; r < kVR; ++r) {
-      const int k = row - sst[r];
-      if (k >= 0 && k < taps) acc[r] = fmaf(sw[r][k], v, acc[r]);
+    for (int u = 0; u < 8; ++u) v[u] = row0 + u < row_hi ? __ldg(in + (long long)(row0 + u) * in_pitch) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int r = 0; r < kVR; ++r) {
+        const int k = row0 + u - sst[r];
+        if (k >= 0 && k < taps && row0 + u < row_hi) acc[r] = fmaf(sw[r][k], v[u], acc[r]);
+      }
     }
   }
   float* o = tmp + (long long)img * tmp_stride + j;
@@ -217,18 +224,18 @@ __global__ void __launch_bounds__(128) pyr_vertical_fast_kernel(
   const int img = blockIdx.z;
   const int j4 = blockIdx.x * blockDim.x + threadIdx.x;
   if (j4 >= ncols4 || (int)blockIdx.y >= ngroups) return;
-  const int oy = oy_lo + blockIdx.y * kFR;
+  const int oy = oy_lo + blockIdx.y * kFRV;
   const float* inb = img < nset ? in0a + (long long)img * in_stride : in0b + (long long)(img - nset) * in_stride;
   const float4* in = reinterpret_cast<const float4*>(inb + (long long)(2 * oy + s0) * in_pitch) + j4;
   const int p4 = in_pitch >> 2;
-  float4 acc[kFR];
+  float4 acc[kFRV];
 #pragma unroll
-  for (int r = 0; r < kFR; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < kFRV; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int j = 0; j < TP + 2 * (kFR - 1); ++j) {
+  for (int j = 0; j < TP + 2 * (kFRV - 1); ++j) {
     const float4 v = __ldg(in + (long long)j * p4);
 #pragma unroll
-    for (int r = 0; r < kFR; ++r) {
+    for (int r = 0; r < kFRV; ++r) {
       const int k = j - 2 * r;
       if (k >= 0 && k < TP) {
         const float w = fw.w[k];
@@ -240,7 +247,7 @@ __global__ void __launch_bounds__(128) pyr_vertical_fast_kernel(
   float4* o = reinterpret_cast<float4*>(tmp + (long long)img * tmp_stride + (long long)oy * tmp_pitch) + j4;
   const int t4 = tmp_pitch >> 2;
 #pragma unroll
-  for (int r = 0; r < kFR; ++r) o[(long long)r * t4] = acc[r];
+  for (int r = 0; r < kFRV; ++r) o[(long long)r * t4] = acc[r];
 }
 
 __device__ __forceinline__ void block_minmax_atomic(float val, bool active, MinMaxKeys* ck) {
@@ -284,7 +291,17 @@ __global__ void __launch_bounds__(256) pyr_horizontal_kernel(
     const float* row = tmp + (long long)img * tmp_stride + (long long)oy * ncols_in + c;
     const int st = __ldg(start + ox);
     float acc = 0.f;
-    for (int k = 0; k < taps; ++k) acc = fmaf(__ldg(Wt + (long long)k * nx_out + ox), __ldg(row + (st + k) * C), acc);
+    for (int k0 = 0; k0 < taps; k0 += 8) {   // 16 independent loads in flight, same summation order
+      float w[8], v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool in = k0 + u < taps;
+        w[u] = in ? __ldg(Wt + (long long)(k0 + u) * nx_out + ox) : 0.f;
+        v[u] = in ? __ldg(row + (st + k0 + u) * C) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) if (k0 + u < taps) acc = fmaf(w[u], v[u], acc);
+    }
     val = fminf(fmaxf(acc, lo), hi);
     out0[(long long)oy * out_pitch + ox * C + c] = val;
   }
@@ -416,12 +433,12 @@ cudaError_t launch_minmax(const float* img0, long long stride, long long count, 
 
 // Groups of kFR outputs of the uniform range whose (zero-padded) TP-tap footprint stays inside [0, n_in):
 // the padding taps have weight 0, but 0 * (whatever lies past the data) must never be formed.
-static void fast_groups(const FastRows& f, int n_in, int TP, int* lo, int* ngroups) {
+static void fast_groups(const FastRows& f, int n_in, int TP, int FR, int* lo, int* ngroups) {
   int l = f.lo;
   while (2 * l + f.s0 < 0) ++l;
-  const int omax = (n_in - f.s0 - TP - 2 * (kFR - 1)) / 2;   // last admissible group base
+  const int omax = (n_in - f.s0 - TP - 2 * (FR - 1)) / 2;   // last admissible group base
   int ng = 0;
-  if (f.hi - l >= kFR && omax >= l) ng = std::min((f.hi - l) / kFR, (omax - l) / kFR + 1);
+  if (f.hi - l >= FR && omax >= l) ng = std::min((f.hi - l) / FR, (omax - l) / FR + 1);
   *lo = l; *ngroups = std::max(ng, 0);
 }
 
@@ -462,12 +479,12 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
   const bool valign = (ncols % 4 == 0) && (in_pitch % 4 == 0) && (in_stride % 4 == 0) && (tmp_stride % 4 == 0) &&
                       ((reinterpret_cast<unsigned long long>(in0a) | reinterpret_cast<unsigned long long>(in0b) |
                         reinterpret_cast<unsigned long long>(tmp)) & 15ull) == 0;
-  if (valign && ry.fast.hi - ry.fast.lo >= kFR) {
+  if (valign && ry.fast.hi - ry.fast.lo >= kFRV) {
     const int TP = ry.fast.taps <= 32 ? 32 : kFastTapsMax;
     int lo = 0, ngroups = 0;
-    fast_groups(ry.fast, ny_in, TP, &lo, &ngroups);
+    fast_groups(ry.fast, ny_in, TP, kFRV, &lo, &ngroups);
     if (ngroups > 0) {
-      vlo = lo; vhi = vlo + ngroups * kFR;
+      vlo = lo; vhi = vlo + ngroups * kFRV;
       if (TP == 32) launch_vfast<32>(in0a, in0b, nset, in_stride, in_pitch, ncols, ry.fast, lo, ngroups, tmp, tmp_stride, stream);
       else launch_vfast<kFastTapsMax>(in0a, in0b, nset, in_stride, in_pitch, ncols, ry.fast, lo, ngroups, tmp, tmp_stride, stream);
       ++nl;
@@ -486,7 +503,7 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
   if (rx.fast.hi - rx.fast.lo >= kFR) {
     const int TP = rx.fast.taps <= 32 ? 32 : kFastTapsMax;
     int lo = 0, ngroups = 0;
-    fast_groups(rx.fast, nx_in, TP, &lo, &ngroups);
+    fast_groups(rx.fast, nx_in, TP, kFR, &lo, &ngroups);
     if (ngroups > 0) {
       hlo = lo; hhi = hlo + ngroups * kFR;
 #define ICA_HF(CC, TT) launch_hfast<CC, TT>(tmp, tmp_stride, ncols, rx.fast, lo, ngroups, ny_out, out0a, out0b, nset, out_stride, out_pitch, mm_parent, mm_child, mm_stride, stream)

@@ -22,7 +22,7 @@ tl = plan.debug_timeline(True, fetch=True)
 solve_row = tl[-1]; tl = tl[:-1]
 act = tl[tl[:, 0] > 0]
 t0 = act[:, 0].min()
-names = ["start", "first_tile_ready", "tiles_done", "partial_written", "ticket", "sums_done", "assembled", "gj_done", "end", "P:decoded", "P:planned", "P:issued", "P:filled", "block_end"]
+names = ["start", "first_tile_ready", "tiles_done"]
 print("CTAs with work:", len(act))
 for i, nm in enumerate(names):
     col = act[:, i]
@@ -37,3 +37,13 @@ print("items per block:", np.unique(act[:, 14], return_counts=True))
 sr = solve_row
 print("solve kernel block 0 (us since its start): staged %.2f sums %.2f assembled %.2f gj %.2f updated %.2f ticket %.2f scheduled %.2f" % tuple((sr[i] - sr[0]) / 1e3 for i in range(1, 8)))
 print("iterate max end -> solve start: %.2f us" % ((sr[0] - act[:, 13].max()) / 1e3))
+
+# cycle accumulators of the LAST launch (consumer warp 0 / producer lane 0), as fractions of the CTA's consumer lifetime
+tot = act[:, 6].astype(np.float64)
+ok = tot > 0
+if ok.any():
+    f = lambda c: float(np.mean(act[ok, c] / tot[ok]))
+    print("consumer warp 0: waiting for a full stage %.1f%%, chunk epilogues %.1f%%, border fills %.1f%% of its lifetime; tiles per CTA median %d" %
+          (100 * f(3), 100 * f(4), 100 * f(5), int(np.median(act[ok, 15]))))
+    print("producer: fetching/decoding work items %.1f%%, waiting for an empty stage %.1f%%, window projection %.1f%%, tile control %.1f%%, "
+          "row plans + copy issue %.1f%% of the consumer lifetime" % (100 * f(7), 100 * f(8), 100 * f(10), 100 * f(11), 100 * f(12)))
