@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <mutex>
 #include <vector>
+#include <cuda.h>
 #include "ica_common.cuh"
 #include "ica_transform.cuh"
 #include "ica_device.cuh"
@@ -81,6 +82,14 @@ struct ica_plan {
   size_t raw_bytes = 0;
   float *DI_dev = nullptr, *Iw_dev = nullptr;
   const float *last_I1 = nullptr, *last_I2 = nullptr;
+  // K2 stages its tiles with tiled TMA copies: one tensor map per (pair, level, image)
+  void* tmaps_dev = nullptr;                 // CUtensorMap [B][nscales][2], 128 bytes each
+  std::vector<unsigned char> tmaps_host;
+  const float *tm_I1 = nullptr, *tm_I2 = nullptr;   // level-0 images the maps currently describe
+  float *pad1 = nullptr, *pad2 = nullptr;    // level-0 copies with 16-byte rows (only when the caller's rows are not)
+  const float *k2_I1 = nullptr, *k2_I2 = nullptr;   // K2's view of level 0 in the current run
+  long long k2_stride = 0;
+  int k2_pitch = 0;
   cudaStream_t stream = nullptr;  // own stream of the host entry
   size_t device_bytes = 0;
   long long launches = 0;
@@ -161,11 +170,95 @@ int require_device() {
   return ICA_OK;
 }
 
-void fill_iter_params(const ica_plan* pl, const float* I1, const float* I2, IterParams* P) {
+// ---- tensor maps (driver entry point fetched through the runtime: no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// float32 image [ny][pitch] of which nx*C floats per row are valid; box = boxw floats x boxh rows
+int encode_image_map(void* out128, const float* base, int nx, int ny, int C, int pitch, int boxw, int boxh, bool nan_fill) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return ICA_ERR_CUDA; }
+  alignas(64) CUtensorMap m;
+  const cuuint64_t gdim[2] = {(cuuint64_t)nx * C, (cuuint64_t)ny};
+  const cuuint64_t gstr[1] = {(cuuint64_t)pitch * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)boxw, (cuuint32_t)boxh};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for a %d x %d x %d image, pitch %d, box %d x %d", (int)r, nx, ny, C, pitch, boxw, boxh);
+    return ICA_ERR_CUDA;
+  }
+  static_assert(sizeof(CUtensorMap) == 128, "tensor maps are passed as 128-byte records");
+  memcpy(out128, &m, 128);
+  return ICA_OK;
+}
+
+// maps of levels [s_lo, s_hi) of every pair into the host copy
+int encode_level_maps(ica_plan* pl, int s_lo, int s_hi) {
+  int w1, h1, w2, h2;
+  iterate_stage_boxes(pl->C, &w1, &h1, &w2, &h2);
+  for (int b = 0; b < pl->B; ++b)
+    for (int s = s_lo; s < s_hi; ++s) {
+      const LevelDesc& L = pl->lv[s];
+      const float* i1 = s == 0 ? pl->k2_I1 + (long long)b * pl->k2_stride : pl->pyr1 + (long long)b * pl->pyr_stride + L.offset;
+      const float* i2 = s == 0 ? pl->k2_I2 + (long long)b * pl->k2_stride : pl->pyr2 + (long long)b * pl->pyr_stride + L.offset;
+      const int pitch = s == 0 ? pl->k2_pitch : L.pitch;
+      unsigned char* rec = pl->tmaps_host.data() + ((size_t)(b * pl->nscales + s) * 2) * 128;
+      if (int rc = encode_image_map(rec, i1, L.nx, L.ny, pl->C, pitch, w1, h1, false)) return rc;
+      if (int rc = encode_image_map(rec + 128, i2, L.nx, L.ny, pl->C, pitch, w2, h2, true)) return rc;
+    }
+  return ICA_OK;
+}
+
+// K2's view of level 0 (the caller's images, or padded copies when their rows are not multiples of 16 bytes) and the
+// tensor maps that go with it; re-encoded only when the images moved.
+int prepare_level0(ica_plan* pl, const float* I1, const float* I2, cudaStream_t stream) {
+  const int row = pl->W * pl->C;
+  const bool aligned = (row % 4 == 0) && (((reinterpret_cast<unsigned long long>(I1) | reinterpret_cast<unsigned long long>(I2)) & 15ull) == 0);
+  if (aligned) {
+    pl->k2_I1 = I1; pl->k2_I2 = I2; pl->k2_pitch = row; pl->k2_stride = pl->in_stride;
+  } else {
+    const int pitch = (row + 3) / 4 * 4;
+    const long long stride = (long long)pitch * pl->H;
+    if (!pl->pad1) {
+      if (int rc = dev_alloc(pl, &pl->pad1, (size_t)pl->B * stride)) return rc;
+      if (int rc = dev_alloc(pl, &pl->pad2, (size_t)pl->B * stride)) return rc;
+    }
+    ICA_CUDA_CHECK(cudaMemcpy2DAsync(pl->pad1, (size_t)pitch * 4, I1, (size_t)row * 4, (size_t)row * 4, (size_t)pl->B * pl->H,
+                                     cudaMemcpyDeviceToDevice, stream));
+    ICA_CUDA_CHECK(cudaMemcpy2DAsync(pl->pad2, (size_t)pitch * 4, I2, (size_t)row * 4, (size_t)row * 4, (size_t)pl->B * pl->H,
+                                     cudaMemcpyDeviceToDevice, stream));
+    pl->k2_I1 = pl->pad1; pl->k2_I2 = pl->pad2; pl->k2_pitch = pitch; pl->k2_stride = stride;
+  }
+  if (pl->tm_I1 != pl->k2_I1 || pl->tm_I2 != pl->k2_I2) {
+    if (int rc = encode_level_maps(pl, 0, 1)) return rc;
+    ICA_CUDA_CHECK(cudaMemcpyAsync(pl->tmaps_dev, pl->tmaps_host.data(), pl->tmaps_host.size(), cudaMemcpyHostToDevice, stream));
+    pl->tm_I1 = pl->k2_I1; pl->tm_I2 = pl->k2_I2;
+  }
+  return ICA_OK;
+}
+
+// kernel parameters of the current run (prepare_level0 first)
+void fill_iter_params(const ica_plan* pl, const float* /*I1*/, const float* /*I2*/, IterParams* P) {
   memset(P, 0, sizeof(*P));
-  P->I1_0 = I1; P->I2_0 = I2; P->in_stride = pl->in_stride;
+  P->I1_0 = pl->k2_I1; P->I2_0 = pl->k2_I2; P->in_stride = pl->k2_stride;
   P->pyr1 = pl->pyr1; P->pyr2 = pl->pyr2; P->pyr_stride = pl->pyr_stride;
   for (int s = 0; s < pl->nscales; ++s) P->lv[s] = pl->lv[s];
+  P->lv[0].pitch = pl->k2_pitch;
+  P->tmaps = pl->tmaps_dev;
   P->nscales = pl->nscales;
   P->state = pl->state; P->mm = pl->mm; P->partials = pl->partials;
   P->traj = (pl->cfg.flags & ICA_FLAG_RECORD_TRAJECTORY) ? pl->traj : nullptr;
@@ -202,6 +295,7 @@ void fill_iter_params(const ica_plan* pl, const float* I1, const float* I2, Iter
 // kernel's scheduling block sets the condition on the device, so the whole coarse-to-fine loop of every
 // pair runs without a host round trip.  Rebuilt when the image pointers or the moment degree change.
 int ensure_loop_graph(ica_plan* pl, const float* I1, const float* I2) {
+  I1 = pl->k2_I1; I2 = pl->k2_I2;   // the graph bakes K2's view of level 0
   if (pl->graph_exec && pl->graph_I1 == I1 && pl->graph_I2 == I2 && pl->graph_dh == pl->dh) return ICA_OK;
   if (pl->graph_exec) { cudaGraphExecDestroy(pl->graph_exec); pl->graph_exec = nullptr; }
   if (pl->graph) { cudaGraphDestroy(pl->graph); pl->graph = nullptr; }
@@ -298,7 +392,7 @@ int ica_get_constants(double* out5) {
 
 int ica_plan_destroy(ica_plan* pl) {
   if (!pl) return ICA_OK;
-  cudaFree(pl->pyr1); cudaFree(pl->pyr2); cudaFree(pl->tmp);
+  cudaFree(pl->pyr1); cudaFree(pl->pyr2); cudaFree(pl->tmp); cudaFree(pl->tmaps_dev); cudaFree(pl->pad1); cudaFree(pl->pad2);
   for (int s = 0; s < ICA_MAX_SCALES; ++s) { free_resample(&pl->ry[s]); free_resample(&pl->rx[s]); }
   cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->item_pair); cudaFree(pl->solve_ticket); cudaFree(pl->asm_tab); cudaFree(pl->loop_count); cudaFree(pl->tstamp);
   if (pl->h_loop) cudaFreeHost(pl->h_loop);
@@ -407,6 +501,10 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
     TRY(dev_alloc(pl, &pl->DI_dev, (size_t)pl->B * pl->in_stride));
     TRY(dev_alloc(pl, &pl->Iw_dev, (size_t)pl->B * pl->in_stride));
   }
+  pl->tmaps_host.assign((size_t)pl->B * pl->nscales * 2 * 128, 0);
+  TRY_CUDA(cudaMalloc(&pl->tmaps_dev, pl->tmaps_host.size()));
+  pl->device_bytes += pl->tmaps_host.size();
+  if (pl->nscales > 1) TRY(encode_level_maps(pl, 1, pl->nscales));   // levels >= 1 live in the plan's slabs
   TRY_CUDA(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
   TRY_CUDA(cudaEventCreate(&pl->ev_host0));
   TRY_CUDA(cudaEventCreate(&pl->ev_host1));
@@ -508,6 +606,7 @@ int ica_plan_shard_begin(ica_plan* pl, const float* I1, const float* I2, const d
   cudaStream_t stream = (cudaStream_t)stream_;
   pl->launches = 0; pl->n_ev_iter = 0; pl->n_ev_pyr = 0;
   pl->last_I1 = I1; pl->last_I2 = I2;
+  if (int rc = prepare_level0(pl, I1, I2, stream)) return rc;
   if (int rc = build_pyramids(pl, I1, I2, stream)) return rc;
   ICA_LAUNCH_CHECK(launch_init_state(pl->state, p_in, pl->ttypes_dev, pl->B, pl->nscales, pl->cfg.lambda_, pl->n_active, stream));
   IterParams P;
@@ -566,6 +665,7 @@ int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* 
   pl->launches = 0;
   pl->n_ev_iter = 0; pl->n_ev_pyr = 0;
   pl->last_I1 = I1; pl->last_I2 = I2;
+  if (int rc = prepare_level0(pl, I1, I2, stream)) return rc;
   if (int rc = build_pyramids(pl, I1, I2, stream)) return rc;
   ICA_LAUNCH_CHECK(launch_init_state(pl->state, p_inout, pl->ttypes_dev, pl->B, pl->nscales, pl->cfg.lambda_,
                                      pl->n_active, stream));
@@ -891,6 +991,7 @@ int ica_hessian_b_host(const float* I1, const float* I2, int32_t height, int32_t
     if (e == cudaSuccess) e = cudaMemcpy(pl->p_dev, ph, sizeof(ph), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { set_error("ica_hessian_b_host: %s", cudaGetErrorString(e)); rc = ICA_ERR_CUDA; }
   }
+  if (!rc) rc = prepare_level0(pl, pl->in1_dev, pl->in2_dev, 0);
   if (!rc) rc = build_pyramids(pl, pl->in1_dev, pl->in2_dev, 0);
   if (!rc) {
     e = launch_init_state(pl->state, pl->p_dev, pl->ttypes_dev, 1, 1, cfg.lambda_, pl->n_active, 0);

@@ -43,20 +43,21 @@ constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = kConsumerThreads + 32;   // + one producer warp
 constexpr int TW = 64;            // tile width  (2 pixels per lane: x0+lane, x0+32+lane)
 constexpr int TH = kRowsPerWarp * kConsumerWarps;   // tile height (row y0 + warp + rr * kConsumerWarps for warp, rr)
-constexpr int HALO = 4;           // I1 patch starts at x0-4 so that row starts are 16-byte aligned
-constexpr int S1PX = TW + 2 * HALO;
+constexpr int HALO = 4;           // the I1 patch starts at x0-4: the inner coordinate of a TMA box must be a multiple of 16 bytes
 constexpr int S1ROWS = TH + 2;
-constexpr int BW_MAX = 96;        // staged I2 window; 96*C floats per row == 0 (mod 32 banks): lanes of a
-                                  // warp that sit on different window rows never collide
-constexpr int BH_MAX = 20;        // larger windows (strong rotation / zoom) take the global-memory path
+constexpr int BH_MAX = 22;        // rows of the staged I2 window; taller windows (strong rotation / zoom) take the global-memory path
 constexpr int SCR_PITCH = 36;     // floats per row of the per-warp transposition scratch
 
 template <int DH> struct RowVals { static constexpr int K = 3 * (DH + 1) + 2 * (DH / 2 + 1); };
 
+// One stage = the TMA boxes of a tile: the I2 window (S2W floats x BH_MAX rows) and the I1 patch (S1W floats x
+// S1ROWS rows).  A box is at most 256 elements wide, its rows are multiples of 16 bytes, and S2W == 0 (mod 32
+// banks), so lanes of a warp that sit on different window rows never collide.
 template <int C> struct Stage {
-  static constexpr int S1W = S1PX * C;
-  static constexpr int S2W = BW_MAX * C;
-  static constexpr int kFloats = BH_MAX * S2W + S1ROWS * S1W;   // I2 window, then I1 patch
+  static constexpr int S2W = C == 3 ? 256 : 96;            // floats per window row
+  static constexpr int BWPX = S2W / C;                     // window width in pixels (85 RGB, 96 gray)
+  static constexpr int S1W = (TW + 2 * HALO) * C;          // 216 (RGB) / 72 (gray) floats per patch row
+  static constexpr int kFloats = (BH_MAX * S2W + S1ROWS * S1W + 31) / 32 * 32;   // I2 window, then I1 patch; 128-byte multiple
 };
 
 // Everything a consumer needs to know about a staged tile (written by the producer).
@@ -70,9 +71,8 @@ struct TileCtl {
   int x0, y0;
   int bx0, by0, bw, bh, fits;
   int nx, ny, pitch;
-  int fill, bulk_ok, stop;
-  const float* I2;
-  const float* I1;
+  int stop;
+  const float* I2;        // global image, for the pixels whose taps leave the staged window
 };
 
 // ---------------------------------------------------------------- mbarrier / bulk-copy PTX
@@ -95,67 +95,17 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "bra LAB_WAIT;\n\t"
       "LAB_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+// 2-D tiled TMA load: the box described by the tensor map, with its corner at (c0 floats, c1 rows); elements outside
+// the image are filled by the copy engine (NaN for I2 = skimage's cval, 0 for I1), negative corners included.
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define ICA_STAMP(slot) do { if (P.dbg_time && it == 0 && tid == 0) P.dbg_time[blockIdx.x * 16 + (slot)] = gtime(); } while (0)
 // barrier among the consumer threads only (the producer warp never joins it)
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
-
-// One image-row segment [xa, xa+w) of row yy: the part that lies inside the image and whose
-// byte range is a multiple of 16 goes through a bulk copy ([xs, xe4), `bytes`); the rest
-// (out-of-image pixels, a ragged right end, or everything when bulk copies are not possible)
-// is written by fill_window.
-struct RowPlan { int xs, xe4; unsigned bytes; };
-
-template <int C>
-__device__ __forceinline__ RowPlan plan_row(int yy, int xa, int w, int nx, int ny, bool bulk_ok) {
-  RowPlan r; r.xs = xa; r.xe4 = xa; r.bytes = 0;
-  if (yy < 0 || yy >= ny || !bulk_ok) return r;
-  int xs = max(xa, 0), xe = min(xa + w, nx);
-  if (xe <= xs) return r;
-  int xe4 = xs + ((xe - xs) & ~3);
-  r.xs = xs; r.xe4 = xe4; r.bytes = (unsigned)(xe4 - xs) * C * 4u;
-  return r;
-}
-
-// Everything of a staged window [xa, xa+w) x [ya, ya+h) that the bulk copies do not deliver: rows and
-// column strips outside the image get `fill` (plain independent stores, no loads); pixels inside
-// the image but outside the 16-byte-aligned bulk range (a ragged right end when nx % 4 != 0, or the
-// whole row when bulk copies are impossible) are copied with ordinary loads.  Called by the consumer
-// warps (rows are dealt round-robin to the `nw` warps) for tiles the producer flagged.
-template <int C>
-__device__ __forceinline__ void fill_window(float* sbase, int SW, const float* __restrict__ img, int pitch, int xa,
-                                            int w, int ya, int h, int nx, int ny, float fill, bool bulk_ok, int lane,
-                                            int warp, int nw) {
-  const int wf = w * C;
-  const int r0 = min(h, max(0, -ya));          // first in-image row of the window
-  const int r1 = max(r0, min(h, ny - ya));     // one past the last in-image row
-  for (int r = warp; r < h; r += nw) {
-    if (r >= r0 && r < r1) continue;
-    for (int i = lane; i < wf; i += 32) sbase[r * SW + i] = fill;
-  }
-  const int xs = max(xa, 0), xe = max(xs, min(xa + w, nx));
-  const int left = min(wf, (xs - xa) * C);     // floats left of the image
-  const int right0 = (xe - xa) * C;            // first float right of the image
-  if (left > 0 || right0 < wf) {
-    for (int r = r0 + warp; r < r1; r += nw) {
-      for (int i = lane; i < left; i += 32) sbase[r * SW + i] = fill;
-      for (int i = right0 + lane; i < wf; i += 32) sbase[r * SW + i] = fill;
-    }
-  }
-  const int xe4 = xs + ((xe - xs) & ~3);
-  const int rem0 = ((bulk_ok ? xe4 : xs) - xa) * C;
-  if (rem0 < right0) {
-    for (int r = r0 + warp; r < r1; r += nw) {
-      const float* src = img + (long long)(ya + r) * pitch + (long long)xa * C;
-      for (int i = rem0 + lane; i < right0; i += 32) sbase[r * SW + i] = __ldg(src + i);
-    }
-  }
-}
 
 // Jacobian entry k as a monomial, in registers (same table as ica_transform.cuh: jacobian_monomials)
 __device__ __forceinline__ void mono_of(int ttype, int k, Mono& jx, Mono& jy) {
@@ -204,11 +154,11 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
     const int need_h = (P.robust_loop || st.iter == 0) ? 1 : 0;
     const LevelDesc L = P.lv[s];
     const int nx = L.nx, ny = L.ny, pitch = L.pitch;
-    const float* __restrict__ I1 = s == 0 ? P.I1_0 + (long long)pair * P.in_stride
-                                          : P.pyr1 + (long long)pair * P.pyr_stride + L.offset;
     const float* __restrict__ I2 = s == 0 ? P.I2_0 + (long long)pair * P.in_stride
                                           : P.pyr2 + (long long)pair * P.pyr_stride + L.offset;
-    const bool bulk_ok = (pitch & 3) == 0 && ((((unsigned long long)I1) | ((unsigned long long)I2)) & 15ull) == 0;
+    // tensor maps of this pair's level: [pair][scale][0 = I1 (zero fill), 1 = I2 (NaN fill)], 128 bytes each
+    const char* tm1 = static_cast<const char*>(P.tmaps) + ((long long)(pair * P.nscales + s) * 2) * 128;
+    const char* tm2 = tm1 + 128;
     int t_first;
     const int ntiles = band_tiles(L, P.shard_rank, P.shard_n, &t_first);
     const int nch = ntiles < P.max_chunks ? ntiles : P.max_chunks;
@@ -242,40 +192,34 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
         mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
         okall &= __shfl_xor_sync(0xffffffffu, okall, o);
       }
-      const int bx0 = ((mnx - 2) >> 2) << 2;                   // floor to a multiple of 4 pixels
-      const int bw = ((mxx + 3 - bx0 + 1) + 3) & ~3;
-      const int by0 = mny - 2;
+      const int bx0 = ((mnx - 2) >> 2) << 2;                   // floor to a multiple of 4 pixels (16-byte box corner)
+      const int by0 = mny - 2;                                 // one pixel of margin around the corners' taps
+      const int bw = mxx + 3 - bx0 + 1;
       const int bh = mxy + 3 - by0 + 1;
-      const bool fits = okall && bw <= BW_MAX && bh <= BH_MAX && bw > 0 && bh > 0;
-      const int xa1_ = x0 - HALO;
+      const bool fits = okall && bw <= Stage<C>::BWPX && bh <= BH_MAX && bw > 0 && bh > 0;
       const long long pt2 = pdbg ? clock64() : 0;
-      if (lane < 9) tc.m64[lane] = pm64[lane];
-      if (lane == 0) {
-        tc.coef = coef; tc.lo = lo; tc.hi = hi; tc.lambda2 = lambda2;
-        tc.pair = pair; tc.chunk = chunk; tc.nch = nch; tc.scale = s;
-        tc.need_h = need_h; tc.first = tile == t_begin; tc.last = tile + 1 == t_end;
-        tc.x0 = x0; tc.y0 = y0; tc.bx0 = bx0; tc.by0 = by0; tc.bw = bw; tc.bh = bh; tc.fits = fits ? 1 : 0;
-        tc.nx = nx; tc.ny = ny; tc.pitch = pitch; tc.I2 = I2; tc.I1 = I1; tc.bulk_ok = bulk_ok ? 1 : 0; tc.stop = 0;
-        // anything the bulk copies cannot deliver (image borders, ragged ends) is filled by the consumers
-        const bool in2 = !fits || (bx0 >= 0 && bx0 + bw <= nx && by0 >= 0 && by0 + bh <= ny);
-        const bool in1 = xa1_ >= 0 && xa1_ + S1PX <= nx && y0 - 1 >= 0 && y0 - 1 + S1ROWS <= ny;
-        tc.fill = (bulk_ok && in1 && in2) ? 0 : 1;
+      if (tile < t_begin + 2) {   // first use of this stage's control block by the chunk: per-chunk constants
+        if (lane < 9) tc.m64[lane] = pm64[lane];
+        if (lane == 0) {
+          tc.coef = coef; tc.lo = lo; tc.hi = hi; tc.lambda2 = lambda2;
+          tc.pair = pair; tc.chunk = chunk; tc.nch = nch; tc.scale = s; tc.need_h = need_h;
+          tc.nx = nx; tc.ny = ny; tc.pitch = pitch; tc.I2 = I2; tc.stop = 0;
+        }
       }
-      const int xa1 = x0 - HALO;
+      if (lane == 0) {
+        tc.first = tile == t_begin; tc.last = tile + 1 == t_end;
+        tc.x0 = x0; tc.y0 = y0; tc.bx0 = bx0; tc.by0 = by0; tc.bw = bw; tc.bh = bh; tc.fits = fits ? 1 : 0;
+      }
       const long long pt3 = pdbg ? clock64() : 0;
-      RowPlan r2; r2.xs = bx0; r2.xe4 = bx0; r2.bytes = 0;
-      if (fits && lane < bh) r2 = plan_row<C>(by0 + lane, bx0, bw, nx, ny, bulk_ok);
-      RowPlan r1; r1.xs = xa1; r1.xe4 = xa1; r1.bytes = 0;
-      if (lane < S1ROWS) r1 = plan_row<C>(y0 - 1 + lane, xa1, S1PX, nx, ny, bulk_ok);
-      unsigned tot = r2.bytes + r1.bytes;
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-      if (lane == 0) { fence_proxy_async(); mbar_expect_tx(bar, tot); }
-      __syncwarp();
-      if (r2.bytes) bulk_g2s(s2 + lane * S2W + (r2.xs - bx0) * C, I2 + (long long)(by0 + lane) * pitch + (long long)r2.xs * C, r2.bytes, bar);
-      if (r1.bytes) bulk_g2s(s1 + lane * S1W + (r1.xs - xa1) * C, I1 + (long long)(y0 - 1 + lane) * pitch + (long long)r1.xs * C, r1.bytes, bar);
-      __syncwarp();                       // every lane's ordinary stores precede the arrival
-      if (lane == 0) mbar_arrive(bar);    // release; the phase completes when the bulk bytes have landed too
+      __syncwarp();                       // the control block is complete before the arrival below
+      if (lane == 0) {
+        // two tiled TMA copies per tile; pixels outside the image are filled by the copy engine
+        constexpr unsigned kBytes1 = S1ROWS * S1W * 4u, kBytes2 = BH_MAX * S2W * 4u;
+        mbar_expect_tx(bar, kBytes1 + (fits ? kBytes2 : 0u));
+        tma_load_2d(s1, tm1, (x0 - HALO) * C, y0 - 1, bar);
+        if (fits) tma_load_2d(s2, tm2, bx0 * C, by0, bar);
+        mbar_arrive(bar);                 // release; the phase completes when the copied bytes have landed too
+      }
       if (pdbg) { const long long pt4 = clock64(); pd_proj += pt2 - pt1; pd_ctl += pt3 - pt2; pd_issue += pt4 - pt3; }
     }
   }
@@ -288,7 +232,7 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
     const int sidx = k & 1;
     const unsigned use = k >> 1;
     if (use >= 1) mbar_wait(&empty[sidx], (use - 1) & 1);
-    if (lane == 0) { tctl[sidx].stop = 1; tctl[sidx].fill = 0; mbar_arrive(&full[sidx]); }
+    if (lane == 0) { tctl[sidx].stop = 1; mbar_arrive(&full[sidx]); }
   }
 }
 
@@ -342,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   unsigned k = 0;
   int nitems = 0;
   const bool dbg = P.dbg_time != nullptr && tid == 0;       // profiling hook: cycles warp 0 spends waiting / in chunk epilogues
-  long long dbg_wait = 0, dbg_epi = 0, dbg_fill = 0;
+  long long dbg_wait = 0, dbg_epi = 0;
   const long long dbg_t0 = dbg ? clock64() : 0;
 
   if (P.dbg_time && tid == 0) P.dbg_time[blockIdx.x * 16 + 0] = gtime();
@@ -367,19 +311,6 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
       const volatile TileCtl* tcv = &tctl[sidx];
       const float* s2 = sidx ? stage1 : stage0;
       const float* s1 = s2 + BH_MAX * S2W;
-      if (tcv->fill) {   // uniform over the consumers: border tile
-        const long long f0 = dbg ? clock64() : 0;
-        const TileCtl& tc = tctl[sidx];
-        float* w2 = sidx ? stage1 : stage0;
-        float* w1 = w2 + BH_MAX * S2W;
-        if (tc.fits) fill_window<C>(w2, S2W, tc.I2, tc.pitch, tc.bx0, tc.bw, tc.by0, tc.bh, tc.nx, tc.ny,
-                                    __int_as_float(0x7fc00000) /* skimage cval */, tc.bulk_ok != 0, lane, warp, kConsumerWarps);
-        fill_window<C>(w1, S1W, tc.I1, tc.pitch, tc.x0 - HALO, S1PX, tc.y0 - 1, S1ROWS, tc.nx, tc.ny, 0.0f, tc.bulk_ok != 0,
-                       lane, warp, kConsumerWarps);
-        consumer_sync();
-        if (dbg) dbg_fill += clock64() - f0;
-      }
-
 #pragma unroll 1
       for (int rr = 0; rr < TH / kConsumerWarps; ++rr) {
         const int ly = warp + rr * kConsumerWarps;
@@ -592,7 +523,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   }
   if (dbg) {
     long long* d = P.dbg_time + blockIdx.x * 16;
-    d[3] = dbg_wait; d[4] = dbg_epi; d[5] = dbg_fill; d[6] = clock64() - dbg_t0; d[15] = k;
+    d[3] = dbg_wait; d[4] = dbg_epi; d[5] = 0; d[6] = clock64() - dbg_t0; d[15] = k;
   }
   if (P.dbg_time && tid == 32) { P.dbg_time[blockIdx.x * 16 + 13] = gtime(); P.dbg_time[blockIdx.x * 16 + 14] = nitems; }
   if (tid == 32) atomicMax(reinterpret_cast<long long*>(&P.tstamp[1]), gtime());
@@ -1059,6 +990,10 @@ void build_assembly_table(int dh, AsmEntry* tab) {
 
 int iterate_tile_w() { return TW; }
 int iterate_tile_h() { return TH; }
+void iterate_stage_boxes(int channels, int* w1, int* h1, int* w2, int* h2) {
+  *w1 = channels == 3 ? Stage<3>::S1W : Stage<1>::S1W; *h1 = S1ROWS;
+  *w2 = channels == 3 ? Stage<3>::S2W : Stage<1>::S2W; *h2 = BH_MAX;
+}
 int iterate_blocks_per_sm() { return kBlocksPerSM; }
 
 cudaError_t launch_schedule(const IterParams& P, cudaStream_t stream) {

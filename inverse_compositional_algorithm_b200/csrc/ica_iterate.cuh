@@ -27,6 +27,7 @@ struct IterParams {
   int* chunk_start;       // [B+1] work list of the current launch (ica_schedule_kernel)
   int* item_pair;         // [B*max_chunks] pair of each work item
   const AsmEntry* asm_tab;      // [6 transform codes][72]
+  const void* tmaps;            // CUtensorMap [B][nscales][2] (I1 zero-filled, I2 NaN-filled boxes), 128 bytes each
   unsigned long long cond_handle;   // cudaGraphConditionalHandle of the while node (0 outside a graph)
   int* loop_count;              // iterations executed in this run (device)
   int* work_counter;            // next unclaimed work item of the current iterate launch
@@ -54,6 +55,8 @@ void build_assembly_table(int dh, AsmEntry* tab /* [6*72] */);
 int iterate_tile_w();
 int iterate_tile_h();
 int iterate_blocks_per_sm();
+// TMA boxes of one staged tile, in floats x rows: I1 patch (w1 x h1) and I2 window (w2 x h2)
+void iterate_stage_boxes(int channels, int* w1, int* h1, int* w2, int* h2);
 cudaError_t launch_schedule(const IterParams& P, cudaStream_t stream);
 cudaError_t launch_solve(const IterParams& P, int dh, cudaStream_t stream);
 cudaError_t launch_iterate(const IterParams& P, int channels, int dh, int grid, cudaStream_t stream);
