@@ -97,6 +97,16 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 // 2-D tiled TMA load: the box described by the tensor map, with its corner at (c0 floats, c1 rows); elements outside
 // the image are filled by the copy engine (NaN for I2 = skimage's cval, 0 for I1), negative corners included.
+// the producer is usually a tile ahead: poll politely so that its spinning does not take issue slots from the consumers
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long* bar, unsigned parity) {
+  for (;;) {
+    unsigned done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(200);
+  }
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, unsigned long long* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
@@ -171,7 +181,7 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
       const int sidx = k & 1;
       const unsigned use = k >> 1;
       const long long pe0 = pdbg ? clock64() : 0;
-      if (use >= 1) mbar_wait(&empty[sidx], (use - 1) & 1);   // consumers released the previous use
+      if (use >= 1) mbar_wait_backoff(&empty[sidx], (use - 1) & 1);   // consumers released the previous use
       const long long pt1 = pdbg ? clock64() : 0;
       if (pdbg) pd_empty += pt1 - pe0;
       float* s2 = sidx ? stage1 : stage0;
@@ -357,8 +367,10 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
           {
             const int bx0 = tcv->bx0, by0 = tcv->by0, bw = tcv->bw, bh = tcv->bh;
             const bool fits = tcv->fits != 0;
-            insmA = fits && (cxA - 1 >= bx0) && (cxA + 2 < bx0 + bw) && (cyA - 1 >= by0) && (cyA + 2 < by0 + bh);
-            insmB = fits && (cxB - 1 >= bx0) && (cxB + 2 < bx0 + bw) && (cyB - 1 >= by0) && (cyB + 2 < by0 + bh);
+            // 0 <= c - 1 - b0 <= extent - 4, as one unsigned comparison per axis (extent >= 4 whenever fits)
+            const unsigned lx = (unsigned)(bw - 4), lyy = (unsigned)(bh - 4);
+            insmA = fits && (unsigned)(cxA - 1 - bx0) <= lx && (unsigned)(cyA - 1 - by0) <= lyy;
+            insmB = fits && (unsigned)(cxB - 1 - bx0) <= lx && (unsigned)(cyB - 1 - by0) <= lyy;
             offA = (cyA - 1 - by0) * S2W + (cxA - 1 - bx0) * C;
             offB = (cyB - 1 - by0) * S2W + (cxB - 1 - bx0) * C;
           }
