@@ -300,6 +300,34 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   const long long dbg_t0 = dbg ? clock64() : 0;
 
   if (P.dbg_time && tid == 0) P.dbg_time[blockIdx.x * 16 + 0] = gtime();
+  // Per-lane x-moment accumulators of the image row `vrow` (-1: empty).  Consecutive tiles of a chunk usually lie on
+  // the same tile row, so a warp keeps adding pixels of the same image row and pays the cross-lane reduction and
+  // the fp64 fold once per row segment of the chunk instead of once per tile.
+  float v[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) v[i] = 0.0f;
+  int vrow = -1;
+  // transpose through shared memory: moment k of the row lands on lane k (fixed summation order), which folds in
+  // y^b in fp64; the per-lane fp64 accumulators live in shared memory
+  auto flush_row = [&]() {
+#pragma unroll
+    for (int i = 0; i < K; ++i) { sc[i * SCR_PITCH + lane] = v[i]; v[i] = 0.0f; }
+    __syncwarp();
+    if (lane < K) {
+      const float4* r4 = reinterpret_cast<const float4*>(sc + lane * SCR_PITCH);
+      // four independent partial sums (fixed order): a single chain of 32 dependent adds was pure latency
+      float4 t4 = r4[0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) { const float4 q4 = r4[j]; t4.x += q4.x; t4.y += q4.y; t4.z += q4.z; t4.w += q4.w; }
+      const float tot = (t4.x + t4.y) + (t4.z + t4.w);
+      const double yd = (double)vrow, t = (double)tot;
+      double yp = 1.0;
+#pragma unroll
+      for (int b = 0; b < kYPow; ++b) { myacc[b] = fma(t, yp, myacc[b]); yp *= yd; }
+    }
+    __syncwarp();
+    vrow = -1;
+  };
   for (int it = 0;; ++it) {
     if (lane < K) {
 #pragma unroll
@@ -326,10 +354,9 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
         const int ly = warp + rr * kConsumerWarps;
         const int y = tcv->y0 + ly;
         const int ny = tcv->ny;
-        float v[K];
-#pragma unroll
-        for (int i = 0; i < K; ++i) v[i] = 0.0f;
+        if (vrow >= 0 && vrow != y) flush_row();
         if (y < ny) {
+          vrow = y;
           const int nx = tcv->nx;
           const bool need_hr = tcv->need_h != 0;
           // moments of one pixel: v[] += (rho' S, rho' v) * x^a
@@ -489,24 +516,6 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
             }
           }
         }
-        // transpose through shared memory: moment k of the row lands on lane k (fixed summation order)
-#pragma unroll
-        for (int i = 0; i < K; ++i) sc[i * SCR_PITCH + lane] = v[i];
-        __syncwarp();
-        if (lane < K && y < ny) {
-          const float4* r4 = reinterpret_cast<const float4*>(sc + lane * SCR_PITCH);
-          // four independent partial sums (fixed order): a single chain of 32 dependent adds was pure latency
-          float4 t4 = r4[0];
-#pragma unroll
-          for (int j = 1; j < 8; ++j) { const float4 q4 = r4[j]; t4.x += q4.x; t4.y += q4.y; t4.z += q4.z; t4.w += q4.w; }
-          const float tot = (t4.x + t4.y) + (t4.z + t4.w);
-          // fold in y^b in fp64; the per-lane accumulators live in shared memory
-          const double yd = (double)y, t = (double)tot;
-          double yp = 1.0;
-#pragma unroll
-          for (int b = 0; b < kYPow; ++b) { myacc[b] = fma(t, yp, myacc[b]); yp *= yd; }
-        }
-        __syncwarp();
       }
       pair = tcv->pair; chunk = tcv->chunk; nch = tcv->nch; s = tcv->scale; nx = tcv->nx; ny = tcv->ny;
       need_h = tcv->need_h != 0; last = tcv->last != 0;
@@ -515,6 +524,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
       ++k;
     } while (!last);
     if (stop) break;
+    if (vrow >= 0) flush_row();   // the chunk's last row segment
     ++nitems;
     ICA_STAMP(2);
     const long long e0 = dbg ? clock64() : 0;
