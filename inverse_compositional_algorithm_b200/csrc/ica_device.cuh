@@ -37,11 +37,11 @@ __device__ __forceinline__ float approx_rcp(float z) {
 
 // Projects integer pixel (x, y): integer tap origin (cx, cy) = floor(x'), floor(y') and the
 // fractions.  Returns false when the coordinates are unusable (z <= 0, non-finite).
-// Pixels whose projected coordinate falls within 1e-3 of an integer (where fp32 rounding could
+// Pixels whose projected coordinate falls within ~2.5e-4 of an integer (where fp32 rounding could
 // pick the other tap set, or flip the NaN footprint) are re-evaluated in fp64 with exactly the
 // operation order of skimage's _transform_projective -- (M0*x + M1*y) + M2, same for z, then
 // the quotient -- so tap selection agrees with the reference bit for bit.  m64 is the 3x3
-// matrix (row-major, fp64, typically in shared memory); the branch is taken by ~0.4% of pixels.
+// matrix (row-major, fp64, typically in shared memory); the branch is taken by ~0.1% of pixels.
 __device__ __forceinline__ bool project_px(const WarpCoef& k, const double* m64, int x, int y, int& cx,
                                            int& cy, float& tx, float& ty) {
   float fx = (float)x, fy = (float)y;
@@ -56,8 +56,10 @@ __device__ __forceinline__ bool project_px(const WarpCoef& k, const double* m64,
   float flx = floorf(dx), fly = floorf(dy);
   tx = dx - flx; ty = dy - fly;
   cx = x + (int)flx; cy = y + (int)fly;
-  const float kTie = 1.0e-3f;
-  if (ok && (tx < kTie || tx > 1.0f - kTie || ty < kTie || ty > 1.0f - kTie)) {
+  // tie band: a comfortable multiple of the fp32 error of dx, dy (a few ulps of the displacement: 2.5e-4 px covers
+  // displacements of ~100 px, the second term takes over for the huge ones); ~0.1% of the pixels take the branch
+  const float kTie = fmaf(1.0e-6f, fabsf(dx) + fabsf(dy), 2.5e-4f);
+  if (ok && (fminf(tx, ty) < kTie || fmaxf(tx, ty) > 1.0f - kTie)) {
     const double xd = (double)x, yd = (double)y;
     const double xx = __dadd_rn(__dadd_rn(__dmul_rn(m64[0], xd), __dmul_rn(m64[1], yd)), m64[2]);
     const double yy = __dadd_rn(__dadd_rn(__dmul_rn(m64[3], xd), __dmul_rn(m64[4], yd)), m64[5]);
