@@ -408,11 +408,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=128, help="image pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=256, help="image pairs per step per GPU")
     ap.add_argument("--input-dtype", default="u8", choices=["u8", "f32"],
                     help="dtype of the host images on the e2e leg (values are identical on the device-resident leg)")
     ap.add_argument("--streams", type=int, default=4, help="independent sub-batches (plan + CUDA stream each) per GPU")
-    ap.add_argument("--e2e-plans", type=int, default=4, help="sub-batch plans (one host thread each) on the e2e leg")
+    ap.add_argument("--e2e-plans", type=int, default=8, help="sub-batch plans (one host thread each) on the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
     args = ap.parse_args()

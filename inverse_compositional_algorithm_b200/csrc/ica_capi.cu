@@ -116,6 +116,7 @@ int dev_alloc(ica_plan* pl, T** ptr, size_t count) {
 
 int upload_resample(ica_plan* pl, const Resample1D& r, DeviceResample* d) {
   d->n_in = r.n_in; d->n_out = r.n_out; d->taps = r.taps;
+  d->start_host = r.start;
   detect_uniform_rows(r, &d->fast);
   int rc;
   if ((rc = dev_alloc(pl, &d->start, r.start.size()))) return rc;
@@ -457,8 +458,10 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
     TRY(dev_alloc(pl, &pl->pyr1, (size_t)pl->B * pl->pyr_stride));
     TRY(dev_alloc(pl, &pl->pyr2, (size_t)pl->B * pl->pyr_stride));
     pl->tmp_stride = (long long)pl->lv[1].ny * pl->lv[0].nx * pl->C;
-    const long long budget = 64ll << 20;
-    pl->tmp_images = (int)std::max<long long>(1, std::min<long long>(pl->B, budget / std::max<long long>(1, pl->tmp_stride * 4)));
+    // intermediate (vertical-pass) image: only the border rows and columns of a level are ever written when the fused
+    // kernel applies, so it is sized for the whole batch (one launch group per level) up to 4 GiB
+    const long long budget = 4096ll << 20;
+    pl->tmp_images = (int)std::max<long long>(1, std::min<long long>(2ll * pl->B, budget / std::max<long long>(1, pl->tmp_stride * 4)));
     pl->tmp_floats = std::max<long long>((long long)pl->tmp_images * pl->tmp_stride, 2 * pl->tmp_stride);
     pl->tmp_floats = (pl->tmp_floats + 3) / 4 * 4;
     TRY(dev_alloc(pl, &pl->tmp, (size_t)pl->tmp_floats));

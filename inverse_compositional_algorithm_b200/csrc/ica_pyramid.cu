@@ -219,11 +219,12 @@ __global__ void __launch_bounds__(256) pyr_vertical_kernel(
 template <int TP>
 __global__ void __launch_bounds__(128) pyr_vertical_fast_kernel(
     const float* __restrict__ in0a, const float* __restrict__ in0b, int nset, long long in_stride, int in_pitch,
-    int ncols4, int oy_lo, int ngroups, int s0,
+    int col4_off, int ncols4, int oy_lo, int ngroups, int s0,
     const FastW fw, float* __restrict__ tmp, long long tmp_stride, int tmp_pitch) {
   const int img = blockIdx.z;
-  const int j4 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j4 >= ncols4 || (int)blockIdx.y >= ngroups) return;
+  const int j4l = blockIdx.x * blockDim.x + threadIdx.x;   // float4 column inside the strip [col4_off, col4_off + ncols4)
+  if (j4l >= ncols4 || (int)blockIdx.y >= ngroups) return;
+  const int j4 = col4_off + j4l;
   const int oy = oy_lo + blockIdx.y * kFRV;
   const float* inb = img < nset ? in0a + (long long)img * in_stride : in0b + (long long)(img - nset) * in_stride;
   const float4* in = reinterpret_cast<const float4*>(inb + (long long)(2 * oy + s0) * in_pitch) + j4;
@@ -271,12 +272,12 @@ __device__ __forceinline__ void block_minmax_atomic(float val, bool active, MinM
 // ---- horizontal pass (general columns) + clip to the parent's range + min/max of the new level
 template <int C>
 __global__ void __launch_bounds__(256) pyr_horizontal_kernel(
-    const float* __restrict__ tmp, long long tmp_stride, int ncols_in, int nx_out, int ny_out, int skip_lo, int skip_hi,
+    const float* __restrict__ tmp, long long tmp_stride, int ncols_in, int nx_out, int r0, int rs_lo, int rs_hi, int skip_lo, int skip_hi,
     const float* __restrict__ Wt /* [taps][nx_out] */, const int* __restrict__ start, int taps,
     float* __restrict__ out0a, float* __restrict__ out0b, int nset, long long out_stride, int out_pitch,
     const MinMaxKeys* __restrict__ mm_parent, MinMaxKeys* __restrict__ mm_child, int mm_stride) {
   const int img = blockIdx.z;
-  const int oy = blockIdx.y;
+  const int oy = skip_range(r0 + blockIdx.y, rs_lo, rs_hi);   // rows r0.. without [rs_lo, rs_hi)
   const int e = blockIdx.x * blockDim.x + threadIdx.x;   // logical flat index over the general columns
   const int ncol = nx_out - (skip_hi - skip_lo);
   const int set = img < nset ? 0 : 1, pb = img - set * nset;
@@ -311,11 +312,11 @@ __global__ void __launch_bounds__(256) pyr_horizontal_kernel(
 // ---- horizontal pass, uniform columns: kFR consecutive outputs per thread, inputs loaded once
 template <int C, int TP>
 __global__ void __launch_bounds__(128) pyr_horizontal_fast_kernel(
-    const float* __restrict__ tmp, long long tmp_stride, int ncols_in, int ox_lo, int ngroups, int s0, const FastW fw,
+    const float* __restrict__ tmp, long long tmp_stride, int ncols_in, int rs_lo, int rs_hi, int ox_lo, int ngroups, int s0, const FastW fw,
     float* __restrict__ out0a, float* __restrict__ out0b, int nset, long long out_stride, int out_pitch,
     const MinMaxKeys* __restrict__ mm_parent, MinMaxKeys* __restrict__ mm_child, int mm_stride) {
   const int img = blockIdx.z;
-  const int oy = blockIdx.y;
+  const int oy = skip_range(blockIdx.y, rs_lo, rs_hi);   // all rows but [rs_lo, rs_hi) (those belong to the fused kernel)
   const int g = blockIdx.x * blockDim.x + threadIdx.x;   // (group of kFR columns) * C + channel
   const int set = img < nset ? 0 : 1, pb = img - set * nset;
   float* out0 = (set ? out0b : out0a) + (long long)pb * out_stride;
@@ -363,6 +364,131 @@ __global__ void __launch_bounds__(128) pyr_horizontal_fast_kernel(
     __syncthreads();
     if (threadIdx.x == 0) {
       for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { kmin = min(kmin, smin[w]); kmax = max(kmax, smax[w]); }
+      MinMaxKeys* ck = mm_child + (long long)pb * mm_stride + set;
+      if (kmin <= kmax) { atomicMin(&ck->lo, kmin); atomicMax(&ck->hi, kmax); }
+    }
+  }
+}
+
+// ---- both passes in one kernel for the region where rows AND columns are uniform (exact 2:1, interior): a block
+// produces kFRV output rows x OWB output pixels.  Stage 1 = the vertical pass on the input window of the strip
+// (one float4 column and kFRV output rows per thread, as in pyr_vertical_fast_kernel) into shared memory; stage 2 =
+// the horizontal pass from shared memory (kFH consecutive outputs of one channel per task), clip, min/max, store.
+// The intermediate image never goes to global memory.  Shared rows are padded (one float every 2*kFH*C) so that the
+// strided reads of stage 2 spread over the banks.
+constexpr int kFH = 4;
+template <int C> struct FusedCfg {
+  static constexpr int OWB = C == 3 ? 64 : 192;            // output pixels per strip (192 floats per output row)
+  static constexpr int PADN = 2 * kFH * C;                 // floats between pads
+  static constexpr int TASKS_PER_ROW = (OWB / kFH) * C;    // 48
+};
+template <int C, int TP>
+__global__ void __launch_bounds__(128) pyr_fused_fast_kernel(
+    const float* __restrict__ in0a, const float* __restrict__ in0b, int nset, long long in_stride, int in_pitch, int ncols,
+    int oy_lo, int s0y, const FastW fwy, int ox_lo, int ox_hi, int s0x, const FastW fwx,
+    float* __restrict__ out0a, float* __restrict__ out0b, long long out_stride, int out_pitch,
+    const MinMaxKeys* __restrict__ mm_parent, MinMaxKeys* __restrict__ mm_child, int mm_stride) {
+  constexpr int OWB = FusedCfg<C>::OWB, PADN = FusedCfg<C>::PADN, TPR = FusedCfg<C>::TASKS_PER_ROW;
+  constexpr int WF = ((2 * (OWB - 1) + TP) * C + 3 + 3) / 4 * 4;   // window floats incl. alignment slack, float4 multiple
+  constexpr int NW4 = WF / 4;
+  constexpr int SP = WF + WF / PADN + 4;                           // padded shared row
+  static_assert(NW4 <= 128, "one float4 column per thread");
+  __shared__ float stmp[kFRV][SP];
+  const int img = blockIdx.z;
+  const int set = img < nset ? 0 : 1, pb = img - set * nset;
+  const int ox0 = ox_lo + blockIdx.x * OWB;
+  const int oy = oy_lo + blockIdx.y * kFRV;
+  const int fstart = (2 * ox0 + s0x) * C;          // first float of the strip's footprint in an input row
+  const int f0 = fstart & ~3;                      // 16-byte aligned window start
+  const int t = threadIdx.x;
+  // Shared position of the window float g (counted from the strip's first footprint float `fstart`): g + g / PADN.
+  // A horizontal task reads g = PADN * og + c + C * j, whose pad count is og + j / (2 * kFH) -- a compile-time offset.
+  const int shift = fstart - f0;
+  // ---- stage 1: vertical pass (packed fp32: the float4 column is two FFMA2 lanes)
+  {
+    const float* inb = (set ? in0b : in0a) + (long long)pb * in_stride;
+    const bool act = t < NW4 && f0 + 4 * t < ncols;
+    float2 acc[kFRV][2];
+#pragma unroll
+    for (int r = 0; r < kFRV; ++r) { acc[r][0] = make_float2(0.f, 0.f); acc[r][1] = make_float2(0.f, 0.f); }
+    if (act) {
+      const float4* in = reinterpret_cast<const float4*>(inb + (long long)(2 * oy + s0y) * in_pitch + f0) + t;
+      const int p4 = in_pitch >> 2;
+#pragma unroll
+      for (int j = 0; j < TP + 2 * (kFRV - 1); ++j) {
+        const float4 v = __ldg(in + (long long)j * p4);
+        const float2 vlo2 = make_float2(v.x, v.y), vhi2 = make_float2(v.z, v.w);
+#pragma unroll
+        for (int r = 0; r < kFRV; ++r) {
+          const int k = j - 2 * r;
+          if (k >= 0 && k < TP) {
+            const float2 w2 = make_float2(fwy.w[k], fwy.w[k]);
+            acc[r][0] = __ffma2_rn(w2, vlo2, acc[r][0]);
+            acc[r][1] = __ffma2_rn(w2, vhi2, acc[r][1]);
+          }
+        }
+      }
+    }
+    if (t < NW4) {
+      int pos[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const int g = 4 * t + i - shift; pos[i] = g >= 0 ? g + g / PADN : -1; }
+#pragma unroll
+      for (int r = 0; r < kFRV; ++r) {
+        if (pos[0] >= 0) stmp[r][pos[0]] = acc[r][0].x;
+        if (pos[1] >= 0) stmp[r][pos[1]] = acc[r][0].y;
+        if (pos[2] >= 0) stmp[r][pos[2]] = acc[r][1].x;
+        if (pos[3] >= 0) stmp[r][pos[3]] = acc[r][1].y;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- stage 2: horizontal pass from shared memory
+  float* out0 = (set ? out0b : out0a) + (long long)pb * out_stride;
+  const MinMaxKeys pk = mm_parent[(long long)pb * mm_stride + set];
+  const float lo = key_float(pk.lo), hi = key_float(pk.hi);
+  float vmin = 3.4e38f, vmax = -3.4e38f;
+#pragma unroll 1
+  for (int q = t; q < kFRV * TPR; q += 128) {
+    const int r = q / TPR, rem = q - r * TPR;
+    const int og = rem / C, c = rem - og * C;
+    const int ox = ox0 + og * kFH;
+    if (ox >= ox_hi) continue;                       // partial last strip (ox_hi - ox_lo is a multiple of kFH)
+    const float* src = &stmp[r][(PADN + 1) * og + c];
+    float acc[kFH];
+#pragma unroll
+    for (int i = 0; i < kFH; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < TP + 2 * (kFH - 1); ++j) {
+      const float v = src[C * j + j / (2 * kFH)];
+#pragma unroll
+      for (int i = 0; i < kFH; ++i) {
+        const int k = j - 2 * i;
+        if (k >= 0 && k < TP) acc[i] = fmaf(fwx.w[k], v, acc[i]);
+      }
+    }
+    float* o = out0 + (long long)(oy + r) * out_pitch + ox * C + c;
+#pragma unroll
+    for (int i = 0; i < kFH; ++i) {
+      const float val = fminf(fmaxf(acc[i], lo), hi);
+      o[i * C] = val;
+      vmin = fminf(vmin, val); vmax = fmaxf(vmax, val);
+    }
+  }
+  {
+    unsigned kmin = vmin <= vmax ? float_key(vmin) : 0xffffffffu;
+    unsigned kmax = vmin <= vmax ? float_key(vmax) : 0u;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+      kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    __shared__ unsigned smin[4], smax[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { smin[warp] = kmin; smax[warp] = kmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 4; ++w) { kmin = min(kmin, smin[w]); kmax = max(kmax, smax[w]); }
       MinMaxKeys* ck = mm_child + (long long)pb * mm_stride + set;
       if (kmin <= kmax) { atomicMin(&ck->lo, kmin); atomicMax(&ck->hi, kmax); }
     }
@@ -442,26 +568,42 @@ static void fast_groups(const FastRows& f, int n_in, int TP, int FR, int* lo, in
   *lo = l; *ngroups = std::max(ng, 0);
 }
 
+// vertical fast pass on the float4 columns [col4_off, col4_off + ncols4) of the rows lo .. lo + ngroups * kFRV
 template <int TP>
 static void launch_vfast(const float* in0a, const float* in0b, int nset, long long in_stride, int in_pitch, int ncols,
-                         const FastRows& f, int lo, int ngroups, float* tmp, long long tmp_stride, cudaStream_t stream) {
+                         int col4_off, int ncols4, const FastRows& f, int lo, int ngroups, float* tmp, long long tmp_stride,
+                         cudaStream_t stream) {
   FastW fw;
   for (int k = 0; k < kFastTapsMax; ++k) fw.w[k] = f.w[k];
-  const int ncols4 = ncols / 4;
   dim3 grid((ncols4 + 127) / 128, ngroups, 2 * nset);
-  pyr_vertical_fast_kernel<TP><<<grid, 128, 0, stream>>>(in0a, in0b, nset, in_stride, in_pitch, ncols4, lo, ngroups, f.s0, fw,
-                                                          tmp, tmp_stride, ncols);
+  pyr_vertical_fast_kernel<TP><<<grid, 128, 0, stream>>>(in0a, in0b, nset, in_stride, in_pitch, col4_off, ncols4, lo, ngroups, f.s0,
+                                                          fw, tmp, tmp_stride, ncols);
 }
 
+// horizontal fast pass on all output rows except [rs_lo, rs_hi)
 template <int C, int TP>
 static void launch_hfast(const float* tmp, long long tmp_stride, int ncols, const FastRows& f, int lo, int ngroups, int ny_out,
-                         float* out0a, float* out0b, int nset, long long out_stride, int out_pitch,
+                         int rs_lo, int rs_hi, float* out0a, float* out0b, int nset, long long out_stride, int out_pitch,
                          const MinMaxKeys* mm_parent, MinMaxKeys* mm_child, int mm_stride, cudaStream_t stream) {
   FastW fw;
   for (int k = 0; k < kFastTapsMax; ++k) fw.w[k] = f.w[k];
-  dim3 grid((ngroups * C + 127) / 128, ny_out, 2 * nset);
-  pyr_horizontal_fast_kernel<C, TP><<<grid, 128, 0, stream>>>(tmp, tmp_stride, ncols, lo, ngroups, f.s0, fw, out0a, out0b, nset,
-                                                               out_stride, out_pitch, mm_parent, mm_child, mm_stride);
+  dim3 grid((ngroups * C + 127) / 128, ny_out - (rs_hi - rs_lo), 2 * nset);
+  pyr_horizontal_fast_kernel<C, TP><<<grid, 128, 0, stream>>>(tmp, tmp_stride, ncols, rs_lo, rs_hi, lo, ngroups, f.s0, fw, out0a,
+                                                               out0b, nset, out_stride, out_pitch, mm_parent, mm_child, mm_stride);
+}
+
+template <int C, int TP>
+static void launch_fused(const float* in0a, const float* in0b, int nset, long long in_stride, int in_pitch, int ncols,
+                         const FastRows& fy, int vlo, int ngv, const FastRows& fx, int hlo, int hhi,
+                         float* out0a, float* out0b, long long out_stride, int out_pitch,
+                         const MinMaxKeys* mm_parent, MinMaxKeys* mm_child, int mm_stride, cudaStream_t stream) {
+  FastW fwy, fwx;
+  for (int k = 0; k < kFastTapsMax; ++k) { fwy.w[k] = fy.w[k]; fwx.w[k] = fx.w[k]; }
+  constexpr int OWB = FusedCfg<C>::OWB;
+  dim3 grid((hhi - hlo + OWB - 1) / OWB, ngv, 2 * nset);
+  pyr_fused_fast_kernel<C, TP><<<grid, 128, 0, stream>>>(in0a, in0b, nset, in_stride, in_pitch, ncols, vlo, fy.s0, fwy, hlo, hhi,
+                                                          fx.s0, fwx, out0a, out0b, out_stride, out_pitch, mm_parent, mm_child,
+                                                          mm_stride);
 }
 
 // One level for `nset` pairs: both image sets (a = I1, b = I2) in the same launches.  mm_parent / mm_child
@@ -474,22 +616,61 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
   const int ncols = nx_in * channels;
   const int ny_out = ry.n_out, nx_out = rx.n_out;
   int nl = 0;
-  // ---- vertical pass: uniform interior rows through the fast kernel (needs 16-byte rows), the rest general
-  int vlo = 0, vhi = 0;
   const bool valign = (ncols % 4 == 0) && (in_pitch % 4 == 0) && (in_stride % 4 == 0) && (tmp_stride % 4 == 0) &&
                       ((reinterpret_cast<unsigned long long>(in0a) | reinterpret_cast<unsigned long long>(in0b) |
                         reinterpret_cast<unsigned long long>(tmp)) & 15ull) == 0;
+  // uniform (exact 2:1) row range [vlo, vhi) and column range [hlo, hhi); TP covers both operators' taps
+  const int tmax = std::max(ry.fast.taps, rx.fast.taps);
+  const int TP = tmax <= 32 ? 32 : kFastTapsMax;
+  int vlo = 0, vhi = 0, ngv = 0, hlo = 0, hhi = 0;
   if (valign && ry.fast.hi - ry.fast.lo >= kFRV) {
-    const int TP = ry.fast.taps <= 32 ? 32 : kFastTapsMax;
-    int lo = 0, ngroups = 0;
-    fast_groups(ry.fast, ny_in, TP, kFRV, &lo, &ngroups);
-    if (ngroups > 0) {
-      vlo = lo; vhi = vlo + ngroups * kFRV;
-      if (TP == 32) launch_vfast<32>(in0a, in0b, nset, in_stride, in_pitch, ncols, ry.fast, lo, ngroups, tmp, tmp_stride, stream);
-      else launch_vfast<kFastTapsMax>(in0a, in0b, nset, in_stride, in_pitch, ncols, ry.fast, lo, ngroups, tmp, tmp_stride, stream);
-      ++nl;
-    }
+    fast_groups(ry.fast, ny_in, TP, kFRV, &vlo, &ngv);
+    vhi = vlo + ngv * kFRV;
   }
+  // the fused kernel needs both ranges; its horizontal tasks produce kFH outputs
+  int fhl = 0, fhn = 0;
+  if (ngv > 0 && rx.fast.hi - rx.fast.lo >= kFH) fast_groups(rx.fast, nx_in, TP, kFH, &fhl, &fhn);
+  const bool fused = ngv > 0 && fhn > 0;
+#define ICA_TP_C(fn, ...) do { if (channels == 3) { if (TP == 32) fn<3, 32>(__VA_ARGS__); else fn<3, kFastTapsMax>(__VA_ARGS__); } \
+                               else { if (TP == 32) fn<1, 32>(__VA_ARGS__); else fn<1, kFastTapsMax>(__VA_ARGS__); } } while (0)
+#define ICA_VF(...) do { if (TP == 32) launch_vfast<32>(__VA_ARGS__); else launch_vfast<kFastTapsMax>(__VA_ARGS__); } while (0)
+  auto hgeneral = [&](int r0, int nrows, int rs_lo, int rs_hi, int skip_lo, int skip_hi) {
+    const int ne = (nx_out - (skip_hi - skip_lo)) * channels;
+    if (ne <= 0 || nrows <= 0) return;
+    const int threads = ne >= 256 ? 256 : ((ne + 31) / 32) * 32;
+    dim3 grid((ne + threads - 1) / threads, nrows, 2 * nset);
+    if (channels == 3)
+      pyr_horizontal_kernel<3><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, r0, rs_lo, rs_hi, skip_lo, skip_hi,
+                                                              rx.weights_t, rx.start, rx.taps, out0a, out0b, nset, out_stride,
+                                                              out_pitch, mm_parent, mm_child, mm_stride);
+    else
+      pyr_horizontal_kernel<1><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, r0, rs_lo, rs_hi, skip_lo, skip_hi,
+                                                              rx.weights_t, rx.start, rx.taps, out0a, out0b, nset, out_stride,
+                                                              out_pitch, mm_parent, mm_child, mm_stride);
+    ++nl;
+  };
+  if (fused) {
+    hlo = fhl; hhi = hlo + fhn * kFH;
+    // (1) interior x interior: both passes in one kernel, no intermediate image
+    ICA_TP_C(launch_fused, in0a, in0b, nset, in_stride, in_pitch, ncols, ry.fast, vlo, ngv, rx.fast, hlo, hhi, out0a, out0b,
+             out_stride, out_pitch, mm_parent, mm_child, mm_stride, stream);
+    ++nl;
+    // (2) interior rows x border columns: vertical fast pass on the two column strips the border outputs read
+    int in_left = 0, in_right = nx_in;
+    for (int ox = 0; ox < hlo; ++ox) in_left = std::max(in_left, rx.start_host[ox] + rx.taps);
+    for (int ox = hhi; ox < nx_out; ++ox) in_right = std::min(in_right, rx.start_host[ox]);
+    const int l4 = std::min(ncols / 4, (in_left * channels + 3) / 4);            // strip [0, l4) in float4 columns
+    const int r4 = std::max(l4, std::min(ncols / 4, (in_right * channels) / 4)); // strip [r4, ncols/4)
+    if (hlo > 0 && l4 > 0) { ICA_VF(in0a, in0b, nset, in_stride, in_pitch, ncols, 0, l4, ry.fast, vlo, ngv, tmp, tmp_stride, stream); ++nl; }
+    if (hhi < nx_out && ncols / 4 - r4 > 0) {
+      ICA_VF(in0a, in0b, nset, in_stride, in_pitch, ncols, r4, ncols / 4 - r4, ry.fast, vlo, ngv, tmp, tmp_stride, stream); ++nl;
+    }
+    hgeneral(vlo, vhi - vlo, 0x7fffffff, 0x7fffffff, hlo, hhi);
+  } else if (ngv > 0) {
+    ICA_VF(in0a, in0b, nset, in_stride, in_pitch, ncols, 0, ncols / 4, ry.fast, vlo, ngv, tmp, tmp_stride, stream);
+    ++nl;
+  }
+  // (3) border rows (all rows when nothing is uniform): general vertical pass ...
   if (ny_out - (vhi - vlo) > 0) {
     dim3 grid((ncols + 255) / 256, (vlo + kVR - 1) / kVR + (ny_out - vhi + kVR - 1) / kVR, 2 * nset);
     pyr_vertical_kernel<<<grid, 256, 0, stream>>>(in0a, in0b, nset, in_stride, in_pitch, ncols, ny_out, vlo, vhi, ry.weights,
@@ -498,35 +679,24 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  // ---- horizontal pass
-  int hlo = 0, hhi = 0;
-  if (rx.fast.hi - rx.fast.lo >= kFR) {
-    const int TP = rx.fast.taps <= 32 ? 32 : kFastTapsMax;
-    int lo = 0, ngroups = 0;
-    fast_groups(rx.fast, nx_in, TP, kFR, &lo, &ngroups);
-    if (ngroups > 0) {
-      hlo = lo; hhi = hlo + ngroups * kFR;
-#define ICA_HF(CC, TT) launch_hfast<CC, TT>(tmp, tmp_stride, ncols, rx.fast, lo, ngroups, ny_out, out0a, out0b, nset, out_stride, out_pitch, mm_parent, mm_child, mm_stride, stream)
-      if (channels == 3) { if (TP == 32) ICA_HF(3, 32); else ICA_HF(3, kFastTapsMax); }
-      else { if (TP == 32) ICA_HF(1, 32); else ICA_HF(1, kFastTapsMax); }
-#undef ICA_HF
-      ++nl;
+  // ... and the horizontal pass of every row the fused kernel did not produce
+  const int rs_lo = fused ? vlo : 0, rs_hi = fused ? vhi : 0;
+  int glo = 0, ghi = 0;   // column range of the uniform horizontal kernel on those rows
+  if (ny_out - (rs_hi - rs_lo) > 0) {
+    if (rx.fast.hi - rx.fast.lo >= kFR) {
+      int lo = 0, ngroups = 0;
+      fast_groups(rx.fast, nx_in, TP, kFR, &lo, &ngroups);
+      if (ngroups > 0) {
+        glo = lo; ghi = glo + ngroups * kFR;
+        ICA_TP_C(launch_hfast, tmp, tmp_stride, ncols, rx.fast, lo, ngroups, ny_out, rs_lo, rs_hi, out0a, out0b, nset, out_stride,
+                 out_pitch, mm_parent, mm_child, mm_stride, stream);
+        ++nl;
+      }
     }
+    hgeneral(0, ny_out - (rs_hi - rs_lo), rs_lo, rs_hi, glo, ghi);
   }
-  if (nx_out - (hhi - hlo) > 0) {
-    const int ne = (nx_out - (hhi - hlo)) * channels;
-    const int threads = ne >= 256 ? 256 : ((ne + 31) / 32) * 32;
-    dim3 grid((ne + threads - 1) / threads, ny_out, 2 * nset);
-    if (channels == 3)
-      pyr_horizontal_kernel<3><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, ny_out, hlo, hhi, rx.weights_t,
-                                                              rx.start, rx.taps, out0a, out0b, nset, out_stride, out_pitch,
-                                                              mm_parent, mm_child, mm_stride);
-    else
-      pyr_horizontal_kernel<1><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, ny_out, hlo, hhi, rx.weights_t,
-                                                              rx.start, rx.taps, out0a, out0b, nset, out_stride, out_pitch,
-                                                              mm_parent, mm_child, mm_stride);
-    ++nl;
-  }
+#undef ICA_TP_C
+#undef ICA_VF
   if (launches) *launches = nl;
   return cudaGetLastError();
 }

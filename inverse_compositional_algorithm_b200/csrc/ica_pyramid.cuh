@@ -23,6 +23,7 @@ struct DeviceResample {
   float* weights = nullptr;
   float* weights_t = nullptr;
   FastRows fast;
+  std::vector<int> start_host;   // host copy of start[] (footprints of the border outputs)
 };
 
 int round_half_even(double v);
