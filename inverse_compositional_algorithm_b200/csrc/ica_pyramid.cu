@@ -251,64 +251,6 @@ __global__ void __launch_bounds__(128) pyr_vertical_fast_kernel(
   for (int r = 0; r < kFRV; ++r) o[(long long)r * t4] = acc[r];
 }
 
-__device__ __forceinline__ void block_minmax_atomic(float val, bool active, MinMaxKeys* ck) {
-  unsigned kmin = active ? float_key(val) : 0xffffffffu;
-  unsigned kmax = active ? float_key(val) : 0u;
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-  }
-  __shared__ unsigned smin[8], smax[8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { smin[warp] = kmin; smax[warp] = kmax; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < (int)((blockDim.x + 31) >> 5); ++w) { kmin = min(kmin, smin[w]); kmax = max(kmax, smax[w]); }
-    if (kmin <= kmax) { atomicMin(&ck->lo, kmin); atomicMax(&ck->hi, kmax); }
-  }
-}
-
-// ---- horizontal pass (general columns) + clip to the parent's range + min/max of the new level
-template <int C>
-__global__ void __launch_bounds__(256) pyr_horizontal_kernel(
-    const float* __restrict__ tmp, long long tmp_stride, int ncols_in, int nx_out, int r0, int rs_lo, int rs_hi, int skip_lo, int skip_hi,
-    const float* __restrict__ Wt /* [taps][nx_out] */, const int* __restrict__ start, int taps,
-    float* __restrict__ out0a, float* __restrict__ out0b, int nset, long long out_stride, int out_pitch,
-    const MinMaxKeys* __restrict__ mm_parent, MinMaxKeys* __restrict__ mm_child, int mm_stride) {
-  const int img = blockIdx.z;
-  const int oy = skip_range(r0 + blockIdx.y, rs_lo, rs_hi);   // rows r0.. without [rs_lo, rs_hi)
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;   // logical flat index over the general columns
-  const int ncol = nx_out - (skip_hi - skip_lo);
-  const int set = img < nset ? 0 : 1, pb = img - set * nset;
-  float* out0 = (set ? out0b : out0a) + (long long)pb * out_stride;
-  const MinMaxKeys pk = mm_parent[(long long)pb * mm_stride + set];
-  const float lo = key_float(pk.lo), hi = key_float(pk.hi);
-  float val = 0.f;
-  const bool active = e < ncol * C;
-  if (active) {
-    const int oxl = e / C, c = e - oxl * C;
-    const int ox = skip_range(oxl, skip_lo, skip_hi);
-    const float* row = tmp + (long long)img * tmp_stride + (long long)oy * ncols_in + c;
-    const int st = __ldg(start + ox);
-    float acc = 0.f;
-    for (int k0 = 0; k0 < taps; k0 += 8) {   // 16 independent loads in flight, same summation order
-      float w[8], v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const bool in = k0 + u < taps;
-        w[u] = in ? __ldg(Wt + (long long)(k0 + u) * nx_out + ox) : 0.f;
-        v[u] = in ? __ldg(row + (st + k0 + u) * C) : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) if (k0 + u < taps) acc = fmaf(w[u], v[u], acc);
-    }
-    val = fminf(fmaxf(acc, lo), hi);
-    out0[(long long)oy * out_pitch + ox * C + c] = val;
-  }
-  block_minmax_atomic(val, active, mm_child + (long long)pb * mm_stride + set);
-}
-
 // ---- horizontal pass, uniform columns: kFR consecutive outputs per thread, inputs loaded once
 template <int C, int TP>
 __global__ void __launch_bounds__(128) pyr_horizontal_fast_kernel(
@@ -364,6 +306,134 @@ __global__ void __launch_bounds__(128) pyr_horizontal_fast_kernel(
     __syncthreads();
     if (threadIdx.x == 0) {
       for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { kmin = min(kmin, smin[w]); kmax = max(kmax, smax[w]); }
+      MinMaxKeys* ck = mm_child + (long long)pb * mm_stride + set;
+      if (kmin <= kmax) { atomicMin(&ck->lo, kmin); atomicMax(&ck->hi, kmax); }
+    }
+  }
+}
+
+// ---- border rows, 16-byte aligned images: 4 float columns x kVR output rows per thread.  The rows of a group read a
+// common range of input rows; their weights are laid out zero-padded over that range ([input row][output row] in
+// shared memory), so the inner loop is one LDG.128 + one LDS.128 + 16 FMA with no predicates.
+constexpr int kVSpan = kMaxTaps + 16;
+__global__ void __launch_bounds__(128) pyr_vertical_border4_kernel(
+    const float* __restrict__ in0a, const float* __restrict__ in0b, int nset, long long in_stride, int in_pitch,
+    int ncols4, int ny_out, int skip_lo, int skip_hi,
+    const float* __restrict__ W, const int* __restrict__ start, int taps,
+    float* __restrict__ tmp, long long tmp_stride, int tmp_pitch) {
+  __shared__ float4 sw[kVSpan];   // sw[i] = weights of the group's (up to) 4 output rows for input row row_lo + i
+  __shared__ int sst[kVR], soy[kVR], srange[2];
+  const int img = blockIdx.z;
+  const int gA = (skip_lo + kVR - 1) / kVR;   // row groups never straddle [skip_lo, skip_hi)
+  if (threadIdx.x < kVR) {
+    int oy;
+    if ((int)blockIdx.y < gA) { oy = blockIdx.y * kVR + threadIdx.x; if (oy >= skip_lo) oy = -1; }
+    else { oy = skip_hi + ((int)blockIdx.y - gA) * kVR + threadIdx.x; if (oy >= ny_out) oy = -1; }
+    soy[threadIdx.x] = oy;
+    sst[threadIdx.x] = oy >= 0 ? start[oy] : -1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int lo = 0x7fffffff, hi = 0;
+    for (int r = 0; r < kVR; ++r) if (soy[r] >= 0) { lo = min(lo, sst[r]); hi = max(hi, sst[r] + taps); }
+    srange[0] = lo; srange[1] = min(hi, lo + kVSpan);   // (spans beyond kVSpan do not occur: starts of neighbours differ by <= 2)
+  }
+  __syncthreads();
+  const int row_lo = srange[0], n = srange[1] - srange[0];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float w[kVR];
+#pragma unroll
+    for (int r = 0; r < kVR; ++r) {
+      const int k = row_lo + i - sst[r];
+      w[r] = (soy[r] >= 0 && k >= 0 && k < taps) ? W[(long long)soy[r] * taps + k] : 0.f;
+    }
+    sw[i] = make_float4(w[0], w[1], w[2], w[3]);
+  }
+  __syncthreads();
+  const int j4 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j4 >= ncols4) return;
+  const float* inb = img < nset ? in0a + (long long)img * in_stride : in0b + (long long)(img - nset) * in_stride;
+  const float4* in = reinterpret_cast<const float4*>(inb + (long long)row_lo * in_pitch) + j4;
+  const int p4 = in_pitch >> 2;
+  float4 acc[kVR];
+#pragma unroll
+  for (int r = 0; r < kVR; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int i = 0; i < n; ++i) {
+    const float4 v = __ldg(in + (long long)i * p4);
+    const float4 w = sw[i];
+    acc[0].x = fmaf(w.x, v.x, acc[0].x); acc[0].y = fmaf(w.x, v.y, acc[0].y); acc[0].z = fmaf(w.x, v.z, acc[0].z); acc[0].w = fmaf(w.x, v.w, acc[0].w);
+    acc[1].x = fmaf(w.y, v.x, acc[1].x); acc[1].y = fmaf(w.y, v.y, acc[1].y); acc[1].z = fmaf(w.y, v.z, acc[1].z); acc[1].w = fmaf(w.y, v.w, acc[1].w);
+    acc[2].x = fmaf(w.z, v.x, acc[2].x); acc[2].y = fmaf(w.z, v.y, acc[2].y); acc[2].z = fmaf(w.z, v.z, acc[2].z); acc[2].w = fmaf(w.z, v.w, acc[2].w);
+    acc[3].x = fmaf(w.w, v.x, acc[3].x); acc[3].y = fmaf(w.w, v.y, acc[3].y); acc[3].z = fmaf(w.w, v.z, acc[3].z); acc[3].w = fmaf(w.w, v.w, acc[3].w);
+  }
+  float4* o = reinterpret_cast<float4*>(tmp + (long long)img * tmp_stride) + j4;
+  const int t4 = tmp_pitch >> 2;
+#pragma unroll
+  for (int r = 0; r < kVR; ++r) if (soy[r] >= 0) o[(long long)soy[r] * t4] = acc[r];
+}
+
+// ---- border columns: kHR output rows per thread (the weight of a tap is loaded once and used for all of them)
+constexpr int kHR = 8;
+template <int C>
+__global__ void __launch_bounds__(128) pyr_horizontal_border_kernel(
+    const float* __restrict__ tmp, long long tmp_stride, int ncols_in, int nx_out, int r0, int nrows, int rs_lo, int rs_hi,
+    int skip_lo, int skip_hi, const float* __restrict__ Wt /* [taps][nx_out] */, const int* __restrict__ start, int taps,
+    float* __restrict__ out0a, float* __restrict__ out0b, int nset, long long out_stride, int out_pitch,
+    const MinMaxKeys* __restrict__ mm_parent, MinMaxKeys* __restrict__ mm_child, int mm_stride) {
+  const int img = blockIdx.z;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;   // logical flat index over the border columns
+  const int ncol = nx_out - (skip_hi - skip_lo);
+  const int set = img < nset ? 0 : 1, pb = img - set * nset;
+  float* out0 = (set ? out0b : out0a) + (long long)pb * out_stride;
+  const MinMaxKeys pk = mm_parent[(long long)pb * mm_stride + set];
+  const float lo = key_float(pk.lo), hi = key_float(pk.hi);
+  const bool active = e < ncol * C;
+  float vmin = 3.4e38f, vmax = -3.4e38f;
+  if (active) {
+    const int oxl = e / C, c = e - oxl * C;
+    const int ox = skip_range(oxl, skip_lo, skip_hi);
+    const int st = __ldg(start + ox);
+    const float* rows[kHR];
+    int oys[kHR];
+#pragma unroll
+    for (int i = 0; i < kHR; ++i) {
+      const int rl = blockIdx.y * kHR + i;                       // row of this launch
+      oys[i] = rl < nrows ? skip_range(r0 + rl, rs_lo, rs_hi) : -1;
+      rows[i] = tmp + (long long)img * tmp_stride + (long long)(oys[i] >= 0 ? oys[i] : oys[0]) * ncols_in + st * C + c;
+    }
+    float acc[kHR];
+#pragma unroll
+    for (int i = 0; i < kHR; ++i) acc[i] = 0.f;
+    const float* wp = Wt + ox;
+#pragma unroll 2
+    for (int k = 0; k < taps; ++k) {
+      const float w = __ldg(wp + (long long)k * nx_out);
+#pragma unroll
+      for (int i = 0; i < kHR; ++i) acc[i] = fmaf(w, __ldg(rows[i] + k * C), acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < kHR; ++i) {
+      if (oys[i] < 0) continue;
+      const float val = fminf(fmaxf(acc[i], lo), hi);
+      out0[(long long)oys[i] * out_pitch + ox * C + c] = val;
+      vmin = fminf(vmin, val); vmax = fmaxf(vmax, val);
+    }
+  }
+  {
+    unsigned kmin = vmin <= vmax ? float_key(vmin) : 0xffffffffu;
+    unsigned kmax = vmin <= vmax ? float_key(vmax) : 0u;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+      kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    __shared__ unsigned smin[4], smax[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { smin[warp] = kmin; smax[warp] = kmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < (int)((blockDim.x + 31) >> 5); ++w) { kmin = min(kmin, smin[w]); kmax = max(kmax, smax[w]); }
       MinMaxKeys* ck = mm_child + (long long)pb * mm_stride + set;
       if (kmin <= kmax) { atomicMin(&ck->lo, kmin); atomicMax(&ck->hi, kmax); }
     }
@@ -637,16 +707,16 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
   auto hgeneral = [&](int r0, int nrows, int rs_lo, int rs_hi, int skip_lo, int skip_hi) {
     const int ne = (nx_out - (skip_hi - skip_lo)) * channels;
     if (ne <= 0 || nrows <= 0) return;
-    const int threads = ne >= 256 ? 256 : ((ne + 31) / 32) * 32;
-    dim3 grid((ne + threads - 1) / threads, nrows, 2 * nset);
+    const int threads = ne >= 128 ? 128 : ((ne + 31) / 32) * 32;
+    dim3 grid((ne + threads - 1) / threads, (nrows + kHR - 1) / kHR, 2 * nset);
     if (channels == 3)
-      pyr_horizontal_kernel<3><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, r0, rs_lo, rs_hi, skip_lo, skip_hi,
-                                                              rx.weights_t, rx.start, rx.taps, out0a, out0b, nset, out_stride,
-                                                              out_pitch, mm_parent, mm_child, mm_stride);
+      pyr_horizontal_border_kernel<3><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, r0, nrows, rs_lo, rs_hi, skip_lo,
+                                                                     skip_hi, rx.weights_t, rx.start, rx.taps, out0a, out0b, nset,
+                                                                     out_stride, out_pitch, mm_parent, mm_child, mm_stride);
     else
-      pyr_horizontal_kernel<1><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, r0, rs_lo, rs_hi, skip_lo, skip_hi,
-                                                              rx.weights_t, rx.start, rx.taps, out0a, out0b, nset, out_stride,
-                                                              out_pitch, mm_parent, mm_child, mm_stride);
+      pyr_horizontal_border_kernel<1><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, r0, nrows, rs_lo, rs_hi, skip_lo,
+                                                                     skip_hi, rx.weights_t, rx.start, rx.taps, out0a, out0b, nset,
+                                                                     out_stride, out_pitch, mm_parent, mm_child, mm_stride);
     ++nl;
   };
   if (fused) {
@@ -672,9 +742,16 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
   }
   // (3) border rows (all rows when nothing is uniform): general vertical pass ...
   if (ny_out - (vhi - vlo) > 0) {
-    dim3 grid((ncols + 255) / 256, (vlo + kVR - 1) / kVR + (ny_out - vhi + kVR - 1) / kVR, 2 * nset);
-    pyr_vertical_kernel<<<grid, 256, 0, stream>>>(in0a, in0b, nset, in_stride, in_pitch, ncols, ny_out, vlo, vhi, ry.weights,
-                                                   ry.start, ry.taps, tmp, tmp_stride);
+    const int ngroups = (vlo + kVR - 1) / kVR + (ny_out - vhi + kVR - 1) / kVR;
+    if (valign) {
+      dim3 grid((ncols / 4 + 127) / 128, ngroups, 2 * nset);
+      pyr_vertical_border4_kernel<<<grid, 128, 0, stream>>>(in0a, in0b, nset, in_stride, in_pitch, ncols / 4, ny_out, vlo, vhi,
+                                                             ry.weights, ry.start, ry.taps, tmp, tmp_stride, ncols);
+    } else {
+      dim3 grid((ncols + 255) / 256, ngroups, 2 * nset);
+      pyr_vertical_kernel<<<grid, 256, 0, stream>>>(in0a, in0b, nset, in_stride, in_pitch, ncols, ny_out, vlo, vhi, ry.weights,
+                                                     ry.start, ry.taps, tmp, tmp_stride);
+    }
     ++nl;
   }
   cudaError_t e = cudaGetLastError();
