@@ -355,7 +355,10 @@ def run_ours(args, wl):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "iterate_dram_bytes.json")) as f:
-            traffic = json.load(f).get("traffic_bytes_per_launch")
+            prof = json.load(f)
+            # ncu capture of a 32-pair step: DRAM bytes of the kernel relative to its algorithmic bytes, applied to the
+            # per-launch algorithmic bytes of this run (same workload, different batch size)
+            traffic = prof["traffic_over_algorithmic"] * ab / max(1, tm["iterate_launches"])
     except Exception:  # noqa: BLE001
         pass
     line = {
