@@ -456,3 +456,26 @@ def test_non_converging_pair_matches_oracle(nat):
     o = np.array([tr[2] for tr in trace[:30]])
     print("gpu |dp|", g[:8], "oracle |dp|", o[:8], "final epe gpu-vs-oracle", _epe(pr[bad], po, t.value, 1024, 1024))
     assert np.allclose(g[:5], o[:5], rtol=1e-3)
+
+
+@pytest.mark.parametrize("shape,channels,ttype_name,rtype", [((93, 121), 3, "HOMOGRAPHY", 3), ((77, 101), 1, "AFFINITY", 0),
+                                                             ((64, 67), 3, "SIMILARITY", 4)])
+def test_unaligned_shapes_match_oracle(nat, shape, channels, ttype_name, rtype):
+    """Image rows that are not multiples of 16 bytes: the iterate kernel then works on padded level-0 copies (its TMA
+    tensor maps need 16-byte row pitches) and the pyramid takes its unaligned path; results must still match the oracle."""
+    from inverse_compositional_algorithm_b200 import synthetic
+    from inverse_compositional_algorithm_b200.inverse_compositional_algorithm import register_batch
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    t = TransformType[ttype_name]
+    h, w = shape
+    assert (w * channels) % 4 != 0
+    pairs = [synthetic.make_pair(700 + i, h, w, channels, t, max_shift=2.0, margin=32) for i in range(3)]
+    I1 = np.stack([a for a, _, _ in pairs]); I2 = np.stack([b for _, b, _ in pairs])
+    p, err, iters = register_batch(I1, I2, t, nscales=2, robust_type=rtype, delta=5)
+    for i in range(3):
+        a, b = (np.repeat(x, 3, 2) if channels == 1 else x for x in (I1[i], I2[i]))
+        trace = []
+        po, eo, _, _ = orc.ica_pyramidal(a.astype(np.float64), b.astype(np.float64), np.zeros(t.nparams()), t.value, 2, 0.5,
+                                         1e-3, rtype, 0.0, True, 5, trace=trace)
+        assert _epe(p[i, :t.nparams()], po, t.value, w, h) <= EPE_TOL
+        assert int(iters[i].sum()) == len(trace)
