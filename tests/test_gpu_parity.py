@@ -479,3 +479,26 @@ def test_unaligned_shapes_match_oracle(nat, shape, channels, ttype_name, rtype):
                                          1e-3, rtype, 0.0, True, 5, trace=trace)
         assert _epe(p[i, :t.nparams()], po, t.value, w, h) <= EPE_TOL
         assert int(iters[i].sum()) == len(trace)
+
+
+@pytest.mark.parametrize("theta,rtype", [(0.30, 0), (-0.22, 3)])
+def test_large_rotation_takes_global_path(nat, theta, rtype):
+    """A rotation so strong that the window of I2 a 64x11 tile reaches does not fit the staged box: every pixel then
+    samples I2 from global memory (the kernel's generic path).  Same answer as the oracle from the same start."""
+    from inverse_compositional_algorithm_b200 import synthetic
+    from inverse_compositional_algorithm_b200.inverse_compositional_algorithm import (
+        inverse_compositional_algorithm, robust_inverse_compositional_algorithm)
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    t = TransformType.EUCLIDEAN
+    p_gt = np.array([3.0, -2.0, theta])
+    I1, I2, _ = synthetic.make_pair(800, 150, 190, 3, t, margin=96, p_gt=p_gt)
+    p0 = p_gt + np.array([0.6, -0.4, 0.004])
+    a, b = I1.astype(np.float64), I2.astype(np.float64)
+    if rtype == 0:
+        p, err, DI, Iw = inverse_compositional_algorithm(a, b, p0.copy(), t, 1e-3, True, 5, False)
+        po, eo, _, _ = orc.ica_quadratic(a, b, p0.copy(), t.value, 1e-3, True, 5)
+    else:
+        p, err, DI, Iw = robust_inverse_compositional_algorithm(a, b, p0.copy(), t, 1e-3, rtype, 0.0, True, 5, False)
+        po, eo, _, _ = orc.ica_robust(a, b, p0.copy(), t.value, 1e-3, rtype, 0.0, True, 5)
+    assert _epe(p, po, t.value, 190, 150) <= EPE_TOL
+    assert _epe(p, p_gt, t.value, 190, 150) <= 0.1
