@@ -205,6 +205,31 @@ ICA_API int ica_zoom_in_parameters(const double* p, int32_t transform_type, doub
    matrix when exactly singular; n <= 8 */
 ICA_API int ica_inverse_hessian(const double* H, int32_t n, double* H_inv);
 
+/* ---- helper API on materialised float64 arrays (what callers of the reference's helper modules import).
+   The drivers never materialise these arrays; the entry points exist for callers of the helpers.  Host buffers. */
+/* io.rhop (src/image_optimisation.py:17-53), element-wise over `count` values of t2 */
+ICA_API int ica_rhop_host(const double* t2, int64_t count, double lambda_, int32_t robust_type, double* out);
+/* io.robust_error_function (io.py:56-79): DI [H][W][C] -> rho [H][W] */
+ICA_API int ica_robust_error_host(const double* DI, int32_t height, int32_t width, int32_t channels, double lambda_,
+                                  int32_t robust_type, double* rho_out);
+/* io.steepest_descent_images (io.py:158-194): Ix, Iy [H][W][C], J [H][W][2n] -> DIJ [H][W][C][n] */
+ICA_API int ica_steepest_descent_host(const double* Ix, const double* Iy, const double* J, int32_t height, int32_t width,
+                                      int32_t channels, int32_t nparams, double* DIJ_out);
+/* de.hessian / de.hessian_robust (derivatives.py:73-107) when DI == NULL: out = H [n][n];
+   io.independent_vector / _robust (io.py:82-143) when DI is given: out = b [n].  rho == NULL: unweighted. */
+ICA_API int ica_dij_reduce_host(const double* DIJ, const double* DI, const double* rho, int32_t height, int32_t width,
+                                int32_t channels, int32_t nparams, double* out);
+/* tr.transform_image (transformation.py:266-318): skimage warp, order 1, cval 0, clip; matrix9 maps output (col,row) to
+   input (the caller passes the inverse of the transform it wants to apply, as the reference does with tform.inverse) */
+ICA_API int ica_transform_image_host(const double* image, int32_t height, int32_t width, int32_t channels,
+                                     const double* matrix9, double* out);
+
+/* bi.bicubic_interpolation_image (bicubic_interpolation.py:121-152): the IPOL-style warp -- the model is selected by
+   the number of parameters (tr.project, transformation.py:144-186), NaN (nanifoutside) or 0 within `delta` of the border
+   of the projected domain, Catmull-Rom with clamped (Neumann) neighbours, no clipping.  Not used by the drivers. */
+ICA_API int ica_warp_ipol_host(const double* image, int32_t height, int32_t width, int32_t channels, const double* params,
+                               int32_t nparams, int32_t nanifoutside, int32_t delta, double* out);
+
 #ifdef __cplusplus
 }
 #endif

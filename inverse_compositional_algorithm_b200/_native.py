@@ -71,6 +71,12 @@ SIGNATURES = {
     "ica_plan_last_launch_count": (C.c_int64, [_P]),
     "ica_plan_enable_timing": (C.c_int, [_P, C.c_int32]),
     "ica_plan_get_timing": (C.c_int, [_P, _PF, _PI, _PF, _PI]),
+    "ica_rhop_host": (C.c_int, [_P, C.c_int64, C.c_double, C.c_int32, _P]),
+    "ica_robust_error_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, _P]),
+    "ica_steepest_descent_host": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "ica_dij_reduce_host": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "ica_transform_image_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "ica_warp_ipol_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "ica_warp_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "ica_rescale_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _PI, _PI]),
     "ica_resample_operator": (C.c_int, [C.c_int32, C.c_int32, _PI, _PI, _P, C.c_int32, _PI]),
@@ -223,6 +229,73 @@ def _as_image_f32(image) -> np.ndarray:
     if img.ndim != 3 or img.shape[2] not in (1, 3):
         raise ValueError("image must be (H, W), (H, W, 1) or (H, W, 3)")
     return img
+
+
+# ---- helper API on materialised float64 arrays (include/ica_b200.h, last section)
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def rhop(t2, lambda_: float, robust_type: int) -> np.ndarray:
+    require_gpu()
+    a = _f64(t2)
+    out = np.empty_like(a)
+    check(lib().ica_rhop_host(_ptr(a.reshape(-1)), a.size, float(lambda_), int(robust_type), _ptr(out.reshape(-1))))
+    return out
+
+
+def robust_error(DI, lambda_: float, robust_type: int) -> np.ndarray:
+    require_gpu()
+    d = _f64(DI)
+    ny, nx, nz = d.shape
+    rho = np.empty((ny, nx))
+    check(lib().ica_robust_error_host(_ptr(d), ny, nx, nz, float(lambda_), int(robust_type), _ptr(rho)))
+    return rho
+
+
+def steepest_descent(Ix, Iy, J, nparams: int) -> np.ndarray:
+    require_gpu()
+    ix, iy, j = _f64(Ix), _f64(Iy), _f64(J)
+    ny, nx, nz = ix.shape
+    out = np.empty((ny, nx, nz, nparams))
+    check(lib().ica_steepest_descent_host(_ptr(ix), _ptr(iy), _ptr(j), ny, nx, nz, int(nparams), _ptr(out)))
+    return out
+
+
+def dij_reduce(DIJ, DI=None, rho=None) -> np.ndarray:
+    """H (DI is None) or b (DI given), optionally rho-weighted."""
+    require_gpu()
+    dij = _f64(DIJ)
+    ny, nx, nz, n = dij.shape
+    di = _f64(DI) if DI is not None else None
+    r = _f64(rho) if rho is not None else None
+    out = np.empty(n if di is not None else (n, n))
+    check(lib().ica_dij_reduce_host(_ptr(dij), _ptr(di) if di is not None else None, _ptr(r) if r is not None else None,
+                                    ny, nx, nz, n, _ptr(out)))
+    return out
+
+
+def transform_image(image, inverse_matrix) -> np.ndarray:
+    require_gpu()
+    img = _f64(image)
+    squeeze = img.ndim == 2
+    if squeeze:
+        img = img[:, :, None]
+    m = _f64(inverse_matrix).reshape(9)
+    out = np.empty_like(img)
+    check(lib().ica_transform_image_host(_ptr(img), img.shape[0], img.shape[1], img.shape[2], _ptr(m), _ptr(out)))
+    return out[:, :, 0] if squeeze else out
+
+
+def warp_ipol(image, params, nparams: int, nanifoutside: bool, delta: int) -> np.ndarray:
+    require_gpu()
+    img = _f64(image)
+    p = np.zeros(8)
+    p[:nparams] = np.asarray(params, dtype=np.float64)[:nparams]
+    out = np.empty_like(img)
+    check(lib().ica_warp_ipol_host(_ptr(img), img.shape[0], img.shape[1], img.shape[2], _ptr(p), int(nparams),
+                                   1 if nanifoutside else 0, int(delta), _ptr(out)))
+    return out
 
 
 def warp(image, matrix) -> np.ndarray:

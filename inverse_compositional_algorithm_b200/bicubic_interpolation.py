@@ -27,3 +27,29 @@ def bicubic_interpolation_skimage(image, params, transformation_type, nanifoutsi
     img = np.asarray(image)
     out = _native.warp(img, m).astype(np.float64)
     return out[:, :, 0] if img.ndim == 2 else out
+
+
+# ---- the IPOL-style warp and its scalar helpers (secondary API surface of the reference; not on the drivers' path)
+def neumann_bc(x, nx):
+    """``src/bicubic_interpolation.py:8-25``: clamp an index to ``[0, nx-1]``."""
+    return 0 if x < 0 else (nx - 1 if x >= nx else x)
+
+
+def cubic_interpolation(v, x):
+    """``src/bicubic_interpolation.py:28-41``: Catmull-Rom through four samples at parameter ``x``."""
+    return v[1] + 0.5 * x * (v[2] - v[0] + x * (2.0 * v[0] - 5.0 * v[1] + 4.0 * v[2] - v[3]
+                                                + x * (3.0 * (v[1] - v[2]) + v[3] - v[0])))
+
+
+def bicubic_interpolation_array(p, x, y):
+    """``src/bicubic_interpolation.py:44-63``: 4x4 samples ``p[a][b]``, interpolated along ``b`` at ``y``, then at ``x``."""
+    return cubic_interpolation([cubic_interpolation(p[a], y) for a in range(4)], x)
+
+
+def bicubic_interpolation_image(input, params, nparams, nanifoutside, delta):
+    """``src/bicubic_interpolation.py:121-152``: warp of the whole image, IPOL conventions -- the model is selected by
+    ``nparams`` (2/3/4/6/8), NaN (``nanifoutside``) or 0 where the projected point is within ``delta`` of the border,
+    Catmull-Rom with clamped neighbours, no clipping.  Computed on the GPU (``ica_warp_ipol_host``), float64."""
+    if nparams not in (2, 3, 4, 6, 8):
+        raise ValueError("Invalid transformation type")
+    return _native.warp_ipol(np.asarray(input, dtype=np.float64), params, nparams, bool(nanifoutside), int(delta))

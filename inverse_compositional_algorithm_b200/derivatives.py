@@ -46,6 +46,17 @@ def hessian_and_b(I1, I2, p, transform_type, robust_type=0, lambda_=0.0, nanifou
                              nanifoutside is True)
 
 
+def hessian(DIJ):
+    """``src/derivatives.py:73-88``: ``H = sum_{y,x,c} DIJ_c (x) DIJ_c`` on a materialised DIJ (non-finite entries
+    zero-filled element-wise)."""
+    return _native.dij_reduce(DIJ)
+
+
+def hessian_robust(DIJ, rho, nparams):
+    """``src/derivatives.py:91-107``: ``H = sum_{y,x} rho[y,x] sum_c DIJ_c (x) DIJ_c``."""
+    return _native.dij_reduce(DIJ, rho=rho)
+
+
 def inverse_hessian(H, nparams):
     """``src/derivatives.py:110-130``: LU inverse (partial pivoting); zero matrix when singular."""
     return _native.inverse_hessian(np.asarray(H, dtype=np.float64)[:nparams, :nparams])

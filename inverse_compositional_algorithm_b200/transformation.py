@@ -66,6 +66,25 @@ def matrix2params(matrix, transform_type):
     return [m[0, 0] - 1, m[0, 1], m[0, 2], m[1, 0], m[1, 1] - 1, m[1, 2], m[2, 0], m[2, 1]]
 
 
+def transform_image(image, transformation_type, gt):
+    """``src/transformation.py:266-318``: the notebooks' test-data generator -- the image warped by the INVERSE of the
+    model matrix with skimage's defaults (bilinear, zero outside, clipped to the input range), on the GPU.
+    Like the reference, TRANSLATION uses the translation only and EUCLIDEAN is built from ``rotation=-gt[2]``
+    (``transformation.py:309``); all-zero parameters mean the identity."""
+    from . import _native
+    t = _as_type(transformation_type)
+    gt = [float(v) for v in gt]
+    if all(abs(v) < 1e-10 for v in gt):
+        m = np.eye(3)
+    elif t == TransformType.EUCLIDEAN:
+        m = params2matrix([gt[0], gt[1], -gt[2]], t)
+    elif t == TransformType.TRANSLATION:
+        m = params2matrix(gt[:2], t)
+    else:
+        m = params2matrix(gt, t)
+    return _native.transform_image(image, np.linalg.inv(np.asarray(m, dtype=np.float64)))
+
+
 def project_points(x, y, p, transform_type):
     """x'(x; p) for arrays of points (numpy; used for EPE and data synthesis)."""
     t = _as_type(transform_type)

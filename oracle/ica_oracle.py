@@ -467,3 +467,58 @@ def end_point_error(pa, pb, ttype, nx, ny):
     xb, yb = project(x, y, np.asarray(pb, dtype=np.float64), ttype)
     d = np.hypot(xa - xb, ya - yb)
     return float(d.mean()), float(d.max())
+
+
+# ----------------------------------------------------------- bicubic_interpolation.py (IPOL-style warp)
+def project_nparams(x, y, p, nparams):
+    """transformation.py:144-186: x'(x; p), the model selected by the NUMBER of parameters."""
+    p = np.asarray(p, dtype=np.float64)
+    if nparams == 2:
+        return x + p[0], y + p[1]
+    if nparams == 3:
+        return np.cos(p[2]) * x - np.sin(p[2]) * y + p[0], np.sin(p[2]) * x + np.cos(p[2]) * y + p[1]
+    if nparams == 4:
+        return (1 + p[2]) * x - p[3] * y + p[0], p[3] * x + (1 + p[2]) * y + p[1]
+    if nparams == 6:
+        return (1 + p[2]) * x + p[3] * y + p[0], p[4] * x + (1 + p[5]) * y + p[1]
+    if nparams == 8:
+        d = p[6] * x + p[7] * y + 1
+        return ((1 + p[0]) * x + p[1] * y + p[2]) / d, (p[3] * x + (1 + p[4]) * y + p[5]) / d
+    raise ValueError("Invalid transformation type")
+
+
+def _keys(v0, v1, v2, v3, x):
+    """bicubic_interpolation.py:39-41"""
+    return v1 + 0.5 * x * (v2 - v0 + x * (2.0 * v0 - 5.0 * v1 + 4.0 * v2 - v3 + x * (3.0 * (v1 - v2) + v3 - v0)))
+
+
+def bicubic_interpolation_image(image, params, nparams, nanifoutside, delta):
+    """bicubic_interpolation.py:121-152 (+ :66-118): the IPOL-style warp.  A pixel whose projection (x, y) has
+    x < delta, x > nx-1-delta, y < delta or y > ny-1-delta gets NaN (or 0); otherwise Catmull-Rom on the 4x4
+    neighbours int(x)-s .. int(x)+2s (s = sign of the coordinate, int() truncates toward zero), indices clamped to
+    the image (Neumann), fractions measured from the CLAMPED centre index; no clipping of the result."""
+    img = np.asarray(image, dtype=np.float64)
+    ny, nx, nz = img.shape
+    jj, ii = np.meshgrid(np.arange(nx, dtype=np.float64), np.arange(ny, dtype=np.float64))
+    x, y = project_nparams(jj, ii, params, nparams)
+    with np.errstate(invalid="ignore"):
+        out = (x < delta) | (x > nx - 1 - delta) | (y < delta) | (y > ny - 1 - delta)
+    xs = np.where(out | ~np.isfinite(x), 0.0, x)
+    ys = np.where(out | ~np.isfinite(y), 0.0, y)
+    sx = np.where(xs < 0, -1, 1)
+    sy = np.where(ys < 0, -1, 1)
+    ix = np.trunc(xs).astype(np.int64)
+    iy = np.trunc(ys).astype(np.int64)
+    cl = lambda v, n: np.clip(v, 0, n - 1)
+    cx = [cl(ix - sx, nx), cl(ix, nx), cl(ix + sx, nx), cl(ix + 2 * sx, nx)]
+    cy = [cl(iy - sy, ny), cl(iy, ny), cl(iy + sy, ny), cl(iy + 2 * sy, ny)]
+    fx = xs - cx[1]
+    fy = ys - cy[1]
+    res = np.empty_like(img)
+    for k in range(nz):
+        plane = img[:, :, k]
+        # pol[a] = column a over the four rows, interpolated in y first, then across columns in x
+        v = [_keys(plane[cy[0], cx[a]], plane[cy[1], cx[a]], plane[cy[2], cx[a]], plane[cy[3], cx[a]], fy) for a in range(4)]
+        res[:, :, k] = _keys(v[0], v[1], v[2], v[3], fx)
+    res[out] = np.nan if nanifoutside else 0.0
+    return res

@@ -502,3 +502,61 @@ def test_large_rotation_takes_global_path(nat, theta, rtype):
         po, eo, _, _ = orc.ica_robust(a, b, p0.copy(), t.value, 1e-3, rtype, 0.0, True, 5)
     assert _epe(p, po, t.value, 190, 150) <= EPE_TOL
     assert _epe(p, p_gt, t.value, 190, 150) <= 0.1
+
+
+# ------------------------------------------------------------------ helper API on materialised arrays
+def test_helper_api_matches_oracle(nat, rubber_whale):
+    """The building blocks callers of the reference import next to the drivers (io.rhop, io.robust_error_function,
+    io.steepest_descent_images, de.hessian[_robust], io.independent_vector[_robust], tr.transform_image): same
+    names and argument order, computed on the GPU in float64, compared with the oracle's restatement."""
+    from inverse_compositional_algorithm_b200 import derivatives as de, image_optimisation as io, transformation as tr
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    img = rubber_whale["rubber_whale"][40:120, 60:170].astype(np.float64)
+    rng = np.random.default_rng(5)
+    ny, nx, nz = img.shape
+    for t in (TransformType.AFFINITY, TransformType.HOMOGRAPHY):
+        n = t.nparams()
+        Ix, Iy = orc.gradient_with_frame(img, True, 4)            # NaN frame: the zero-fill rules matter
+        J = de.jacobian(t, nx, ny)
+        assert np.array_equal(J, orc.jacobian(t.value, nx, ny))
+        DIJ = io.steepest_descent_images(Ix, Iy, J, n)
+        want = orc.steepest_descent_images(Ix, Iy, J, n)
+        assert np.array_equal(np.isnan(DIJ), np.isnan(want)) and np.allclose(DIJ, want, rtol=1e-14, atol=0, equal_nan=True)
+        DI = rng.normal(0, 20, img.shape)
+        DI[rng.random(img.shape) < 0.05] = np.nan
+        for rt in range(5):
+            rho = io.robust_error_function(DI, 7.0, rt)
+            np.testing.assert_allclose(rho, orc.robust_error_function(DI, 7.0, rt), rtol=1e-13)
+            np.testing.assert_allclose(io.rhop(np.array([0.0, 3.0, 49.0, 1e4]), 7.0, rt),
+                                       orc.rhop(np.array([0.0, 3.0, 49.0, 1e4]), 7.0, rt), rtol=1e-14)
+        rho = io.robust_error_function(DI, 7.0, 3)
+        np.testing.assert_allclose(de.hessian(DIJ), orc.hessian(DIJ), rtol=1e-11)
+        np.testing.assert_allclose(de.hessian_robust(DIJ, rho, n), orc.hessian_robust(DIJ, rho), rtol=1e-11)
+        np.testing.assert_allclose(io.independent_vector(DIJ, DI, n), orc.independent_vector(DIJ, DI), rtol=1e-10)
+        np.testing.assert_allclose(io.independent_vector_robust(DIJ, DI, rho, n), orc.independent_vector_robust(DIJ, DI, rho),
+                                   rtol=1e-10)
+    cases = [(TransformType.TRANSLATION, [3.25, -1.5]), (TransformType.EUCLIDEAN, [2.0, 1.0, 0.05]),
+             (TransformType.SIMILARITY, [1.0, -2.0, 0.02, 0.03]), (TransformType.AFFINITY, [0.5, 0.25, 0.01, 0.02, -0.01, 0.03]),
+             (TransformType.HOMOGRAPHY, [0.01, 0.0, 1.0, 0.0, -0.01, 2.0, 1e-5, -2e-5]), (TransformType.AFFINITY, [0.0] * 6)]
+    for t, gt in cases:
+        got = tr.transform_image(img + 17.0, t, gt)       # min > 0: skimage's "keep cval" clip rule is active
+        want = orc.transform_image(img + 17.0, t.value, gt)
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
+    with pytest.raises(ValueError):
+        io.rhop(np.zeros(3), 1.0, 9)
+
+
+def test_ipol_warp_matches_reference_golden(nat):
+    """``bi.bicubic_interpolation_image`` on the GPU against the reference's own outputs (tests/golden/ipol_warp.npz)."""
+    import os
+    from inverse_compositional_algorithm_b200 import bicubic_interpolation as bi
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "ipol_warp.npz")))
+    for i in range(6):
+        p, fl = g[f"params_{i}"], g[f"flags_{i}"]
+        got = bi.bicubic_interpolation_image(g["image"], p, len(p), bool(fl[0]), int(fl[1]))
+        want = g[f"out_{i}"]
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-10, equal_nan=True)
+    with pytest.raises(ValueError):
+        bi.bicubic_interpolation_image(g["image"], np.zeros(5), 5, True, 1)
+    assert bi.neumann_bc(-3, 10) == 0 and bi.neumann_bc(12, 10) == 9 and bi.cubic_interpolation([1.0, 2.0, 3.0, 4.0], 0.5) == 2.5

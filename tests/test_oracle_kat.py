@@ -165,3 +165,16 @@ def test_reference_runs_match_oracle(idx, reference_runs):
         np.testing.assert_allclose(pp, row[3:3 + n], rtol=1e-7, atol=1e-11)
     np.testing.assert_allclose(p, g[name + "/p"], rtol=1e-7, atol=1e-11)
     assert int(np.isnan(Iw).sum()) == int(g[name + "/nan_count"])
+
+
+def test_ipol_warp_matches_reference_golden():
+    """``bicubic_interpolation_image`` (the IPOL-style warp, secondary API): the oracle's restatement against outputs
+    of the unmodified reference (numba, fastmath) stored by ``oracle/make_golden_ipol.py``."""
+    import os
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "ipol_warp.npz")))
+    for i in range(6):
+        p, fl = g[f"params_{i}"], g[f"flags_{i}"]
+        got = orc.bicubic_interpolation_image(g["image"], p, len(p), bool(fl[0]), int(fl[1]))
+        want = g[f"out_{i}"]
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-10, equal_nan=True)
