@@ -172,3 +172,36 @@ def register_batch(I1, I2, transform_type, nscales=1, nu=0.5, TOL=1e-3,
     if return_images:
         return pout, err, iters, DI, Iw
     return pout, err, iters
+
+
+class PyramidalInverseCompositional:
+    """Batched, layer-shaped front end with the call shape of the reference's Keras layer
+    (``tf_inverse_compositional_algorithm.py:467-583``): constructed with the algorithm's options, called on
+    ``[I1, I2]`` of shape ``[B, H, W, C]``, returns ``(p [B, 8] zero-padded, error [B], DI, Iw)``.  Unlike the
+    reference's layer, whose stopping rule looks at the whole batch (``tf_ica.py:225-232`` -- its authors call it with
+    B = 1 for that reason), every pair follows its own coarse-to-fine schedule and stops on its own ``|dp|``.
+    No TensorFlow involved: inputs are numpy arrays (uint8 / float32 / float64), the work is the CUDA path."""
+
+    def __init__(self, transform_type, nscales=3, nu=0.5, TOL=1e-3,
+                 robust_type=RobustErrorFunctionType.QUADRATIC, lambda_=0.0, nanifoutside=True, delta=10,
+                 verbose=False, return_images=True):
+        self.transform_type = transform_type
+        self.nscales, self.nu, self.TOL = int(nscales), float(nu), float(TOL)
+        self.robust_type, self.lambda_ = robust_type, float(lambda_)
+        self.nanifoutside, self.delta, self.verbose = nanifoutside, int(delta), bool(verbose)
+        self.return_images = bool(return_images)
+        self.iterations = None      # [B, nscales] of the last call
+
+    def __call__(self, inputs):
+        I1, I2 = inputs
+        res = register_batch(I1, I2, self.transform_type, nscales=self.nscales, nu=self.nu, TOL=self.TOL,
+                             robust_type=self.robust_type, lambda_=self.lambda_, nanifoutside=self.nanifoutside,
+                             delta=self.delta, gray_as_rgb=True, return_images=self.return_images)
+        self.iterations = res[2]
+        if self.verbose:
+            for b in range(len(res[0])):
+                print(f"pair {b}: |Dp|={res[1][b]:.6f}: p=({' '.join(f'{v:.6f}' for v in res[0][b])}), "
+                      f"iterations per scale (fine->coarse) {res[2][b].tolist()}")
+        if self.return_images:
+            return res[0], res[1], res[3].astype(np.float64), res[4].astype(np.float64)
+        return res[0], res[1]

@@ -560,3 +560,24 @@ def test_ipol_warp_matches_reference_golden(nat):
     with pytest.raises(ValueError):
         bi.bicubic_interpolation_image(g["image"], np.zeros(5), 5, True, 1)
     assert bi.neumann_bc(-3, 10) == 0 and bi.neumann_bc(12, 10) == 9 and bi.cubic_interpolation([1.0, 2.0, 3.0, 4.0], 0.5) == 2.5
+
+
+def test_layer_shaped_front_end(nat, rubber_whale):
+    """`PyramidalInverseCompositional(...)([I1, I2])`: the batched call shape of the reference's Keras layer, with
+    per-pair convergence; every pair must equal its own run of the drop-in driver."""
+    from inverse_compositional_algorithm_b200.inverse_compositional_algorithm import (
+        PyramidalInverseCompositional, pyramidal_inverse_compositional_algorithm)
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    I2 = rubber_whale["rubber_whale"][100:260, 200:440]
+    names = ["rubber_whale_tr", "rubber_whale_eu", "rubber_whale_zo"]
+    I1 = np.stack([rubber_whale[n][100:260, 200:440] for n in names])
+    layer = PyramidalInverseCompositional(TransformType.SIMILARITY, nscales=3, nu=0.5, TOL=1e-3, robust_type=4,
+                                          lambda_=0.0, nanifoutside=True, delta=5)
+    p, err, DI, Iw = layer([I1, np.stack([I2] * 3)])
+    assert p.shape == (3, 8) and err.shape == (3,) and DI.shape == I1.shape and Iw.dtype == np.float64
+    for i in range(3):
+        ps, es, DIs, Iws = pyramidal_inverse_compositional_algorithm(I1[i], I2, np.zeros(4), TransformType.SIMILARITY, 3, 0.5,
+                                                                     1e-3, 4, 0.0, True, 5, False)
+        assert np.array_equal(p[i, :4], ps) and err[i] == es
+        assert np.array_equal(np.isnan(Iw[i]), np.isnan(Iws)) and np.nanmax(np.abs(Iw[i] - Iws)) == 0.0
+    assert layer.iterations.shape == (3, 3)
