@@ -5,6 +5,7 @@
 #include <string.h>
 #include <math.h>
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <vector>
 #include <cuda.h>
@@ -716,26 +717,41 @@ int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* 
 }
 
 // Host->device copies of concurrent ica_plan_run_host calls (different plans, different threads) take turns on the
-// PCIe link: while one plan's kernels run, the next plan's inputs are copied, instead of all copies first.
+// PCIe link: while one plan's kernels run, the next plan's inputs are copied, instead of all copies sharing the link
+// and every plan starting late.  (Ordering the copies on the device with a chained event instead of this host-side
+// hand-over was measured slower.)
 static std::mutex g_h2d_mutex;
 
-static int upload_images(ica_plan* pl, const void* host, int dtype, float* dst, cudaStream_t stream) {
+// both images of the batch host -> device; u8 / f64 inputs go through two staging areas so that the two copies run
+// back to back and the link is released before the conversions to float32 are even scheduled
+static int upload_pair(ica_plan* pl, const void* h1, const void* h2, int dtype, cudaStream_t stream) {
   const long long n = (long long)pl->B * pl->in_stride;
   if (dtype == 0) {
-    ICA_CUDA_CHECK(cudaMemcpyAsync(dst, host, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    ICA_CUDA_CHECK(cudaMemcpyAsync(pl->in1_dev, h1, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    ICA_CUDA_CHECK(cudaMemcpyAsync(pl->in2_dev, h2, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    ICA_CUDA_CHECK(cudaEventRecord(pl->ev_h2d_done, stream));
     return ICA_OK;
   }
   const size_t esz = dtype == 1 ? 1 : 8;
-  if (pl->raw_bytes < (size_t)n * esz) {
-    cudaFree(pl->raw_dev); pl->raw_dev = nullptr; pl->raw_bytes = 0;
-    cudaError_t e = cudaMalloc(&pl->raw_dev, (size_t)n * esz);
+  const size_t area = ((size_t)n * esz + 255) / 256 * 256;
+  if (pl->raw_bytes < 2 * area) {
+    cudaFree(pl->raw_dev); pl->raw_dev = nullptr; pl->device_bytes -= pl->raw_bytes; pl->raw_bytes = 0;
+    cudaError_t e = cudaMalloc(&pl->raw_dev, 2 * area);
     if (e != cudaSuccess) { set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return ICA_ERR_ALLOC; }
-    pl->raw_bytes = (size_t)n * esz; pl->device_bytes += pl->raw_bytes;
+    pl->raw_bytes = 2 * area; pl->device_bytes += pl->raw_bytes;
   }
-  ICA_CUDA_CHECK(cudaMemcpyAsync(pl->raw_dev, host, (size_t)n * esz, cudaMemcpyHostToDevice, stream));
-  if (dtype == 1) ICA_LAUNCH_CHECK(launch_convert_u8((const unsigned char*)pl->raw_dev, dst, n, stream));
-  else ICA_LAUNCH_CHECK(launch_convert_f64((const double*)pl->raw_dev, dst, n, stream));
-  pl->launches += 1;
+  unsigned char* r1 = static_cast<unsigned char*>(pl->raw_dev);
+  unsigned char* r2 = r1 + area;
+  ICA_CUDA_CHECK(cudaMemcpyAsync(r1, h1, (size_t)n * esz, cudaMemcpyHostToDevice, stream));
+  ICA_CUDA_CHECK(cudaMemcpyAsync(r2, h2, (size_t)n * esz, cudaMemcpyHostToDevice, stream));
+  ICA_CUDA_CHECK(cudaEventRecord(pl->ev_h2d_done, stream));
+  if (dtype == 1) {
+    ICA_LAUNCH_CHECK(launch_convert_u8(r1, pl->in1_dev, n, stream));
+    ICA_LAUNCH_CHECK(launch_convert_u8(r2, pl->in2_dev, n, stream));
+  } else {
+    ICA_LAUNCH_CHECK(launch_convert_f64(reinterpret_cast<const double*>(r1), pl->in1_dev, n, stream));
+    ICA_LAUNCH_CHECK(launch_convert_f64(reinterpret_cast<const double*>(r2), pl->in2_dev, n, stream));
+  }
   return ICA_OK;
 }
 
@@ -755,18 +771,13 @@ int ica_plan_run_host(ica_plan* pl, const void* I1_host, const void* I2_host, in
   {
     std::lock_guard<std::mutex> lock(g_h2d_mutex);
     ICA_CUDA_CHECK(cudaEventRecord(pl->ev_host0, stream));
-    // the dtype staging buffer is reused for the second image only after the first conversion was enqueued
-    if (int rc = upload_images(pl, I1_host, dtype, pl->in1_dev, stream)) return rc;
-    if (int rc = upload_images(pl, I2_host, dtype, pl->in2_dev, stream)) return rc;
     ICA_CUDA_CHECK(cudaMemcpyAsync(pl->p_dev, p_inout_host, (size_t)pl->B * ICA_MAX_PARAMS * sizeof(double),
                                    cudaMemcpyHostToDevice, stream));
-    ICA_CUDA_CHECK(cudaEventRecord(pl->ev_h2d_done, stream));
+    if (int rc = upload_pair(pl, I1_host, I2_host, dtype, stream)) return rc;
     ICA_CUDA_CHECK(cudaEventSynchronize(pl->ev_h2d_done));   // the link is free for the next caller
   }
-  const long long conv_launches = pl->launches;
   if (int rc = ica_plan_run_device(pl, pl->in1_dev, pl->in2_dev, pl->p_dev, stream)) return rc;
-  pl->launches += (dtype == 0 ? 0 : 2);
-  (void)conv_launches;
+  pl->launches += (dtype == 0 ? 0 : 2);   // the two conversion kernels
   ICA_CUDA_CHECK(cudaMemcpyAsync(p_inout_host, pl->p_dev, (size_t)pl->B * ICA_MAX_PARAMS * sizeof(double),
                                  cudaMemcpyDeviceToHost, stream));
   if (err_out) ICA_CUDA_CHECK(cudaMemcpyAsync(err_out, pl->err_dev, pl->B * sizeof(double), cudaMemcpyDeviceToHost, stream));
