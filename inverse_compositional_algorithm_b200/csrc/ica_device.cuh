@@ -114,27 +114,4 @@ __device__ __forceinline__ float sample_global(const float* __restrict__ img, in
   return acc;
 }
 
-// Transposing warp reduction: every lane holds NP partial values v[0..NP-1]; on return lane l
-// holds in v[0] the sum over all 32 lanes of value index (l >> log2(32/NP)).  NP in {8,16,32}.
-// Costs NP-1 (+ log2(32/NP)) shuffles instead of 5*NP.
-template <int NP>
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[NP], int lane) {
-  constexpr int kFirstOff = 16;
-  int off = kFirstOff;
-#pragma unroll
-  for (int h = NP / 2; h >= 1; h >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < h; ++i) {
-      float keep = up ? v[i + h] : v[i];
-      float send = up ? v[i] : v[i + h];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-    off >>= 1;
-  }
-  float r = v[0];
-  for (; off >= 1; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
-  return r;
-}
-
 }  // namespace ica

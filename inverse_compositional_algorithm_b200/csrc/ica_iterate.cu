@@ -8,26 +8,27 @@
 //   io.independent_vector[_robust]    (b)
 //   de.hessian_robust / de.hessian    (H; gradients, Jacobian and steepest-descent images are
 //                                      recomputed per pixel, never stored: ica.py:81-100)
-// and, in the block that delivers a pair's last chunk (ticket pattern, nobody spins):
+// and, in ica_solve_kernel (one block per pair, launched after it):
 //   de.inverse_hessian, io.parametric_solve, tr.update_transform, the lambda schedule, the
 //   stopping rule and zm.zoom_in_parameters at a scale change.
 //
 // Execution model
-//   * ica_schedule_kernel (1 block) turns the per-pair scales into a work list: pair b at a
-//     level with T tiles contributes min(T, max_chunks) chunks of consecutive 64x14 tiles.
-//   * ica_iterate_kernel is PERSISTENT (2 CTAs per SM) and WARP-SPECIALISED: warp 7 of each CTA
-//     is a producer that walks the CTA's chunks, and per tile stages the I1 patch (+halo) and
-//     the window of I2 the warp can reach into shared memory with 1-D TMA bulk copies
-//     (cp.async.bulk -> UBLKCP) completing on a "full" mbarrier; warps 0-6 consume the stage and
-//     release it through an "empty" mbarrier.  Two stages, so copies of tile t+1 (even of the
-//     next chunk) overlap the arithmetic of tile t, and there is no block-wide barrier in the
-//     tile loop.  Pixels of the window that fall outside the image are filled by ordinary
-//     stores (NaN for I2 = skimage's cval, so the NaN footprint falls out of the arithmetic).
-//   * a consumer warp owns one image row at a time; x-moments are accumulated per lane in fp32,
-//     transposed through shared memory so that moment k lands on lane k, which folds in y^b in
-//     fp64.  Chunk partials go to fixed slots; the last chunk of a pair sums them in a fixed
-//     order (deterministic) and runs the n x n solve / compose epilogue.
-// Bound: HBM (read I1 once + I2 once per pixel-iteration = 2*C*4 bytes); no tensor cores.
+//   * The work list of a launch (built by ica_schedule_kernel for the first iteration, by the last block of
+//     ica_solve_kernel afterwards): pair b at a level with T tiles of 64 x 11 pixels contributes min(T, max_chunks)
+//     chunks of consecutive tiles.  The chunk decomposition of a pair never depends on what else is in the batch.
+//   * ica_iterate_kernel is PERSISTENT (2 CTAs per SM, 12 warps each at 80 registers) and WARP-SPECIALISED.  CTAs claim
+//     chunks through an atomic counter.  Warp 11 is the producer: per tile it projects the tile corners and stages the
+//     I1 patch (+halo) and the window of I2 the tile can reach with two tiled TMA copies (cp.async.bulk.tensor.2d ->
+//     UTMALDG, tensor maps per pair / level / image) that complete on a "full" mbarrier; the copy engine fills what
+//     lies outside the image (NaN for I2 = skimage's cval, so the NaN footprint falls out of the arithmetic; 0 for
+//     I1).  Warps 0-10 consume the stage and release it through an "empty" mbarrier.  Two stages: the copies of tile
+//     t+1 (even of the next chunk) overlap the arithmetic of tile t; no block-wide barrier in the tile loop.
+//   * A consumer warp owns one image row of the tile (two pixels per lane, packed fp32).  Lanes accumulate the
+//     x-moments of that row in fp32 and keep them across the consecutive tiles of the row; once per row segment they
+//     are transposed through shared memory so that moment k lands on lane k, which folds in y^b in fp64.  Chunk
+//     partials go to fixed slots; ica_solve_kernel sums them in a fixed order (deterministic, batch-invariant).
+// Bound named by the north star: HBM (read I1 once + I2 once per pixel-iteration = 2*C*4 bytes); measured: DRAM
+// traffic = 1.01x that, the kernel is limited by instruction issue and shared-memory wavefronts.  No tensor cores.
 #include "ica_device.cuh"
 #include "ica_transform.cuh"
 #include "ica_iterate.cuh"
