@@ -581,3 +581,30 @@ def test_layer_shaped_front_end(nat, rubber_whale):
         assert np.array_equal(p[i, :4], ps) and err[i] == es
         assert np.array_equal(np.isnan(Iw[i]), np.isnan(Iws)) and np.nanmax(np.abs(Iw[i] - Iws)) == 0.0
     assert layer.iterations.shape == (3, 3)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("ICA_SLOW_TESTS"), reason="minutes of CPU oracle time (set ICA_SLOW_TESTS=1)")
+@pytest.mark.parametrize("config", ["c3", "c4"])
+def test_full_size_configs_match_oracle(nat, config):
+    """BASELINE configs 3 and 4 at full size against the oracle on a couple of pairs: 640x480 gray, similarity /
+    affinity, quadratic, 5 scales; 1024^2 RGB homography, Geman-McClure, 20 % occlusion, 5 scales."""
+    from inverse_compositional_algorithm_b200 import synthetic
+    from inverse_compositional_algorithm_b200.inverse_compositional_algorithm import register_batch
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    if config == "c3":
+        h, w, c, types, rtype, occ = 480, 640, 1, [TransformType.SIMILARITY, TransformType.AFFINITY], 0, 0.0
+    else:
+        h, w, c, types, rtype, occ = 1024, 1024, 3, [TransformType.HOMOGRAPHY, TransformType.HOMOGRAPHY], 2, 0.2
+    pairs = [synthetic.make_pair(300 + i, h, w, c, t, occlusion=occ) for i, t in enumerate(types)]
+    I1 = np.round(np.stack([a for a, _, _ in pairs])); I2 = np.round(np.stack([b for _, b, _ in pairs]))
+    p, err, iters = register_batch(I1, I2, types, nscales=5, robust_type=rtype, delta=10)
+    for i, t in enumerate(types):
+        a, b = (np.repeat(x, 3, 2) if c == 1 else x for x in (I1[i], I2[i]))
+        trace = []
+        po, eo, _, _ = orc.ica_pyramidal(a.astype(np.float64), b.astype(np.float64), np.zeros(t.nparams()), t.value, 5, 0.5,
+                                         1e-3, rtype, 0.0, True, 10, trace=trace)
+        epe = _epe(p[i, :t.nparams()], po, t.value, w, h)
+        print(config, t.name, "EPE vs oracle", epe, "iterations", int(iters[i].sum()), len(trace),
+              "EPE vs ground truth", _epe(p[i, :t.nparams()], pairs[i][2], t.value, w, h))
+        assert epe <= EPE_TOL
+        assert int(iters[i].sum()) == len(trace)
