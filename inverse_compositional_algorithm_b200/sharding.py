@@ -71,7 +71,7 @@ def row_band(tiles_y: int, rank: int, nranks: int):
 
 def register_row_sharded(I1, I2, transform_type, *, nscales=5, nu=0.5, robust_type=0, robust_loop=None,
                          lambda_=0.0, tol=1e-3, max_iter=30, delta=5, nanifoutside=True,
-                         gray_as_rgb=True, p0=None, group=None, emulate_ranks=None, stats=None):
+                         gray_as_rgb=True, p0=None, group=None, emulate_ranks=None, stats=None, poll_every=4):
     """Registers one image pair with the pixels of every iteration split by rows over the ranks of
     ``group`` (``torch.distributed``, NCCL).  ``I1``/``I2``: float32 CUDA tensors ``[H, W, C]`` (the full
     images, on every rank).  Returns ``(p [8], err, iters [nscales])``, identical on all ranks.
@@ -143,8 +143,13 @@ def register_row_sharded(I1, I2, transform_type, *, nscales=5, nu=0.5, robust_ty
         if want_time:
             e1.record()
             ar_events.append((e0, e1))
+        # the number of unfinished pairs is read back (a stream synchronisation) only every few iterations: an
+        # iteration past convergence has an empty work list and changes nothing
+        poll = (it + 1) % poll_every == 0 and it + 1 >= nscales     # a pair needs at least one iteration per scale
         for pl in plans:
-            n_active = pl.shard_solve(total.data_ptr(), stream)
+            n = pl.shard_solve(total.data_ptr(), stream, poll=poll)
+            if n >= 0:
+                n_active = n
         it += 1
     out = torch.zeros((1, 8), dtype=torch.float64, device=dev)
     for pl in plans:
@@ -152,7 +157,8 @@ def register_row_sharded(I1, I2, transform_type, *, nscales=5, nu=0.5, robust_ty
     torch.cuda.current_stream().synchronize()
     p, err, iters = plans[0].results()
     if stats is not None:
-        stats["iterations"] = it
+        stats["iterations"] = int(iters.sum())
+        stats["launched_iterations"] = it
         stats["world"] = world
         if want_time:
             stats["allreduce_ms"] = [a.elapsed_time(b) for a, b in ar_events]

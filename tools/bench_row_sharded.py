@@ -81,7 +81,7 @@ def main():
             "workload": f"single {n}x{n} grayscale pair, homography, {args.robust}, {args.nscales} scales, "
                         f"row-sharded over {args.emulate or world} ranks" + (" (emulated on one GPU)" if args.emulate else ""),
             "n_gpus": world, "ms_per_registration": float(np.median(times)), "reps": args.reps,
-            "iterations": int(stats["iterations"]), "iters_per_scale(coarse->fine)": [int(v) for v in iters_all[::-1]],
+            "iterations": int(stats["iterations"]), "launched_iterations": int(stats["launched_iterations"]), "iters_per_scale(coarse->fine)": [int(v) for v in iters_all[::-1]],
             "allreduce_ms_median": float(np.median(ar)), "allreduce_ms_mean": float(ar.mean()),
             "allreduce_ms_p95": float(np.percentile(ar, 95)), "allreduce_bytes": 105 * 8,
             "epe_vs_ground_truth_px": epe}))
