@@ -29,7 +29,9 @@ def _get_plan(**key):
     if plan is None:
         if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
             _PLAN_CACHE.pop(next(iter(_PLAN_CACHE))).close()
-        plan = _native.Plan(**key)
+        args = dict(key)
+        args.pop("device", None)      # part of the cache key only: plans live on the device that is current
+        plan = _native.Plan(**args)
         _PLAN_CACHE[k] = plan
     return plan
 
@@ -172,6 +174,45 @@ def register_batch(I1, I2, transform_type, nscales=1, nu=0.5, TOL=1e-3,
     if return_images:
         return pout, err, iters, DI, Iw
     return pout, err, iters
+
+
+def register_batch_device(I1, I2, transform_type, nscales=1, nu=0.5, TOL=1e-3,
+                          robust_type=RobustErrorFunctionType.QUADRATIC, lambda_=0.0, nanifoutside=True,
+                          delta=10, p0=None, gray_as_rgb=True):
+    """``register_batch`` for images that already live on the GPU: ``I1``/``I2`` are float32 CUDA tensors
+    ``[B, H, W, C]`` (torch is only the container: the library reads the device pointers in place, on torch's
+    current stream, with no host round trip until the small result arrays are fetched).
+    Returns ``(p [B, 8] float64 CUDA tensor, error [B], iters [B, nscales])``."""
+    import torch
+    if not (isinstance(I1, torch.Tensor) and I1.is_cuda and I1.dtype == torch.float32 and I1.dim() == 4):
+        raise ValueError("I1 and I2 must be float32 CUDA tensors [B, H, W, C]")
+    if I1.shape[3] not in (1, 3):
+        raise ValueError("I1 and I2 must be [B, H, W, C] with C in (1, 3)")
+    _check_common(I1, I2, TOL)
+    I1, I2 = I1.contiguous(), I2.contiguous()
+    B, ny, nx, nz = (int(v) for v in I1.shape)
+    types = ([_as_type(transform_type)] * B if not isinstance(transform_type, (list, tuple, np.ndarray))
+             else [_as_type(t) for t in transform_type])
+    if len(types) != B:
+        raise ValueError("one transform type per pair is required")
+    r = _as_robust(robust_type)
+    with torch.cuda.device(I1.device):
+        plan = _get_plan(batch=B, height=ny, width=nx, channels=nz, nscales=int(nscales), nu=float(nu),
+                         transform_type=types[0].value, robust_type=r.value,
+                         robust_loop=r != RobustErrorFunctionType.QUADRATIC, lambda_=float(lambda_), tol=float(TOL),
+                         max_iter=cts.MAX_ITER, delta=int(delta), nanifoutside=(nanifoutside is True),
+                         gray_as_rgb=bool(gray_as_rgb) and nz == 1, record_trajectory=False, write_di_iw=False,
+                         device=int(I1.device.index or 0))
+        plan.set_transform_types([t.value for t in types])
+        p = torch.zeros((B, 8), dtype=torch.float64, device=I1.device)
+        if p0 is not None:
+            p0 = np.asarray(p0, dtype=np.float64).reshape(B, -1)
+            p[:, :p0.shape[1]] = torch.from_numpy(p0).to(I1.device)
+        stream = torch.cuda.current_stream(I1.device)
+        plan.run_device(I1.data_ptr(), I2.data_ptr(), p.data_ptr(), stream.cuda_stream)
+        stream.synchronize()
+        _, err, iters = plan.results()
+    return p, err, iters
 
 
 class PyramidalInverseCompositional:

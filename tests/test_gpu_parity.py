@@ -608,3 +608,21 @@ def test_full_size_configs_match_oracle(nat, config):
               "EPE vs ground truth", _epe(p[i, :t.nparams()], pairs[i][2], t.value, w, h))
         assert epe <= EPE_TOL
         assert int(iters[i].sum()) == len(trace)
+
+
+def test_device_resident_entry_matches_host_entry(nat):
+    """`register_batch_device` (torch CUDA tensors, read in place) gives bit for bit what `register_batch` gives from
+    host arrays."""
+    import torch
+    from inverse_compositional_algorithm_b200 import synthetic
+    from inverse_compositional_algorithm_b200.inverse_compositional_algorithm import register_batch, register_batch_device
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    t = TransformType.HOMOGRAPHY
+    pairs = [synthetic.make_pair(60 + i, 128, 160, 3, t, max_shift=3.0, margin=32) for i in range(3)]
+    I1 = np.stack([a for a, _, _ in pairs]); I2 = np.stack([b for _, b, _ in pairs])
+    ph, eh, ih = register_batch(I1, I2, t, nscales=3, robust_type=3, delta=5)
+    pd, ed, idv = register_batch_device(torch.from_numpy(I1).cuda(), torch.from_numpy(I2).cuda(), t, nscales=3,
+                                        robust_type=3, delta=5)
+    assert np.array_equal(pd.cpu().numpy(), ph) and np.array_equal(ed, eh) and np.array_equal(idv, ih)
+    with pytest.raises(ValueError):
+        register_batch_device(torch.zeros((2, 8, 8, 3)), torch.zeros((2, 8, 8, 3)), t)
