@@ -37,7 +37,7 @@ namespace ica {
 
 namespace {
 
-constexpr int kBlocksPerSM = 2;      // 2 CTAs x 12 warps per SM at 80 registers per thread
+constexpr int kBlocksPerSM = 2;      // 2 CTAs x 12 warps per SM at 80 registers per thread (16 warps at 64 registers measured 9 % slower)
 constexpr int kConsumerWarps = 11;   // + 1 producer warp = 12 warps: warps are allocated in groups of 4
 constexpr int kRowsPerWarp = 1;      // rows of a tile per consumer warp
 constexpr int kConsumerThreads = kConsumerWarps * 32;
@@ -46,8 +46,7 @@ constexpr int TW = 64;            // tile width  (2 pixels per lane: x0+lane, x0
 constexpr int TH = kRowsPerWarp * kConsumerWarps;   // tile height (row y0 + warp + rr * kConsumerWarps for warp, rr)
 constexpr int HALO = 4;           // the I1 patch starts at x0-4: the inner coordinate of a TMA box must be a multiple of 16 bytes
 constexpr int S1ROWS = TH + 2;
-constexpr int BH_MAX = 22;        // rows of the staged I2 window; taller windows (strong rotation / zoom) take the global-memory path
-constexpr int SCR_PITCH = 36;     // floats per row of the per-warp transposition scratch
+constexpr int BH_MAX = 30;        // rows of the staged I2 window; taller windows (strong rotation / zoom) take the global-memory path
 
 template <int DH> struct RowVals { static constexpr int K = 3 * (DH + 1) + 2 * (DH / 2 + 1); };
 
@@ -117,6 +116,27 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 #define ICA_STAMP(slot) do { if (P.dbg_time && it == 0 && tid == 0) P.dbg_time[blockIdx.x * 16 + (slot)] = gtime(); } while (0)
 // barrier among the consumer threads only (the producer warp never joins it)
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
+
+// Transposing warp reduction: every lane holds NP partial values v[0..NP-1]; on return lane l holds in v[0] the sum
+// over all 32 lanes of value index (l >> log2(32 / NP)), NP in {8, 16, 32}.  Fixed order -> deterministic.
+template <int NP>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[NP], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int h = NP / 2; h >= 1; h >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float keep = up ? v[i + h] : v[i];
+      const float send = up ? v[i] : v[i + h];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+  float r = v[0];
+  for (; off >= 1; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+  return r;
+}
 
 // Jacobian entry k as a monomial, in registers (same table as ica_transform.cuh: jacobian_monomials)
 __device__ __forceinline__ void mono_of(int ttype, int k, Mono& jx, Mono& jy) {
@@ -256,12 +276,10 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   constexpr int S1W = Stage<C>::S1W;
   constexpr int S2W = Stage<C>::S2W;
   constexpr int NENT = K * kYPow;
-  constexpr int SCR = K * SCR_PITCH;                 // floats of transposition scratch per consumer warp
 
   extern __shared__ __align__(128) float smem[];
   float* const stage0 = smem;
   float* const stage1 = smem + Stage<C>::kFloats;
-  float* const scratch = smem + 2 * Stage<C>::kFloats;   // kConsumerWarps * SCR floats
   __shared__ __align__(8) unsigned long long s_full[2], s_empty[2];
   __shared__ TileCtl tctl[2];
   __shared__ double s_pm64[9];
@@ -291,9 +309,13 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   const bool robust = P.robust_loop != 0;
   const float chm = P.ch_mult;
   const int rtype = P.robust_type;
-  float* const sc = scratch + warp * SCR;
-  double* const accs = reinterpret_cast<double*>(scratch + kConsumerWarps * SCR);   // [kConsumerWarps][K][kYPow]
-  double* const myacc = accs + (warp * K + (lane < K ? lane : 0)) * kYPow;
+  double* const accs = reinterpret_cast<double*>(smem + 2 * Stage<C>::kFloats);   // [kConsumerWarps][K][kYPow]
+  // the transposing reduction leaves moment k on the lanes k << kTrShift .. ; the first of them owns the fp64 accumulators
+  constexpr int kTrN = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
+  constexpr int kTrShift = kTrN == 8 ? 2 : (kTrN == 16 ? 1 : 0);
+  const int midx = lane >> kTrShift;
+  const bool mown = (lane & ((1 << kTrShift) - 1)) == 0 && midx < K;
+  double* const myacc = accs + (warp * K + (mown ? midx : 0)) * kYPow;
   unsigned k = 0;
   int nitems = 0;
   const bool dbg = P.dbg_time != nullptr && tid == 0;       // profiling hook: cycles warp 0 spends waiting / in chunk epilogues
@@ -308,29 +330,25 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
 #pragma unroll
   for (int i = 0; i < K; ++i) v[i] = 0.0f;
   int vrow = -1;
-  // transpose through shared memory: moment k of the row lands on lane k (fixed summation order), which folds in
-  // y^b in fp64; the per-lane fp64 accumulators live in shared memory
+  // once per row segment: a transposing shuffle reduction leaves the row's moment k on the lane that owns it (fixed
+  // summation order), which folds in y^b in fp64; the fp64 accumulators live in shared memory
   auto flush_row = [&]() {
+    float t32[kTrN];
 #pragma unroll
-    for (int i = 0; i < K; ++i) { sc[i * SCR_PITCH + lane] = v[i]; v[i] = 0.0f; }
-    __syncwarp();
-    if (lane < K) {
-      const float4* r4 = reinterpret_cast<const float4*>(sc + lane * SCR_PITCH);
-      // four independent partial sums (fixed order): a single chain of 32 dependent adds was pure latency
-      float4 t4 = r4[0];
+    for (int i = 0; i < kTrN; ++i) t32[i] = i < K ? v[i] : 0.0f;
 #pragma unroll
-      for (int j = 1; j < 8; ++j) { const float4 q4 = r4[j]; t4.x += q4.x; t4.y += q4.y; t4.z += q4.z; t4.w += q4.w; }
-      const float tot = (t4.x + t4.y) + (t4.z + t4.w);
+    for (int i = 0; i < K; ++i) v[i] = 0.0f;
+    const float tot = warp_transpose_reduce<kTrN>(t32, lane);
+    if (mown) {
       const double yd = (double)vrow, t = (double)tot;
       double yp = 1.0;
 #pragma unroll
       for (int b = 0; b < kYPow; ++b) { myacc[b] = fma(t, yp, myacc[b]); yp *= yd; }
     }
-    __syncwarp();
     vrow = -1;
   };
   for (int it = 0;; ++it) {
-    if (lane < K) {
+    if (mown) {
 #pragma unroll
       for (int b = 0; b < kYPow; ++b) myacc[b] = 0.0;
     }
@@ -969,7 +987,7 @@ __global__ void ica_gradient_kernel(const float* __restrict__ img, int nx, int n
 
 template <int C, int DH>
 cudaError_t launch_iterate_t(const IterParams& P, int grid, cudaStream_t stream) {
-  constexpr size_t smem = (2 * (size_t)Stage<C>::kFloats + (size_t)kConsumerWarps * RowVals<DH>::K * SCR_PITCH) * sizeof(float) +
+  constexpr size_t smem = 2 * (size_t)Stage<C>::kFloats * sizeof(float) +
                           (size_t)kConsumerWarps * RowVals<DH>::K * kYPow * sizeof(double);
   static bool configured = false;
   if (!configured) {
