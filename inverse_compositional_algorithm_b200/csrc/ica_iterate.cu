@@ -46,6 +46,7 @@ constexpr int TW = 64;            // tile width  (2 pixels per lane: x0+lane, x0
 constexpr int TH = kRowsPerWarp * kConsumerWarps;   // tile height (row y0 + warp + rr * kConsumerWarps for warp, rr)
 constexpr int HALO = 4;           // the I1 patch starts at x0-4: the inner coordinate of a TMA box must be a multiple of 16 bytes
 constexpr int S1ROWS = TH + 2;
+constexpr int kStages = 2;         // staged tiles in flight per CTA (3 stages with a 22-row window measured the same)
 constexpr int BH_MAX = 30;        // rows of the staged I2 window; taller windows (strong rotation / zoom) take the global-memory path
 
 template <int DH> struct RowVals { static constexpr int K = 3 * (DH + 1) + 2 * (DH / 2 + 1); };
@@ -158,7 +159,7 @@ __device__ __noinline__ float sample_global_slow(const float* __restrict__ img, 
 
 // ============================================================ producer warp
 template <int C>
-__device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0, float* stage1,
+__device__ __forceinline__ void producer_loop(const IterParams& P, float* stages, int stage_floats,
                                               unsigned long long* full, unsigned long long* empty, TileCtl* tctl,
                                               double* pm64, int total_chunks, int lane) {
   constexpr int S1W = Stage<C>::S1W, S2W = Stage<C>::S2W;
@@ -199,13 +200,13 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
     if (P.dbg_time && k == 0 && lane == 0) P.dbg_time[blockIdx.x * 16 + 9] = gtime();
     if (pdbg) pd_fetch += clock64() - pf0;
     for (int tile = t_begin; tile < t_end; ++tile, ++k) {
-      const int sidx = k & 1;
-      const unsigned use = k >> 1;
+      const int sidx = k % kStages;
+      const unsigned use = k / kStages;
       const long long pe0 = pdbg ? clock64() : 0;
       if (use >= 1) mbar_wait_backoff(&empty[sidx], (use - 1) & 1);   // consumers released the previous use
       const long long pt1 = pdbg ? clock64() : 0;
       if (pdbg) pd_empty += pt1 - pe0;
-      float* s2 = sidx ? stage1 : stage0;
+      float* s2 = stages + sidx * stage_floats;
       float* s1 = s2 + BH_MAX * S2W;
       unsigned long long* bar = &full[sidx];
       TileCtl& tc = tctl[sidx];
@@ -229,7 +230,7 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
       const int bh = mxy + 3 - by0 + 1;
       const bool fits = okall && bw <= Stage<C>::BWPX && bh <= BH_MAX && bw > 0 && bh > 0;
       const long long pt2 = pdbg ? clock64() : 0;
-      if (tile < t_begin + 2) {   // first use of this stage's control block by the chunk: per-chunk constants
+      if (tile < t_begin + kStages) {   // first use of this stage's control block by the chunk: per-chunk constants
         if (lane < 9) tc.m64[lane] = pm64[lane];
         if (lane == 0) {
           tc.coef = coef; tc.lo = lo; tc.hi = hi; tc.lambda2 = lambda2;
@@ -260,8 +261,8 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stage0
   }
   // no more work: hand the consumers a stop marker through the next stage
   {
-    const int sidx = k & 1;
-    const unsigned use = k >> 1;
+    const int sidx = k % kStages;
+    const unsigned use = k / kStages;
     if (use >= 1) mbar_wait(&empty[sidx], (use - 1) & 1);
     if (lane == 0) { tctl[sidx].stop = 1; mbar_arrive(&full[sidx]); }
   }
@@ -278,10 +279,9 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   constexpr int NENT = K * kYPow;
 
   extern __shared__ __align__(128) float smem[];
-  float* const stage0 = smem;
-  float* const stage1 = smem + Stage<C>::kFloats;
-  __shared__ __align__(8) unsigned long long s_full[2], s_empty[2];
-  __shared__ TileCtl tctl[2];
+  float* const stages = smem;                      // kStages x Stage<C>::kFloats
+  __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages];
+  __shared__ TileCtl tctl[kStages];
   __shared__ double s_pm64[9];
 
   const int tid = threadIdx.x;
@@ -292,14 +292,13 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   if (tid == 0) atomicMin(reinterpret_cast<long long*>(&P.tstamp[0]), gtime());
 
   if (tid == 0) {
-    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
-    mbar_init(&s_empty[0], kConsumerWarps); mbar_init(&s_empty[1], kConsumerWarps);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], kConsumerWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   if (warp == kConsumerWarps) {
-    producer_loop<C>(P, stage0, stage1, s_full, s_empty, tctl, s_pm64, total_chunks, lane);
+    producer_loop<C>(P, stages, Stage<C>::kFloats, s_full, s_empty, tctl, s_pm64, total_chunks, lane);
     return;
   }
 
@@ -309,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   const bool robust = P.robust_loop != 0;
   const float chm = P.ch_mult;
   const int rtype = P.robust_type;
-  double* const accs = reinterpret_cast<double*>(smem + 2 * Stage<C>::kFloats);   // [kConsumerWarps][K][kYPow]
+  double* const accs = reinterpret_cast<double*>(smem + kStages * Stage<C>::kFloats);   // [kConsumerWarps][K][kYPow]
   // the transposing reduction leaves moment k on the lanes k << kTrShift .. ; the first of them owns the fp64 accumulators
   constexpr int kTrN = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
   constexpr int kTrShift = kTrN == 8 ? 2 : (kTrN == 16 ? 1 : 0);
@@ -357,16 +356,16 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
     bool last;
     bool stop = false;
     do {
-      const int sidx = k & 1;
+      const int sidx = k % kStages;
       const long long w0 = dbg ? clock64() : 0;
-      mbar_wait(&s_full[sidx], (k >> 1) & 1);
+      mbar_wait(&s_full[sidx], (k / kStages) & 1);
       if (dbg) dbg_wait += clock64() - w0;
       if (tctl[sidx].stop) { stop = true; break; }   // uniform: the producer ran out of work
       if (k == 0) ICA_STAMP(1);
       // Tile constants stay in shared memory and are re-read (volatile) where they are used: the
       // register file is the scarce resource of this kernel, it must hold the tap loads in flight.
       const volatile TileCtl* tcv = &tctl[sidx];
-      const float* s2 = sidx ? stage1 : stage0;
+      const float* s2 = stages + sidx * Stage<C>::kFloats;
       const float* s1 = s2 + BH_MAX * S2W;
 #pragma unroll 1
       for (int rr = 0; rr < TH / kConsumerWarps; ++rr) {
@@ -987,7 +986,7 @@ __global__ void ica_gradient_kernel(const float* __restrict__ img, int nx, int n
 
 template <int C, int DH>
 cudaError_t launch_iterate_t(const IterParams& P, int grid, cudaStream_t stream) {
-  constexpr size_t smem = 2 * (size_t)Stage<C>::kFloats * sizeof(float) +
+  constexpr size_t smem = kStages * (size_t)Stage<C>::kFloats * sizeof(float) +
                           (size_t)kConsumerWarps * RowVals<DH>::K * kYPow * sizeof(double);
   static bool configured = false;
   if (!configured) {
