@@ -602,9 +602,12 @@ __device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal, bo
     }
     __syncthreads();
     const int excl = s_scal[0] + s_warp[warp] + incl - c;
-    if (b < B) {
-      P.chunk_start[b] = excl;
-      for (int i = 0; i < c; ++i) P.item_pair[excl + i] = b;
+    if (b < B) P.chunk_start[b] = excl;
+    // the items of a pair are written by the whole warp (up to 256-1024 per pair: one thread would take microseconds)
+#pragma unroll 1
+    for (int src = 0; src < 32; ++src) {
+      const int cb = __shfl_sync(0xffffffffu, c, src), eb = __shfl_sync(0xffffffffu, excl, src);
+      for (int i = lane; i < cb; i += 32) P.item_pair[eb + i] = base + (warp << 5) + src;
     }
     if (lane == 0 && actmask) atomicAdd(&s_scal[1], __popc(actmask));
     __syncthreads();
