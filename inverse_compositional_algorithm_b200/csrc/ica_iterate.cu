@@ -46,7 +46,6 @@ constexpr int TW = 64;            // tile width  (2 pixels per lane: x0+lane, x0
 constexpr int TH = kRowsPerWarp * kConsumerWarps;   // tile height (row y0 + warp + rr * kConsumerWarps for warp, rr)
 constexpr int HALO = 4;           // the I1 patch starts at x0-4: the inner coordinate of a TMA box must be a multiple of 16 bytes
 constexpr int S1ROWS = TH + 2;
-constexpr int kStages = 2;         // staged tiles in flight per CTA (3 stages with a 22-row window measured the same)
 constexpr int BH_MAX = 30;        // rows of the staged I2 window; taller windows (strong rotation / zoom) take the global-memory path
 
 template <int DH> struct RowVals { static constexpr int K = 3 * (DH + 1) + 2 * (DH / 2 + 1); };
@@ -59,6 +58,9 @@ template <int C> struct Stage {
   static constexpr int BWPX = S2W / C;                     // window width in pixels (85 RGB, 96 gray)
   static constexpr int S1W = (TW + 2 * HALO) * C;          // 216 (RGB) / 72 (gray) floats per patch row
   static constexpr int kFloats = (BH_MAX * S2W + S1ROWS * S1W + 31) / 32 * 32;   // I2 window, then I1 patch; 128-byte multiple
+  // staged tiles in flight per CTA: RGB tiles are compute-heavy (a third stage measured no gain); gray tiles are consumed
+  // in ~2 us, where two stages leave the consumers waiting for the producer 11-17 % of the time
+  static constexpr int kStages = C == 3 ? 2 : 4;
 };
 
 // Everything a consumer needs to know about a staged tile (written by the producer).
@@ -162,7 +164,7 @@ template <int C>
 __device__ __forceinline__ void producer_loop(const IterParams& P, float* stages, int stage_floats,
                                               unsigned long long* full, unsigned long long* empty, TileCtl* tctl,
                                               double* pm64, int total_chunks, int lane) {
-  constexpr int S1W = Stage<C>::S1W, S2W = Stage<C>::S2W;
+  constexpr int S1W = Stage<C>::S1W, S2W = Stage<C>::S2W, kStages = Stage<C>::kStages;
   unsigned k = 0;   // tiles staged so far by this CTA
   const bool pdbg = P.dbg_time != nullptr && lane == 0;   // profiling hook: cycles spent fetching work / waiting for a free stage
   long long pd_fetch = 0, pd_empty = 0, pd_proj = 0, pd_ctl = 0, pd_issue = 0;
@@ -277,6 +279,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   constexpr int S1W = Stage<C>::S1W;
   constexpr int S2W = Stage<C>::S2W;
   constexpr int NENT = K * kYPow;
+  constexpr int kStages = Stage<C>::kStages;
 
   extern __shared__ __align__(128) float smem[];
   float* const stages = smem;                      // kStages x Stage<C>::kFloats
@@ -989,7 +992,7 @@ __global__ void ica_gradient_kernel(const float* __restrict__ img, int nx, int n
 
 template <int C, int DH>
 cudaError_t launch_iterate_t(const IterParams& P, int grid, cudaStream_t stream) {
-  constexpr size_t smem = kStages * (size_t)Stage<C>::kFloats * sizeof(float) +
+  constexpr size_t smem = Stage<C>::kStages * (size_t)Stage<C>::kFloats * sizeof(float) +
                           (size_t)kConsumerWarps * RowVals<DH>::K * kYPow * sizeof(double);
   static bool configured = false;
   if (!configured) {

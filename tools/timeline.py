@@ -10,11 +10,14 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 nscales = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 H = W = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
 max_iter = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-t = TransformType.HOMOGRAPHY
-pairs = [synthetic.make_pair(i, H, W, 3, t, max_shift=1.0) for i in range(min(B, 2))]
+CH = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+RT = int(sys.argv[6]) if len(sys.argv) > 6 else 3
+TT = sys.argv[7] if len(sys.argv) > 7 else 'HOMOGRAPHY'
+t = TransformType[TT]
+pairs = [synthetic.make_pair(i, H, W, CH, t, max_shift=1.0) for i in range(min(B, 2))]
 I1 = np.stack([pairs[i % len(pairs)][0] for i in range(B)]); I2 = np.stack([pairs[i % len(pairs)][1] for i in range(B)])
-plan = _native.Plan(batch=B, height=H, width=W, channels=3, nscales=nscales, nu=0.5, transform_type=t.value,
-                    robust_type=3, robust_loop=True, lambda_=0.0, tol=1e-9, max_iter=max_iter, delta=10, nanifoutside=True)
+plan = _native.Plan(batch=B, height=H, width=W, channels=CH, nscales=nscales, nu=0.5, transform_type=t.value,
+                    robust_type=RT, robust_loop=RT != 0, lambda_=0.0, tol=1e-9, max_iter=max_iter, delta=10, nanifoutside=True)
 plan.debug_timeline(True)
 plan.run_host(I1, I2)
 plan.run_host(I1, I2)
