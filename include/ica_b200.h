@@ -224,6 +224,13 @@ ICA_API int ica_dij_reduce_host(const double* DIJ, const double* DI, const doubl
 ICA_API int ica_transform_image_host(const double* image, int32_t height, int32_t width, int32_t channels,
                                      const double* matrix9, double* out);
 
+/* out = A_y * image * A_x^T for caller-supplied banded operators: output row o of axis y reads input rows
+   ystart[o] .. ystart[o]+ytaps-1 with weights yweights[o*ytaps ..]; same along x (at most 64 taps).  Optionally clipped to
+   the input's [min,max].  Runs on the pyramid kernels; used by the mirror of zm.zoom_out (zoom.py:29-60). */
+ICA_API int ica_apply_operators_host(const float* image, int32_t height, int32_t width, int32_t channels,
+                                     const int32_t* ystart, const float* yweights, int32_t ytaps, int32_t ny_out,
+                                     const int32_t* xstart, const float* xweights, int32_t xtaps, int32_t nx_out,
+                                     int32_t clip_to_input_range, float* out);
 /* bi.bicubic_interpolation_image (bicubic_interpolation.py:121-152): the IPOL-style warp -- the model is selected by
    the number of parameters (tr.project, transformation.py:144-186), NaN (nanifoutside) or 0 within `delta` of the border
    of the projected domain, Catmull-Rom with clamped (Neumann) neighbours, no clipping.  Not used by the drivers. */

@@ -76,6 +76,8 @@ SIGNATURES = {
     "ica_steepest_descent_host": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "ica_dij_reduce_host": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "ica_transform_image_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "ica_apply_operators_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _PI, _P, C.c_int32, C.c_int32,
+                                           _PI, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "ica_warp_ipol_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "ica_warp_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "ica_rescale_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _PI, _PI]),
@@ -285,6 +287,19 @@ def transform_image(image, inverse_matrix) -> np.ndarray:
     out = np.empty_like(img)
     check(lib().ica_transform_image_host(_ptr(img), img.shape[0], img.shape[1], img.shape[2], _ptr(m), _ptr(out)))
     return out[:, :, 0] if squeeze else out
+
+
+def apply_operators(image, ystart, yweights, xstart, xweights, clip: bool) -> np.ndarray:
+    """``out = A_y . image . A_x^T`` with banded operators given as (start [n_out], weights [n_out, taps])."""
+    require_gpu()
+    img = _as_image_f32(image)
+    ys = np.ascontiguousarray(ystart, dtype=np.int32); yw = np.ascontiguousarray(yweights, dtype=np.float32)
+    xs = np.ascontiguousarray(xstart, dtype=np.int32); xw = np.ascontiguousarray(xweights, dtype=np.float32)
+    out = np.empty((ys.size, xs.size, img.shape[2]), dtype=np.float32)
+    check(lib().ica_apply_operators_host(_ptr(img), img.shape[0], img.shape[1], img.shape[2],
+                                         ys.ctypes.data_as(_PI), _ptr(yw), yw.shape[1], ys.size,
+                                         xs.ctypes.data_as(_PI), _ptr(xw), xw.shape[1], xs.size, 1 if clip else 0, _ptr(out)))
+    return out
 
 
 def warp_ipol(image, params, nparams: int, nanifoutside: bool, delta: int) -> np.ndarray:

@@ -881,6 +881,63 @@ int ica_resample_operator(int32_t n_in, int32_t n_out, int32_t* taps_out, int32_
   return ICA_OK;
 }
 
+// out = A_y * image * A_x^T for caller-supplied banded operators (rows of `taps` weights starting at start[o]); the
+// two-pass / fused kernels of the pyramid do the work.  Used by the Python mirror of zoom.zoom_out.
+int ica_apply_operators_host(const float* image, int32_t height, int32_t width, int32_t channels,
+                             const int32_t* ystart, const float* yweights, int32_t ytaps, int32_t ny_out,
+                             const int32_t* xstart, const float* xweights, int32_t xtaps, int32_t nx_out,
+                             int32_t clip_to_input_range, float* out) {
+  if (!image || !out || !ystart || !yweights || !xstart || !xweights || height < 1 || width < 1 || (channels != 1 && channels != 3) ||
+      ny_out < 1 || nx_out < 1 || ytaps < 1 || xtaps < 1) { set_error("bad argument"); return ICA_ERR_INVALID; }
+  if (ytaps > max_taps() || xtaps > max_taps() || ytaps > height || xtaps > width) {
+    set_error("operator band too wide (%d / %d taps; at most %d and the image size)", ytaps, xtaps, max_taps());
+    return ICA_ERR_INVALID;
+  }
+  for (int o = 0; o < ny_out; ++o) if (ystart[o] < 0 || ystart[o] + ytaps > height) { set_error("row operator reads outside the image"); return ICA_ERR_INVALID; }
+  for (int o = 0; o < nx_out; ++o) if (xstart[o] < 0 || xstart[o] + xtaps > width) { set_error("column operator reads outside the image"); return ICA_ERR_INVALID; }
+  if (int rc = require_device()) return rc;
+  Resample1D ry, rx;
+  ry.n_in = height; ry.n_out = ny_out; ry.taps = ytaps; ry.start.assign(ystart, ystart + ny_out);
+  ry.weights.assign(yweights, yweights + (size_t)ny_out * ytaps);
+  rx.n_in = width; rx.n_out = nx_out; rx.taps = xtaps; rx.start.assign(xstart, xstart + nx_out);
+  rx.weights.assign(xweights, xweights + (size_t)nx_out * xtaps);
+  DeviceResample dy, dx;
+  float *d_in = nullptr, *d_out = nullptr, *d_tmp = nullptr;
+  MinMaxKeys* d_mm = nullptr;
+  const size_t n_in = (size_t)height * width * channels;
+  const int out_pitch = (nx_out * channels + 3) / 4 * 4;
+  const size_t n_out = (size_t)ny_out * out_pitch;
+  const long long tmp_stride = ((long long)ny_out * width * channels + 3) / 4 * 4;
+  int rc = upload_resample(nullptr, ry, &dy);
+  if (!rc) rc = upload_resample(nullptr, rx, &dx);
+  if (!rc) rc = dev_alloc<float>(nullptr, &d_in, n_in);
+  if (!rc) rc = dev_alloc<float>(nullptr, &d_out, 2 * n_out);
+  if (!rc) rc = dev_alloc<float>(nullptr, &d_tmp, (size_t)(2 * tmp_stride));
+  if (!rc) rc = dev_alloc<MinMaxKeys>(nullptr, &d_mm, 4);
+  cudaError_t e = cudaSuccess;
+  if (!rc) {
+    e = cudaMemcpy(d_in, image, n_in * sizeof(float), cudaMemcpyHostToDevice);
+    // keys: [0],[1] parent (image a, b), [2],[3] child
+    MinMaxKeys open_range[4];
+    for (auto& k : open_range) { k.lo = float_key(-3.4028235e38f); k.hi = float_key(3.4028235e38f); }
+    if (e == cudaSuccess) e = cudaMemcpy(d_mm, open_range, sizeof(open_range), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && clip_to_input_range) {
+      e = launch_minmax_reset(d_mm, 2, 0);
+      if (e == cudaSuccess) e = launch_minmax(d_in, 0, (long long)n_in, 2, d_mm, 1, 0);   // the same image stands for both sets
+    }
+    if (e == cudaSuccess)
+      e = launch_pyr_down(d_in, d_in, (long long)n_in, width * channels, width, height, channels, dy, dx, d_tmp, tmp_stride, d_out,
+                          d_out + n_out, (long long)n_out, out_pitch, 1, d_mm, d_mm + 2, 2, 0, nullptr);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2D(out, (size_t)nx_out * channels * sizeof(float), d_out, (size_t)out_pitch * sizeof(float),
+                       (size_t)nx_out * channels * sizeof(float), ny_out, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_error("ica_apply_operators_host: %s", cudaGetErrorString(e)); rc = ICA_ERR_CUDA; }
+  }
+  free_resample(&dy); free_resample(&dx);
+  cudaFree(d_in); cudaFree(d_out); cudaFree(d_tmp); cudaFree(d_mm);
+  return rc;
+}
+
 int ica_nparams(int32_t t) { int n = nparams_of(t); if (n < 0) set_error("Unknown transform type"); return n < 0 ? ICA_ERR_INVALID : n; }
 
 int ica_params2matrix(const double* p, int32_t t, double* m9) {

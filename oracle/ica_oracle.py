@@ -522,3 +522,21 @@ def bicubic_interpolation_image(image, params, nparams, nanifoutside, delta):
         res[:, :, k] = _keys(v[0], v[1], v[2], v[3], fx)
     res[out] = np.nan if nanifoutside else 0.0
     return res
+
+
+# ----------------------------------------------------------- zoom.py: zoom_out (dead code in the reference)
+def zoom_out(I, factor, sigma_zero=0.6):
+    """zoom.py:29-60 as its docstring and loop state it: per channel ``gaussian_filter(sigma = 0.6 * sqrt(1/f^2 - 1))``
+    (scipy defaults: reflect, truncate 4), then ``map_coordinates(order=3, mode='nearest')`` at (i / f, j / f) for
+    i < round(ny f), j < round(nx f).  PARITY UNPINNED: the reference function itself raises on current scipy (it passes
+    scalar coordinates), and nothing in the reference calls it."""
+    from scipy import ndimage as ndi
+    img = np.asarray(I, dtype=np.float64)
+    ny, nx, nz = img.shape
+    nyy, nxx = int(np.round(ny * factor)), int(np.round(nx * factor))
+    sigma = sigma_zero * np.sqrt(1.0 / (factor * factor) - 1.0)
+    ii, jj = np.meshgrid(np.arange(nyy) / factor, np.arange(nxx) / factor, indexing="ij")
+    out = np.empty((nyy, nxx, nz))
+    for c in range(nz):
+        out[:, :, c] = ndi.map_coordinates(ndi.gaussian_filter(img[:, :, c], sigma=sigma), [ii, jj], order=3, mode="nearest")
+    return out

@@ -626,3 +626,17 @@ def test_device_resident_entry_matches_host_entry(nat):
     assert np.array_equal(pd.cpu().numpy(), ph) and np.array_equal(ed, eh) and np.array_equal(idv, ih)
     with pytest.raises(ValueError):
         register_batch_device(torch.zeros((2, 8, 8, 3)), torch.zeros((2, 8, 8, 3)), t)
+
+
+def test_zoom_out_matches_oracle(nat, rubber_whale):
+    """zm.zoom_out (IPOL-style level; dead code in the reference, parity unpinned): GPU application of the host-built
+    operators against the oracle's direct scipy evaluation."""
+    from inverse_compositional_algorithm_b200 import zoom as zm
+    img = rubber_whale["rubber_whale"][:201, :300].astype(np.float64)
+    for f in (0.5, 0.75):
+        got = zm.zoom_out(img, f)
+        want = orc.zoom_out(img, f)
+        assert got.shape == want.shape
+        assert rel_err(got, want) <= 1e-5
+    gray = zm.zoom_out(img[:, :, :1], 0.5)
+    assert rel_err(gray, orc.zoom_out(img[:, :, :1], 0.5)) <= 1e-5

@@ -208,3 +208,23 @@ def test_sharded_registration_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0 and "ok" in o, o
+
+
+def test_zoom_out_operator_reproduces_scipy_chain():
+    """Host logic of zoom.zoom_out: the banded 1-D operator (built by pushing the identity through scipy) applied along
+    both axes equals the direct Gaussian + cubic-spline resampling of the oracle."""
+    from oracle import ica_oracle as orc
+    from inverse_compositional_algorithm_b200.zoom import zoom_out_operator
+    rng = np.random.default_rng(11)
+    img = rng.uniform(0, 255, (75, 98, 2))
+    for f in (0.5, 0.6):
+        ys, yw = zoom_out_operator(75, f)
+        xs, xw = zoom_out_operator(98, f)
+        assert yw.shape[1] <= 64 and xw.shape[1] <= 64
+        ay = np.zeros((ys.size, 75)); ax = np.zeros((xs.size, 98))
+        for o in range(ys.size): ay[o, ys[o]:ys[o] + yw.shape[1]] = yw[o]
+        for o in range(xs.size): ax[o, xs[o]:xs[o] + xw.shape[1]] = xw[o]
+        got = np.einsum("oy,yxc,px->opc", ay, img, ax)
+        want = orc.zoom_out(img, f)
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
