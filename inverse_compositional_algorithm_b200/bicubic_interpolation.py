@@ -53,3 +53,15 @@ def bicubic_interpolation_image(input, params, nparams, nanifoutside, delta):
     if nparams not in (2, 3, 4, 6, 8):
         raise ValueError("Invalid transformation type")
     return _native.warp_ipol(np.asarray(input, dtype=np.float64), params, nparams, bool(nanifoutside), int(delta))
+
+
+def bicubic_interpolation_point(input, uu, vv, nx, ny, nz, k):
+    """``src/bicubic_interpolation.py:66-118``: the IPOL-style interpolation of channel ``k`` at ONE point (scalar host
+    logic; whole images go through :func:`bicubic_interpolation_image` on the GPU)."""
+    sx = -1 if uu < 0 else 1
+    sy = -1 if vv < 0 else 1
+    x, y = neumann_bc(int(uu), nx), neumann_bc(int(vv), ny)
+    xs = [neumann_bc(int(uu) - sx, nx), x, neumann_bc(int(uu) + sx, nx), neumann_bc(int(uu) + 2 * sx, nx)]
+    ys = [neumann_bc(int(vv) - sy, ny), y, neumann_bc(int(vv) + sy, ny), neumann_bc(int(vv) + 2 * sy, ny)]
+    pol = [[float(input[ys[b], xs[a], k]) for b in range(4)] for a in range(4)]
+    return bicubic_interpolation_array(pol, uu - x, vv - y)

@@ -228,3 +228,15 @@ def test_zoom_out_operator_reproduces_scipy_chain():
         want = orc.zoom_out(img, f)
         assert got.shape == want.shape
         assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+
+
+def test_ipol_point_interpolation_matches_reference_golden():
+    """Scalar helper ``bicubic_interpolation_point`` (host logic) against the reference's whole-image outputs."""
+    from inverse_compositional_algorithm_b200 import bicubic_interpolation as bi
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ipol_warp.npz")))
+    img, p, want = g["image"], g["params_0"], g["out_0"]          # translation, delta 2, NaN outside
+    ny, nx, nz = img.shape
+    for (i, j) in [(5, 7), (10, 20), (15, 3)]:
+        x, y = j + p[0], i + p[1]
+        for k in range(nz):
+            assert abs(bi.bicubic_interpolation_point(img, x, y, nx, ny, nz, k) - want[i, j, k]) <= 1e-10
