@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <vector>
 #include <cuda.h>
 #include "ica_common.cuh"
@@ -722,6 +723,18 @@ int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* 
 // hand-over was measured slower.)
 static std::mutex g_h2d_mutex;
 
+// The host entry waits on events by polling with a yield in between: a lone caller sees the event as fast as a spinning
+// cudaEventSynchronize would, while many concurrent callers (several plans per GPU, several ranks per host) give their
+// core away instead of spinning on it (blocking-sync events were measured to add ~0.4 ms to a single call).
+static int wait_event_polite(cudaEvent_t ev) {
+  for (;;) {
+    const cudaError_t e = cudaEventQuery(ev);
+    if (e == cudaSuccess) return ICA_OK;
+    if (e != cudaErrorNotReady) { set_error("cudaEventQuery failed: %s", cudaGetErrorString(e)); return ICA_ERR_CUDA; }
+    std::this_thread::yield();
+  }
+}
+
 // both images of the batch host -> device; u8 / f64 inputs go through two staging areas so that the two copies run
 // back to back and the link is released before the conversions to float32 are even scheduled
 static int upload_pair(ica_plan* pl, const void* h1, const void* h2, int dtype, cudaStream_t stream) {
@@ -774,7 +787,7 @@ int ica_plan_run_host(ica_plan* pl, const void* I1_host, const void* I2_host, in
     ICA_CUDA_CHECK(cudaMemcpyAsync(pl->p_dev, p_inout_host, (size_t)pl->B * ICA_MAX_PARAMS * sizeof(double),
                                    cudaMemcpyHostToDevice, stream));
     if (int rc = upload_pair(pl, I1_host, I2_host, dtype, stream)) return rc;
-    ICA_CUDA_CHECK(cudaEventSynchronize(pl->ev_h2d_done));   // the link is free for the next caller
+    if (int rc = wait_event_polite(pl->ev_h2d_done)) return rc;   // the link is free for the next caller
   }
   if (int rc = ica_plan_run_device(pl, pl->in1_dev, pl->in2_dev, pl->p_dev, stream)) return rc;
   pl->launches += (dtype == 0 ? 0 : 2);   // the two conversion kernels
@@ -786,7 +799,7 @@ int ica_plan_run_host(ica_plan* pl, const void* I1_host, const void* I2_host, in
   if (DI_out) ICA_CUDA_CHECK(cudaMemcpyAsync(DI_out, pl->DI_dev, nimg * sizeof(float), cudaMemcpyDeviceToHost, stream));
   if (Iw_out) ICA_CUDA_CHECK(cudaMemcpyAsync(Iw_out, pl->Iw_dev, nimg * sizeof(float), cudaMemcpyDeviceToHost, stream));
   ICA_CUDA_CHECK(cudaEventRecord(pl->ev_host1, stream));
-  ICA_CUDA_CHECK(cudaStreamSynchronize(stream));
+  if (int rc = wait_event_polite(pl->ev_host1)) return rc;
   return ICA_OK;
 }
 
