@@ -640,3 +640,35 @@ def test_zoom_out_matches_oracle(nat, rubber_whale):
         assert rel_err(got, want) <= 1e-5
     gray = zm.zoom_out(img[:, :, :1], 0.5)
     assert rel_err(gray, orc.zoom_out(img[:, :, :1], 0.5)) <= 1e-5
+
+
+def test_random_shapes_and_options_match_oracle(nat):
+    """Seeded sweep over image shapes (odd sizes, smaller than a tile, wider than several tiles), channel counts,
+    transform types, error functions, scale counts and frame widths: the motion and the iteration counts of every case
+    must match the oracle.  Exercises tile/box edges of the iterate kernel and the border logic of the pyramid."""
+    from inverse_compositional_algorithm_b200 import synthetic
+    from inverse_compositional_algorithm_b200.inverse_compositional_algorithm import register_batch
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    rng = np.random.default_rng(424242)
+    types = list(TransformType)
+    worst = 0.0
+    for case in range(24):
+        h, w = int(rng.integers(24, 230)), int(rng.integers(24, 300))
+        c = int(rng.choice([1, 3]))
+        t = types[int(rng.integers(0, 5))]
+        rtype = int(rng.integers(0, 5))
+        nscales = int(rng.integers(1, 4))
+        while min(h, w) * 0.5 ** (nscales - 1) < 12:
+            nscales -= 1
+        delta = int(rng.integers(0, 6))
+        I1, I2, _ = synthetic.make_pair(9000 + case, h, w, c, t, max_shift=1.5, max_lin=0.01, margin=24)
+        p, err, iters = register_batch(I1[None], I2[None], t, nscales=nscales, robust_type=rtype, delta=delta)
+        a, b = (np.repeat(x, 3, 2) if c == 1 else x for x in (I1, I2))
+        trace = []
+        po, eo, _, _ = orc.ica_pyramidal(a.astype(np.float64), b.astype(np.float64), np.zeros(t.nparams()), t.value, nscales,
+                                         0.5, 1e-3, rtype, 0.0, True, delta, trace=trace)
+        epe = _epe(p[0, :t.nparams()], po, t.value, w, h)
+        worst = max(worst, epe)
+        assert epe <= EPE_TOL, (case, h, w, c, t, rtype, nscales, delta, epe)
+        assert int(iters[0].sum()) == len(trace), (case, h, w, c, t, rtype, nscales, delta, iters[0], len(trace))
+    print("worst EPE over the sweep:", worst)
