@@ -672,3 +672,32 @@ def test_random_shapes_and_options_match_oracle(nat):
         assert epe <= EPE_TOL, (case, h, w, c, t, rtype, nscales, delta, epe)
         assert int(iters[0].sum()) == len(trace), (case, h, w, c, t, rtype, nscales, delta, iters[0], len(trace))
     print("worst EPE over the sweep:", worst)
+
+
+def test_plan_reuse_with_moving_images_and_types(nat):
+    """One plan, several calls with images at different device addresses (the level-0 TMA tensor maps are re-encoded)
+    and changing per-pair transform types (moment degree and loop graph change): every call must equal a fresh run."""
+    import torch
+    from inverse_compositional_algorithm_b200 import _native, synthetic
+    from inverse_compositional_algorithm_b200.inverse_compositional_algorithm import register_batch
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    B, h, w = 3, 120, 152
+    sets = []
+    for k, t in enumerate([TransformType.HOMOGRAPHY, TransformType.SIMILARITY, TransformType.HOMOGRAPHY]):
+        pairs = [synthetic.make_pair(1200 + 10 * k + i, h, w, 3, t, max_shift=2.0, margin=32) for i in range(B)]
+        sets.append((t, np.stack([a for a, _, _ in pairs]), np.stack([b for _, b, _ in pairs])))
+    plan = _native.Plan(batch=B, height=h, width=w, channels=3, nscales=3, nu=0.5, transform_type=TransformType.HOMOGRAPHY.value,
+                        robust_type=3, robust_loop=True, lambda_=0.0, tol=1e-3, max_iter=30, delta=5, nanifoutside=True)
+    keep = []          # keep every upload alive so that the addresses really differ
+    for rep in range(2):
+        for t, I1, I2 in sets:
+            a, b = torch.from_numpy(I1).cuda(), torch.from_numpy(I2).cuda()
+            keep.append((a, b))
+            plan.set_transform_types([t.value] * B)
+            p = torch.zeros((B, 8), dtype=torch.float64, device="cuda")
+            plan.run_device(a.data_ptr(), b.data_ptr(), p.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            got, err, iters = plan.results()
+            want, werr, wit = register_batch(I1, I2, t, nscales=3, robust_type=3, delta=5)
+            assert np.array_equal(got, want) and np.array_equal(iters, wit)
+    plan.close()
