@@ -311,13 +311,15 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   const bool robust = P.robust_loop != 0;
   const float chm = P.ch_mult;
   const int rtype = P.robust_type;
-  double* const accs = reinterpret_cast<double*>(smem + kStages * Stage<C>::kFloats);   // [kConsumerWarps][K][kYPow]
+  // fp64 accumulators of the chunk in progress, double-buffered over consecutive chunks: [2][kConsumerWarps][K][kYPow]
+  double* const accs0 = reinterpret_cast<double*>(smem + kStages * Stage<C>::kFloats);
+  constexpr int kAccSet = kConsumerWarps * K * kYPow;
   // the transposing reduction leaves moment k on the lanes k << kTrShift .. ; the first of them owns the fp64 accumulators
   constexpr int kTrN = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
   constexpr int kTrShift = kTrN == 8 ? 2 : (kTrN == 16 ? 1 : 0);
   const int midx = lane >> kTrShift;
   const bool mown = (lane & ((1 << kTrShift) - 1)) == 0 && midx < K;
-  double* const myacc = accs + (warp * K + (mown ? midx : 0)) * kYPow;
+  double* myacc = accs0 + (warp * K + (mown ? midx : 0)) * kYPow;    // this lane's slot in the current set
   unsigned k = 0;
   int nitems = 0;
   const bool dbg = P.dbg_time != nullptr && tid == 0;       // profiling hook: cycles warp 0 spends waiting / in chunk epilogues
@@ -550,9 +552,12 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
     ICA_STAMP(2);
     const long long e0 = dbg ? clock64() : 0;
 
-    // ---------------- chunk partial: [K][kYPow] doubles, warps summed in fixed order
+    // ---------------- chunk partial: [K][kYPow] doubles, warps summed in fixed order.  One barrier per chunk: the
+    // next chunk accumulates into the other set, and this set is only zeroed again after the next chunk's barrier,
+    // which the summing threads reach after they are done with it.
     consumer_sync();
     {
+      const double* accs = accs0 + (nitems & 1 ? 0 : kAccSet);   // nitems was just incremented: the set of this chunk
       double* out = P.partials + ((long long)pair * P.max_chunks + chunk) * kAccStride;
       for (int i = tid; i < NENT; i += kConsumerThreads) {
         double sum = 0.0;
@@ -561,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
         out[i] = sum;
       }
     }
-    consumer_sync();   // every warp's shared accumulators may be reused by the CTA's next chunk
+    myacc += (nitems & 1) ? kAccSet : -kAccSet;     // the other set for the next chunk
     if (dbg) dbg_epi += clock64() - e0;
   }
   if (dbg) {
@@ -993,7 +998,7 @@ __global__ void ica_gradient_kernel(const float* __restrict__ img, int nx, int n
 template <int C, int DH>
 cudaError_t launch_iterate_t(const IterParams& P, int grid, cudaStream_t stream) {
   constexpr size_t smem = Stage<C>::kStages * (size_t)Stage<C>::kFloats * sizeof(float) +
-                          (size_t)kConsumerWarps * RowVals<DH>::K * kYPow * sizeof(double);
+                          2 * (size_t)kConsumerWarps * RowVals<DH>::K * kYPow * sizeof(double);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(ica_iterate_kernel<C, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
