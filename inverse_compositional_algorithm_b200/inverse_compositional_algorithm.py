@@ -12,6 +12,8 @@ but with per-pair convergence).
 """
 from __future__ import annotations
 
+import threading
+
 import numpy as np
 
 from . import _native
@@ -21,10 +23,18 @@ from .transformation import TransformType, _as_type
 
 _PLAN_CACHE: dict = {}
 _PLAN_CACHE_MAX = 8
+# cached plans are shared by every caller of this module: calls are serialised (a plan runs one registration at a time;
+# for concurrent streams of work create `_native.Plan` objects per thread, as bench.py does)
+_LOCK = threading.RLock()
 
 
 def _get_plan(**key):
     k = tuple(sorted(key.items()))
+    with _LOCK:
+        return _get_plan_locked(k, key)
+
+
+def _get_plan_locked(k, key):
     plan = _PLAN_CACHE.get(k)
     if plan is None:
         if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
@@ -84,16 +94,17 @@ def _run_single(I1, I2, p, transform_type, nscales, nu, TOL, robust_type, robust
     r = _as_robust(robust_type)
     n = t.nparams()
     ny, nx, nz = I1.shape
-    plan = _get_plan(batch=1, height=ny, width=nx, channels=nz, nscales=int(nscales), nu=float(nu),
-                     transform_type=t.value, robust_type=r.value, robust_loop=bool(robust_loop),
-                     lambda_=float(lambda_), tol=float(TOL), max_iter=cts.MAX_ITER, delta=int(delta),
-                     nanifoutside=(nanifoutside is True), gray_as_rgb=False,
-                     record_trajectory=bool(verbose), write_di_iw=True)
-    p0 = np.zeros(_native.MAX_PARAMS)
-    p0[:n] = np.asarray(p, dtype=np.float64)[:n]
-    pout, err, iters, DI, Iw = plan.run_host(_as_batch(I1), _as_batch(I2), p0[None], want_images=True)
-    if verbose:
-        _print_trace(plan.trajectory()[0], n, quadratic=not robust_loop, with_scale=nscales > 1)
+    with _LOCK:      # plan acquisition and use are one critical section (an eviction must not close a plan in use)
+        plan = _get_plan(batch=1, height=ny, width=nx, channels=nz, nscales=int(nscales), nu=float(nu),
+                         transform_type=t.value, robust_type=r.value, robust_loop=bool(robust_loop),
+                         lambda_=float(lambda_), tol=float(TOL), max_iter=cts.MAX_ITER, delta=int(delta),
+                         nanifoutside=(nanifoutside is True), gray_as_rgb=False,
+                         record_trajectory=bool(verbose), write_di_iw=True)
+        p0 = np.zeros(_native.MAX_PARAMS)
+        p0[:n] = np.asarray(p, dtype=np.float64)[:n]
+        pout, err, iters, DI, Iw = plan.run_host(_as_batch(I1), _as_batch(I2), p0[None], want_images=True)
+        if verbose:
+            _print_trace(plan.trajectory()[0], n, quadratic=not robust_loop, with_scale=nscales > 1)
     return pout[0, :n].copy(), float(err[0]), DI[0].astype(np.float64), Iw[0].astype(np.float64)
 
 
@@ -162,15 +173,16 @@ def register_batch(I1, I2, transform_type, nscales=1, nu=0.5, TOL=1e-3,
     if len(types) != B:
         raise ValueError("one transform type per pair is required")
     r = _as_robust(robust_type)
-    if plan is None:
-        plan = _get_plan(batch=B, height=ny, width=nx, channels=nz, nscales=int(nscales),
-                         nu=float(nu), transform_type=types[0].value, robust_type=r.value,
-                         robust_loop=r != RobustErrorFunctionType.QUADRATIC, lambda_=float(lambda_),
-                         tol=float(TOL), max_iter=cts.MAX_ITER, delta=int(delta),
-                         nanifoutside=(nanifoutside is True), gray_as_rgb=bool(gray_as_rgb) and nz == 1,
-                         record_trajectory=False, write_di_iw=bool(return_images))
-    plan.set_transform_types([t.value for t in types])
-    pout, err, iters, DI, Iw = plan.run_host(I1, I2, p0, want_images=return_images)
+    with _LOCK:
+        if plan is None:
+            plan = _get_plan(batch=B, height=ny, width=nx, channels=nz, nscales=int(nscales),
+                             nu=float(nu), transform_type=types[0].value, robust_type=r.value,
+                             robust_loop=r != RobustErrorFunctionType.QUADRATIC, lambda_=float(lambda_),
+                             tol=float(TOL), max_iter=cts.MAX_ITER, delta=int(delta),
+                             nanifoutside=(nanifoutside is True), gray_as_rgb=bool(gray_as_rgb) and nz == 1,
+                             record_trajectory=False, write_di_iw=bool(return_images))
+        plan.set_transform_types([t.value for t in types])
+        pout, err, iters, DI, Iw = plan.run_host(I1, I2, p0, want_images=return_images)
     if return_images:
         return pout, err, iters, DI, Iw
     return pout, err, iters
@@ -196,7 +208,7 @@ def register_batch_device(I1, I2, transform_type, nscales=1, nu=0.5, TOL=1e-3,
     if len(types) != B:
         raise ValueError("one transform type per pair is required")
     r = _as_robust(robust_type)
-    with torch.cuda.device(I1.device):
+    with _LOCK, torch.cuda.device(I1.device):
         plan = _get_plan(batch=B, height=ny, width=nx, channels=nz, nscales=int(nscales), nu=float(nu),
                          transform_type=types[0].value, robust_type=r.value,
                          robust_loop=r != RobustErrorFunctionType.QUADRATIC, lambda_=float(lambda_), tol=float(TOL),

@@ -701,3 +701,27 @@ def test_plan_reuse_with_moving_images_and_types(nat):
             want, werr, wit = register_batch(I1, I2, t, nscales=3, robust_type=3, delta=5)
             assert np.array_equal(got, want) and np.array_equal(iters, wit)
     plan.close()
+
+
+def test_drivers_are_thread_safe(nat):
+    """Several Python threads calling the drop-in driver with the same configuration share one cached plan: calls are
+    serialised and every thread gets its own (correct, bit-identical) answer."""
+    import threading
+    from inverse_compositional_algorithm_b200 import synthetic
+    from inverse_compositional_algorithm_b200.inverse_compositional_algorithm import pyramidal_inverse_compositional_algorithm
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    t = TransformType.AFFINITY
+    pairs = [synthetic.make_pair(1500 + i, 100, 140, 3, t, max_shift=2.0, margin=32) for i in range(4)]
+    want = [pyramidal_inverse_compositional_algorithm(a, b, np.zeros(6), t, 2, 0.5, 1e-3, 3, 0.0, True, 5, False)[0] for a, b, _ in pairs]
+    got = [[None] * 3 for _ in pairs]
+
+    def work(i):
+        a, b, _ = pairs[i]
+        for rep in range(3):
+            got[i][rep] = pyramidal_inverse_compositional_algorithm(a, b, np.zeros(6), t, 2, 0.5, 1e-3, 3, 0.0, True, 5, False)[0]
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [x.start() for x in ths]; [x.join() for x in ths]
+    for i in range(4):
+        for rep in range(3):
+            assert np.array_equal(got[i][rep], want[i])
