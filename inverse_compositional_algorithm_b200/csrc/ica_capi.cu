@@ -89,6 +89,7 @@ struct ica_plan {
   std::vector<unsigned char> tmaps_host;
   const float *tm_I1 = nullptr, *tm_I2 = nullptr;   // level-0 images the maps currently describe
   float *pad1 = nullptr, *pad2 = nullptr;    // level-0 copies with 16-byte rows (only when the caller's rows are not)
+  bool mm_ready = false;                     // the keys were reset and level 0's min/max filled by the ingest conversion
   const float *k2_I1 = nullptr, *k2_I2 = nullptr;   // K2's view of level 0 in the current run
   long long k2_stride = 0;
   int k2_pitch = 0;
@@ -333,14 +334,17 @@ int ensure_loop_graph(ica_plan* pl, const float* I1, const float* I2) {
 // minmax of level 0 and all pyramid levels of both images
 int build_pyramids(ica_plan* pl, const float* I1, const float* I2, cudaStream_t stream) {
   const int B = pl->B, ns = pl->nscales;
-  ICA_LAUNCH_CHECK(launch_minmax_reset(pl->mm, B * ns * 2, stream));
-  pl->launches += 1;
-  const long long n0 = (long long)pl->H * pl->W * pl->C;
-  const float* src[2] = {I1, I2};
-  for (int which = 0; which < 2; ++which) {
-    ICA_LAUNCH_CHECK(launch_minmax(src[which], pl->in_stride, n0, B, pl->mm + which, ns * 2, stream));
+  if (!pl->mm_ready) {   // (the host entry's u8 / f64 conversion kernels have done this already)
+    ICA_LAUNCH_CHECK(launch_minmax_reset(pl->mm, B * ns * 2, stream));
     pl->launches += 1;
+    const long long n0 = (long long)pl->H * pl->W * pl->C;
+    const float* src[2] = {I1, I2};
+    for (int which = 0; which < 2; ++which) {
+      ICA_LAUNCH_CHECK(launch_minmax(src[which], pl->in_stride, n0, B, pl->mm + which, ns * 2, stream));
+      pl->launches += 1;
+    }
   }
+  pl->mm_ready = false;
   for (int s = 0; s + 1 < ns; ++s) {
     const LevelDesc& Li = pl->lv[s];
     const LevelDesc& Lo = pl->lv[s + 1];
@@ -758,13 +762,17 @@ static int upload_pair(ica_plan* pl, const void* h1, const void* h2, int dtype, 
   ICA_CUDA_CHECK(cudaMemcpyAsync(r1, h1, (size_t)n * esz, cudaMemcpyHostToDevice, stream));
   ICA_CUDA_CHECK(cudaMemcpyAsync(r2, h2, (size_t)n * esz, cudaMemcpyHostToDevice, stream));
   ICA_CUDA_CHECK(cudaEventRecord(pl->ev_h2d_done, stream));
+  // conversion to float32 fused with the level-0 min/max of every image (saves the separate pass over level 0)
+  const int ns = pl->nscales;
+  ICA_LAUNCH_CHECK(launch_minmax_reset(pl->mm, pl->B * ns * 2, stream));
   if (dtype == 1) {
-    ICA_LAUNCH_CHECK(launch_convert_u8(r1, pl->in1_dev, n, stream));
-    ICA_LAUNCH_CHECK(launch_convert_u8(r2, pl->in2_dev, n, stream));
+    ICA_LAUNCH_CHECK(launch_convert_u8(r1, pl->in1_dev, pl->in_stride, pl->B, pl->mm + 0, ns * 2, stream));
+    ICA_LAUNCH_CHECK(launch_convert_u8(r2, pl->in2_dev, pl->in_stride, pl->B, pl->mm + 1, ns * 2, stream));
   } else {
-    ICA_LAUNCH_CHECK(launch_convert_f64(reinterpret_cast<const double*>(r1), pl->in1_dev, n, stream));
-    ICA_LAUNCH_CHECK(launch_convert_f64(reinterpret_cast<const double*>(r2), pl->in2_dev, n, stream));
+    ICA_LAUNCH_CHECK(launch_convert_f64(reinterpret_cast<const double*>(r1), pl->in1_dev, pl->in_stride, pl->B, pl->mm + 0, ns * 2, stream));
+    ICA_LAUNCH_CHECK(launch_convert_f64(reinterpret_cast<const double*>(r2), pl->in2_dev, pl->in_stride, pl->B, pl->mm + 1, ns * 2, stream));
   }
+  pl->mm_ready = true;
   return ICA_OK;
 }
 
@@ -789,8 +797,10 @@ int ica_plan_run_host(ica_plan* pl, const void* I1_host, const void* I2_host, in
     if (int rc = upload_pair(pl, I1_host, I2_host, dtype, stream)) return rc;
     if (int rc = wait_event_polite(pl->ev_h2d_done)) return rc;   // the link is free for the next caller
   }
-  if (int rc = ica_plan_run_device(pl, pl->in1_dev, pl->in2_dev, pl->p_dev, stream)) return rc;
-  pl->launches += (dtype == 0 ? 0 : 2);   // the two conversion kernels
+  const int rc_run = ica_plan_run_device(pl, pl->in1_dev, pl->in2_dev, pl->p_dev, stream);
+  pl->mm_ready = false;
+  if (rc_run) return rc_run;
+  pl->launches += (dtype == 0 ? 0 : 3);   // key reset + the two conversion kernels
   ICA_CUDA_CHECK(cudaMemcpyAsync(p_inout_host, pl->p_dev, (size_t)pl->B * ICA_MAX_PARAMS * sizeof(double),
                                  cudaMemcpyDeviceToHost, stream));
   if (err_out) ICA_CUDA_CHECK(cudaMemcpyAsync(err_out, pl->err_dev, pl->B * sizeof(double), cudaMemcpyDeviceToHost, stream));

@@ -605,11 +605,48 @@ __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ i
   }
 }
 
-// dtype conversion of host-format inputs (uint8 / float64 -> float32), vectorised by 4
+// dtype conversion of host-format inputs (uint8 / float64 -> float32) fused with the min/max of the converted image
+// (the level-0 clip range): grid (blocks, images); NaNs are skipped like np.nanmin / np.nanmax
 template <typename T>
-__global__ void convert_to_float_kernel(const T* __restrict__ in, float* __restrict__ out, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = (float)in[i];
+__global__ void __launch_bounds__(256) convert_minmax_kernel(const T* __restrict__ in0, float* __restrict__ out0, long long count,
+                                                              MinMaxKeys* __restrict__ mm, int mm_stride) {
+  const T* in = in0 + (long long)blockIdx.y * count;
+  float* out = out0 + (long long)blockIdx.y * count;
+  float fmin_ = 3.4e38f, fmax_ = -3.4e38f;
+  const bool vec = sizeof(T) == 1 && (count & 3) == 0 &&
+                   (((reinterpret_cast<unsigned long long>(in)) & 3ull) == 0) && (((reinterpret_cast<unsigned long long>(out)) & 15ull) == 0);
+  if (vec) {
+    const long long n4 = count >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(in) + i);
+      const float4 v = make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+      reinterpret_cast<float4*>(out)[i] = v;
+      fmin_ = fminf(fminf(fmin_, v.x), fminf(v.y, fminf(v.z, v.w)));
+      fmax_ = fmaxf(fmaxf(fmax_, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+      const float v = (float)in[i];
+      out[i] = v;
+      fmin_ = fminf(fmin_, v); fmax_ = fmaxf(fmax_, v);
+    }
+  }
+  unsigned kmin = 0xffffffffu, kmax = 0u;
+  if (fmin_ <= fmax_) { kmin = float_key(fmin_); kmax = float_key(fmax_); }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  }
+  __shared__ unsigned smin[8], smax[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { smin[warp] = kmin; smax[warp] = kmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { kmin = min(kmin, smin[w]); kmax = max(kmax, smax[w]); }
+    MinMaxKeys* k = mm + (long long)blockIdx.y * mm_stride;
+    if (kmin <= kmax) { atomicMin(&k->lo, kmin); atomicMax(&k->hi, kmax); }
+  }
 }
 
 }  // namespace
@@ -778,14 +815,17 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
   return cudaGetLastError();
 }
 
-cudaError_t launch_convert_u8(const unsigned char* in, float* out, long long n, cudaStream_t stream) {
-  int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
-  convert_to_float_kernel<unsigned char><<<blocks, 256, 0, stream>>>(in, out, n);
+// `nimg` images of `count` elements each; mm[img * mm_stride] receives the min/max keys of the converted image
+cudaError_t launch_convert_u8(const unsigned char* in, float* out, long long count, int nimg, MinMaxKeys* mm, int mm_stride,
+                              cudaStream_t stream) {
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((count / 4 + 256 * 8 - 1) / (256 * 8), 256));
+  convert_minmax_kernel<unsigned char><<<dim3(blocks, nimg), 256, 0, stream>>>(in, out, count, mm, mm_stride);
   return cudaGetLastError();
 }
-cudaError_t launch_convert_f64(const double* in, float* out, long long n, cudaStream_t stream) {
-  int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
-  convert_to_float_kernel<double><<<blocks, 256, 0, stream>>>(in, out, n);
+cudaError_t launch_convert_f64(const double* in, float* out, long long count, int nimg, MinMaxKeys* mm, int mm_stride,
+                               cudaStream_t stream) {
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((count + 256 * 8 - 1) / (256 * 8), 256));
+  convert_minmax_kernel<double><<<dim3(blocks, nimg), 256, 0, stream>>>(in, out, count, mm, mm_stride);
   return cudaGetLastError();
 }
 

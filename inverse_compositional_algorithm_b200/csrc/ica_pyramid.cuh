@@ -41,7 +41,10 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
                             long long tmp_stride, float* out0a, float* out0b, long long out_stride, int out_pitch, int nset,
                             const MinMaxKeys* mm_parent, MinMaxKeys* mm_child, int mm_stride, cudaStream_t stream,
                             int* launches = nullptr);
-cudaError_t launch_convert_u8(const unsigned char* in, float* out, long long n, cudaStream_t stream);
-cudaError_t launch_convert_f64(const double* in, float* out, long long n, cudaStream_t stream);
+// uint8 / float64 -> float32 for nimg images of `count` elements, fused with each image's min/max keys
+cudaError_t launch_convert_u8(const unsigned char* in, float* out, long long count, int nimg, MinMaxKeys* mm, int mm_stride,
+                              cudaStream_t stream);
+cudaError_t launch_convert_f64(const double* in, float* out, long long count, int nimg, MinMaxKeys* mm, int mm_stride,
+                               cudaStream_t stream);
 
 }  // namespace ica
