@@ -225,7 +225,7 @@ ICA_API int ica_transform_image_host(const double* image, int32_t height, int32_
                                      const double* matrix9, double* out);
 
 /* out = A_y * image * A_x^T for caller-supplied banded operators: output row o of axis y reads input rows
-   ystart[o] .. ystart[o]+ytaps-1 with weights yweights[o*ytaps ..]; same along x (at most 64 taps).  Optionally clipped to
+   ystart[o] .. ystart[o]+ytaps-1 with weights yweights[o*ytaps ..]; same along x (at most 128 taps).  Optionally clipped to
    the input's [min,max].  Runs on the pyramid kernels; used by the mirror of zm.zoom_out (zoom.py:29-60). */
 ICA_API int ica_apply_operators_host(const float* image, int32_t height, int32_t width, int32_t channels,
                                      const int32_t* ystart, const float* yweights, int32_t ytaps, int32_t ny_out,

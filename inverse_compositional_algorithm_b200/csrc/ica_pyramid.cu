@@ -148,7 +148,7 @@ void detect_uniform_rows(const Resample1D& r, FastRows* f) {
 namespace {
 
 constexpr int kVR = 4;        // output rows per thread in the vertical pass
-constexpr int kMaxTaps = 64;
+constexpr int kMaxTaps = 128;
 constexpr int kFR = 8;        // outputs per thread along the filtered axis in the uniform (fast) horizontal kernel
 constexpr int kFRV = 8;       // output rows per thread in the uniform vertical kernel (each input row is read (TP+14)/16 times)
 
@@ -780,7 +780,20 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
   // (3) border rows (all rows when nothing is uniform): general vertical pass ...
   if (ny_out - (vhi - vlo) > 0) {
     const int ngroups = (vlo + kVR - 1) / kVR + (ny_out - vhi + kVR - 1) / kVR;
-    if (valign) {
+    // the 4-row kernel keeps the weights of a row group over the group's common input range in shared memory
+    // (kVSpan rows): operators whose rows start far apart (strong down-scaling) take the scalar kernel instead
+    bool span_ok = (int)ry.start_host.size() == ny_out;
+    for (int g = 0; span_ok && g < ngroups; ++g) {
+      const int gA = (vlo + kVR - 1) / kVR;
+      int lo = 0x7fffffff, hi = 0;
+      for (int r = 0; r < kVR; ++r) {
+        const int oy = g < gA ? g * kVR + r : vhi + (g - gA) * kVR + r;
+        if ((g < gA && oy >= vlo) || oy >= ny_out) continue;
+        lo = std::min(lo, ry.start_host[oy]); hi = std::max(hi, ry.start_host[oy] + ry.taps);
+      }
+      if (hi - lo > kVSpan) span_ok = false;
+    }
+    if (valign && span_ok) {
       dim3 grid((ncols / 4 + 127) / 128, ngroups, 2 * nset);
       pyr_vertical_border4_kernel<<<grid, 128, 0, stream>>>(in0a, in0b, nset, in_stride, in_pitch, ncols / 4, ny_out, vlo, vhi,
                                                              ry.weights, ry.start, ry.taps, tmp, tmp_stride, ncols);

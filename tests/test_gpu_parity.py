@@ -640,6 +640,10 @@ def test_zoom_out_matches_oracle(nat, rubber_whale):
         assert rel_err(got, want) <= 1e-5
     gray = zm.zoom_out(img[:, :, :1], 0.5)
     assert rel_err(gray, orc.zoom_out(img[:, :, :1], 0.5)) <= 1e-5
+    # strong down-scaling: rows of the operator start 20 samples apart with ~100 taps each -- the border kernels' scalar variant
+    full = rubber_whale["rubber_whale"].astype(np.float64)
+    assert rel_err(zm.zoom_out(full, 0.05), orc.zoom_out(full, 0.05)) <= 1e-5
+    assert rel_err(zm.zoom_out(full, 0.08), orc.zoom_out(full, 0.08)) <= 1e-5
 
 
 def test_random_shapes_and_options_match_oracle(nat):

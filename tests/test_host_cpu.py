@@ -220,7 +220,7 @@ def test_zoom_out_operator_reproduces_scipy_chain():
     for f in (0.5, 0.6):
         ys, yw = zoom_out_operator(75, f)
         xs, xw = zoom_out_operator(98, f)
-        assert yw.shape[1] <= 64 and xw.shape[1] <= 64
+        assert yw.shape[1] <= 128 and xw.shape[1] <= 128
         ay = np.zeros((ys.size, 75)); ax = np.zeros((xs.size, 98))
         for o in range(ys.size): ay[o, ys[o]:ys[o] + yw.shape[1]] = yw[o]
         for o in range(xs.size): ax[o, xs[o]:xs[o] + xw.shape[1]] = xw[o]
