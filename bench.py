@@ -198,7 +198,7 @@ def run_ours(args, wl):
         I2 = I2.round_().clamp_(0, 255)
     plan = _native.Plan(batch=B, height=H, width=W, channels=C, nscales=ns, nu=NU, transform_type=types[0].value,
                         robust_type=robust.value, robust_loop=robust != RobustErrorFunctionType.QUADRATIC,
-                        lambda_=LAMBDA, tol=TOL, max_iter=30, delta=DELTA, nanifoutside=True, gray_as_rgb=(C == 1))
+                        lambda_=LAMBDA, tol=TOL, max_iter=30, delta=DELTA, nanifoutside=True, gray_as_rgb=(C == 1), blocks_per_pair=args.chunks)
     plan.set_transform_types([t.value for t in types])
     nx, ny = plan.level_shapes()
     p_dev = torch.zeros((B, 8), dtype=torch.float64, device=dev)
@@ -225,7 +225,7 @@ def run_ours(args, wl):
         sp = _native.Plan(batch=hi_ - lo_, height=H, width=W, channels=C, nscales=ns, nu=NU,
                           transform_type=types[0].value, robust_type=robust.value,
                           robust_loop=robust != RobustErrorFunctionType.QUADRATIC, lambda_=LAMBDA, tol=TOL, max_iter=30,
-                          delta=DELTA, nanifoutside=True, gray_as_rgb=(C == 1))
+                          delta=DELTA, nanifoutside=True, gray_as_rgb=(C == 1), blocks_per_pair=args.chunks)
         sp.set_transform_types([t.value for t in types[lo_:hi_]])
         subs.append(dict(plan=sp, stream=torch.cuda.Stream(device=dev), i1=I1[lo_:hi_], i2=I2[lo_:hi_], p=p_dev[lo_:hi_]))
 
@@ -301,7 +301,7 @@ def run_ours(args, wl):
         nb = hi_ - lo_
         hp = _native.Plan(batch=nb, height=H, width=W, channels=C, nscales=ns, nu=NU, transform_type=types[0].value,
                           robust_type=robust.value, robust_loop=robust != RobustErrorFunctionType.QUADRATIC,
-                          lambda_=LAMBDA, tol=TOL, max_iter=30, delta=DELTA, nanifoutside=True, gray_as_rgb=(C == 1))
+                          lambda_=LAMBDA, tol=TOL, max_iter=30, delta=DELTA, nanifoutside=True, gray_as_rgb=(C == 1), blocks_per_pair=args.chunks)
         hp.set_transform_types([t.value for t in types[lo_:hi_]])
         h1 = torch.empty((nb, H, W, C), dtype=host_dtype).pin_memory()
         h2 = torch.empty((nb, H, W, C), dtype=host_dtype).pin_memory()
@@ -420,6 +420,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="image pairs per step per GPU")
     ap.add_argument("--input-dtype", default="u8", choices=["u8", "f32"],
                     help="dtype of the host images on the e2e leg (values are identical on the device-resident leg)")
+    ap.add_argument("--chunks", type=int, default=0, help="partial-sum slots per pair (0 = library default: 256, or 1024 for very large images)")
     ap.add_argument("--streams", type=int, default=4, help="independent sub-batches (plan + CUDA stream each) per GPU")
     ap.add_argument("--e2e-plans", type=int, default=8, help="sub-batch plans (one host thread each) on the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
