@@ -27,6 +27,9 @@ GERMAN_MCCLURE / TRUNCATED_QUADRATIC error functions have no stored notebook out
 pinned by (c) only.  TRUNCATED_QUADRATIC crashes in the reference (``image_optimisation.py:40``
 applies ``if`` to an array); the element-wise reading used here is the evident intent and is
 pinned against the reference with that single line patched (see ``make_golden.py``).
+``bicubic_interpolation_image`` (the IPOL-style warp, secondary API) is pinned by outputs of the reference's own numba
+function (``oracle/make_golden_ipol.py`` -> ``tests/golden/ipol_warp.npz``).  ``zoom_out`` is PARITY UNPINNED: the
+reference's function is dead code that raises on current scipy, so its restatement follows the algorithm it states.
 
 Integer codes across the C-ABI equal the reference's Enum values:
 transform 1..5 = TRANSLATION, EUCLIDEAN, SIMILARITY, AFFINITY, HOMOGRAPHY (``transformation.py:8-13``),
