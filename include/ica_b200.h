@@ -82,6 +82,7 @@ ICA_API const char* ica_last_error(void);
 ICA_API int ica_version(void);
 ICA_API int ica_device_count(void);       /* 0 when no GPU is visible */
 ICA_API int ica_set_device(int device);
+ICA_API int ica_get_device(int* device_out);  /* the calling thread's current CUDA device */
 /* compile-time constants of the native code, for the constants.py parity test:
    out[0..4] = MAX_ITER, LAMBDA_0, LAMBDA_N, LAMBDA_RATIO, prefilter pad (12) */
 ICA_API int ica_get_constants(double* out5);

@@ -47,6 +47,7 @@ SIGNATURES = {
     "ica_version": (C.c_int, []),
     "ica_device_count": (C.c_int, []),
     "ica_set_device": (C.c_int, [C.c_int]),
+    "ica_get_device": (C.c_int, [_PI]),
     "ica_get_constants": (C.c_int, [_PD]),
     "ica_plan_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
     "ica_plan_destroy": (C.c_int, [_P]),
@@ -106,7 +107,9 @@ def lib():
         if _lib is not None:
             return _lib
         path = _build.LIB_PATH
-        if not os.path.exists(path):
+        # rebuild when missing, or when a source is newer than the library and a compiler is at hand (on a box
+        # without nvcc the shipped library is used as it is)
+        if not os.path.exists(path) or (_build.is_stale() and _build.have_nvcc()):
             try:
                 path = _build.build()
             except Exception as exc:  # noqa: BLE001
@@ -141,6 +144,12 @@ def device_count() -> int:
 
 def set_device(index: int) -> None:
     check(lib().ica_set_device(int(index)))
+
+
+def current_device() -> int:
+    d = C.c_int32(-1)
+    check(lib().ica_get_device(C.byref(d)))
+    return d.value
 
 
 def require_gpu() -> None:

@@ -28,17 +28,41 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libica_b200.so (there is no CPU fallback)")
 
 
+def have_nvcc() -> bool:
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
 def _deps():
-    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     files.append(os.path.join(ROOT, "include", "ica_b200.h"))
     return files
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def _source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(_deps()):
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    """True when the library is missing or was built from other sources (content hash, not mtimes: the snapshot that
+    travels to the GPU box does not keep them)."""
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(f) > t for f in _deps())
+    with open(HASH_PATH) as fh:
+        return fh.read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -68,6 +92,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, LIB_PATH)
+    with open(HASH_PATH, "w") as fh:
+        fh.write(_source_hash())
     return LIB_PATH
 
 

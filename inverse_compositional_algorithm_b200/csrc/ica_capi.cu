@@ -41,6 +41,7 @@ using namespace ica;
 struct ica_plan {
   ica_config cfg;
   int B, H, W, C, nscales, dh;
+  int device = 0;                    // the CUDA device the plan's buffers, stream and graph live on
   int max_chunks = 0, grid = 0;
   int shard_rank = 0, shard_n = 1;   // row-sharded mode (ica_plan_set_row_shard)
   int* chunk_start = nullptr;
@@ -171,6 +172,14 @@ int require_device() {
               e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     return ICA_ERR_NO_DEVICE;
   }
+  return ICA_OK;
+}
+
+// a plan belongs to the device that was current when it was created: make it current for the calling thread
+int enter_plan_device(const ica_plan* pl) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur == pl->device) return ICA_OK;
+  ICA_CUDA_CHECK(cudaSetDevice(pl->device));
   return ICA_OK;
 }
 
@@ -391,6 +400,13 @@ int ica_set_device(int device) {
   return ICA_OK;
 }
 
+int ica_get_device(int* device_out) {
+  if (!device_out) return ICA_ERR_INVALID;
+  if (int rc = require_device()) return rc;
+  ICA_CUDA_CHECK(cudaGetDevice(device_out));
+  return ICA_OK;
+}
+
 int ica_get_constants(double* out5) {
   if (!out5) return ICA_ERR_INVALID;
   out5[0] = kMaxIter; out5[1] = kLambda0; out5[2] = kLambdaN; out5[3] = kLambdaRatio; out5[4] = kSplinePad;
@@ -457,6 +473,7 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
+    pl->device = dev;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     pl->grid = iterate_blocks_per_sm() * sms;   // persistent kernel: every CTA resident
   }
@@ -615,6 +632,7 @@ int ica_plan_set_row_shard(ica_plan* pl, int32_t rank, int32_t nranks) {
 
 int ica_plan_shard_begin(ica_plan* pl, const float* I1, const float* I2, const double* p_in, void* stream_) {
   if (!pl || !I1 || !I2 || !p_in) { set_error("NULL argument"); return ICA_ERR_INVALID; }
+  if (int rc = enter_plan_device(pl)) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
   pl->launches = 0; pl->n_ev_iter = 0; pl->n_ev_pyr = 0;
   pl->last_I1 = I1; pl->last_I2 = I2;
@@ -673,6 +691,7 @@ int ica_plan_shard_finish(ica_plan* pl, double* p_out, void* stream_) {
 int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* p_inout, void* stream_) {
   if (!pl || !I1 || !I2 || !p_inout) { set_error("NULL argument"); return ICA_ERR_INVALID; }
   if (pl->shard_n != 1) { set_error("the plan is row-sharded: use ica_plan_shard_begin/partial/solve/finish"); return ICA_ERR_INVALID; }
+  if (int rc = enter_plan_device(pl)) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
   pl->launches = 0;
   pl->n_ev_iter = 0; pl->n_ev_pyr = 0;
@@ -728,7 +747,9 @@ int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* 
 // PCIe link: while one plan's kernels run, the next plan's inputs are copied, instead of all copies sharing the link
 // and every plan starting late.  (Ordering the copies on the device with a chained event instead of this host-side
 // hand-over was measured slower.)
-static std::mutex g_h2d_mutex;
+static std::mutex g_h2d_mutex[64];   // one per device: copies to different GPUs do not wait for one another
+
+
 
 // The host entry waits on events by polling with a yield in between: a lone caller sees the event as fast as a spinning
 // cudaEventSynchronize would, while many concurrent callers (several plans per GPU, several ranks per host) give their
@@ -786,6 +807,7 @@ int ica_plan_run_host(ica_plan* pl, const void* I1_host, const void* I2_host, in
   if ((DI_out || Iw_out) && !(pl->cfg.flags & ICA_FLAG_WRITE_DI_IW)) {
     set_error("DI/Iw requested but the plan was created without ICA_FLAG_WRITE_DI_IW"); return ICA_ERR_INVALID;
   }
+  if (int rc = enter_plan_device(pl)) return rc;
   cudaStream_t stream = pl->stream;
   const size_t nimg = (size_t)pl->B * pl->in_stride;
   if (!pl->in1_dev) {
@@ -793,7 +815,7 @@ int ica_plan_run_host(ica_plan* pl, const void* I1_host, const void* I2_host, in
     if (int rc = dev_alloc(pl, &pl->in2_dev, nimg)) return rc;
   }
   {
-    std::lock_guard<std::mutex> lock(g_h2d_mutex);
+    std::lock_guard<std::mutex> lock(g_h2d_mutex[pl->device & 63]);
     ICA_CUDA_CHECK(cudaEventRecord(pl->ev_host0, stream));
     ICA_CUDA_CHECK(cudaMemcpyAsync(pl->p_dev, p_inout_host, (size_t)pl->B * ICA_MAX_PARAMS * sizeof(double),
                                    cudaMemcpyHostToDevice, stream));

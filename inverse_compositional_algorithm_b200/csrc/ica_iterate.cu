@@ -29,6 +29,7 @@
 //     partials go to fixed slots; ica_solve_kernel sums them in a fixed order (deterministic, batch-invariant).
 // Bound named by the north star: HBM (read I1 once + I2 once per pixel-iteration = 2*C*4 bytes); measured: DRAM
 // traffic = 1.01x that, the kernel is limited by instruction issue and shared-memory wavefronts.  No tensor cores.
+#include <atomic>
 #include "ica_device.cuh"
 #include "ica_transform.cuh"
 #include "ica_iterate.cuh"
@@ -114,6 +115,9 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0,
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void fence_tensormap_acquire(const void* tmap) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(tmap) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define ICA_STAMP(slot) do { if (P.dbg_time && it == 0 && tid == 0) P.dbg_time[blockIdx.x * 16 + (slot)] = gtime(); } while (0)
@@ -193,6 +197,9 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stages
     // tensor maps of this pair's level: [pair][scale][0 = I1 (zero fill), 1 = I2 (NaN fill)], 128 bytes each
     const char* tm1 = static_cast<const char*>(P.tmaps) + ((long long)(pair * P.nscales + s) * 2) * 128;
     const char* tm2 = tm1 + 128;
+    // the maps live in global memory and are rewritten (cudaMemcpyAsync) when the level-0 images move or a new plan
+    // reuses the allocation: acquire them through the tensormap proxy before the first copy that uses them
+    if (lane == 0) { fence_tensormap_acquire(tm1); fence_tensormap_acquire(tm2); }
     int t_first;
     const int ntiles = band_tiles(L, P.shard_rank, P.shard_n, &t_first);
     const int nch = ntiles < P.max_chunks ? ntiles : P.max_chunks;
@@ -999,11 +1006,15 @@ template <int C, int DH>
 cudaError_t launch_iterate_t(const IterParams& P, int grid, cudaStream_t stream) {
   constexpr size_t smem = Stage<C>::kStages * (size_t)Stage<C>::kFloats * sizeof(float) +
                           2 * (size_t)kConsumerWarps * RowVals<DH>::K * kYPow * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
+  // the attribute belongs to the (device, function) pair: configure once per device
+  static std::atomic<unsigned long long> configured{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(configured.load(std::memory_order_acquire) & bit)) {
     cudaError_t e = cudaFuncSetAttribute(ica_iterate_kernel<C, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.fetch_or(bit, std::memory_order_release);
   }
   ica_iterate_kernel<C, DH><<<grid, kThreads, smem, stream>>>(P);
   return cudaGetLastError();

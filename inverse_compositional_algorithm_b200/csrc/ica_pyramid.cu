@@ -53,7 +53,8 @@ void build_resample_1d(int n_in, int n_out, Resample1D* out, double rel_threshol
     ew[4 * o + 3] = t * t * t / 6.0;
   }
   // banded storage around the centre of each output row
-  const int RB = 48;
+  // half-width kept around each output's centre: the Gaussian radius plus the prefilter tails (|z|^k < 1e-9 at k = 16)
+  const int RB = std::max(48, radius + 24);
   const int BWD = 2 * RB + 1;
   std::vector<double> band((size_t)n_out * BWD, 0.0);
   std::vector<int> bstart(n_out);

@@ -29,6 +29,8 @@ _LOCK = threading.RLock()
 
 
 def _get_plan(**key):
+    # plans, their streams and graphs belong to one CUDA device: the calling thread's current device is part of the key
+    key.setdefault("device", _native.current_device())
     k = tuple(sorted(key.items()))
     with _LOCK:
         return _get_plan_locked(k, key)
@@ -196,8 +198,11 @@ def register_batch_device(I1, I2, transform_type, nscales=1, nu=0.5, TOL=1e-3,
     current stream, with no host round trip until the small result arrays are fetched).
     Returns ``(p [B, 8] float64 CUDA tensor, error [B], iters [B, nscales])``."""
     import torch
-    if not (isinstance(I1, torch.Tensor) and I1.is_cuda and I1.dtype == torch.float32 and I1.dim() == 4):
-        raise ValueError("I1 and I2 must be float32 CUDA tensors [B, H, W, C]")
+    for I in (I1, I2):
+        if not (isinstance(I, torch.Tensor) and I.is_cuda and I.dtype == torch.float32 and I.dim() == 4):
+            raise ValueError("I1 and I2 must be float32 CUDA tensors [B, H, W, C]")
+    if I2.device != I1.device:
+        raise ValueError("I1 and I2 must live on the same CUDA device")
     if I1.shape[3] not in (1, 3):
         raise ValueError("I1 and I2 must be [B, H, W, C] with C in (1, 3)")
     _check_common(I1, I2, TOL)

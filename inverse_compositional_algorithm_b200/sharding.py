@@ -85,8 +85,11 @@ def register_row_sharded(I1, I2, transform_type, *, nscales=5, nu=0.5, robust_ty
     from . import _native
     from .image_optimisation import RobustErrorFunctionType
 
-    if I1.dim() != 3 or I1.shape != I2.shape or I1.dtype != torch.float32 or not I1.is_cuda:
-        raise ValueError("I1 and I2 must be float32 CUDA tensors of the same [H, W, C] shape")
+    for I in (I1, I2):
+        if not (isinstance(I, torch.Tensor) and I.is_cuda and I.dtype == torch.float32 and I.dim() == 3):
+            raise ValueError("I1 and I2 must be float32 CUDA tensors of the same [H, W, C] shape")
+    if I1.shape != I2.shape or I1.device != I2.device:
+        raise ValueError("I1 and I2 must be float32 CUDA tensors of the same [H, W, C] shape on one device")
     I1, I2 = I1.contiguous(), I2.contiguous()
     H, W, Cn = (int(v) for v in I1.shape)
     rt = RobustErrorFunctionType(getattr(robust_type, "value", robust_type)).value
