@@ -184,6 +184,15 @@ ICA_API int ica_rescale_host(const float* image, int32_t height, int32_t width, 
    weights_out needs n_out * 64 floats at most; fast_range_out[3] = {lo, hi, s0} of the uniform rows. */
 ICA_API int ica_resample_operator(int32_t n_in, int32_t n_out, int32_t* taps_out, int32_t* start_out,
                                   float* weights_out, int32_t weights_capacity, int32_t* fast_range_out);
+/* zoom.zoom_out (src/zoom.py:29-60, the IPOL-style level: Gaussian sigma = 0.6 sqrt(1/f^2 - 1) with scipy's reflect
+   extension, then cubic-spline map_coordinates(mode='nearest') at o / f).  The reference's function is dead code that
+   raises on current scipy, so parity is UNPINNED (oracle restates the algorithm it spells out).
+   ica_zoom_out_operator: the 1-D banded operator (host only, no device); ica_zoom_out_host: one image, float32
+   [H][W][C] -> [round(H f)][round(W f)][C]. */
+ICA_API int ica_zoom_out_operator(int32_t n_in, double factor, int32_t* n_out, int32_t* taps_out, int32_t* start_out,
+                                  float* weights_out, int32_t weights_capacity);
+ICA_API int ica_zoom_out_host(const float* image, int32_t height, int32_t width, int32_t channels, double factor,
+                              float* out, int32_t* out_h, int32_t* out_w);
 /* zoom.zoom_size (src/zoom.py:8-22), round-half-to-even */
 ICA_API int ica_zoom_size(int32_t nx, int32_t ny, double factor, int32_t* nxx, int32_t* nyy);
 /* Gradient of I1 + frame (ica.py:81-93): Ix, Iy float32 [H][W][C]; NaN on the frame */

@@ -20,6 +20,7 @@ TRAJ_STRIDE = 12
 
 FLAG_RECORD_TRAJECTORY = 1
 FLAG_WRITE_DI_IW = 2
+FLAG_HOST_LOOP = 8
 
 DTYPE_F32, DTYPE_U8, DTYPE_F64 = 0, 1, 2
 
@@ -84,6 +85,8 @@ SIGNATURES = {
     "ica_rescale_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _PI, _PI]),
     "ica_resample_operator": (C.c_int, [C.c_int32, C.c_int32, _PI, _PI, _P, C.c_int32, _PI]),
     "ica_zoom_size": (C.c_int, [C.c_int32, C.c_int32, C.c_double, _PI, _PI]),
+    "ica_zoom_out_operator": (C.c_int, [C.c_int32, C.c_double, _PI, _PI, _PI, _P, C.c_int32]),
+    "ica_zoom_out_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _PI, _PI]),
     "ica_gradient_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "ica_hessian_b_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P,
                                      C.c_int32, C.c_double, C.c_int32, C.c_int32, _P, _P]),
@@ -208,7 +211,8 @@ def resample_operator(n_in: int, n_out: int):
     """Dense (n_out x n_in) matrix of the banded pyramid operator along one axis, plus the uniform range."""
     taps = C.c_int32()
     start = np.zeros(n_out, dtype=np.int32)
-    w = np.zeros(n_out * 64, dtype=np.float32)
+    check(lib().ica_resample_operator(int(n_in), int(n_out), C.byref(taps), None, None, 0, None))   # band width first
+    w = np.zeros(n_out * taps.value, dtype=np.float32)
     fast = np.zeros(3, dtype=np.int32)
     check(lib().ica_resample_operator(int(n_in), int(n_out), C.byref(taps), start.ctypes.data_as(_PI), _ptr(w), w.size,
                                       fast.ctypes.data_as(_PI)))
@@ -216,6 +220,29 @@ def resample_operator(n_in: int, n_out: int):
     for o in range(n_out):
         A[o, start[o]:start[o] + taps.value] = w[o * taps.value:(o + 1) * taps.value]
     return A, taps.value, fast
+
+
+def zoom_out_operator(n_in: int, factor: float):
+    """``(start [n_out] int32, weights [n_out, taps] float32)`` of the zoom_out operator along one axis (built in C++)."""
+    n_out, taps = C.c_int32(), C.c_int32()
+    check(lib().ica_zoom_out_operator(int(n_in), float(factor), C.byref(n_out), C.byref(taps), None, None, 0))
+    start = np.zeros(n_out.value, dtype=np.int32)
+    w = np.zeros(n_out.value * taps.value, dtype=np.float32)
+    check(lib().ica_zoom_out_operator(int(n_in), float(factor), C.byref(n_out), C.byref(taps), start.ctypes.data_as(_PI),
+                                      _ptr(w), w.size))
+    return start, w.reshape(n_out.value, taps.value)
+
+
+def zoom_out(image, factor: float) -> np.ndarray:
+    require_gpu()
+    img = _as_image_f32(image)
+    nxx, nyy = zoom_size(img.shape[1], img.shape[0], factor)
+    out = np.empty((max(nyy, 1), max(nxx, 1), img.shape[2]), dtype=np.float32)
+    oh, ow = C.c_int32(), C.c_int32()
+    check(lib().ica_zoom_out_host(_ptr(img), img.shape[0], img.shape[1], img.shape[2], float(factor), _ptr(out),
+                                  C.byref(oh), C.byref(ow)))
+    assert (oh.value, ow.value) == out.shape[:2]
+    return out
 
 
 def inverse_hessian(H: np.ndarray) -> np.ndarray:
@@ -378,10 +405,10 @@ class Plan:
 
     def __init__(self, *, batch, height, width, channels, nscales, nu, transform_type, robust_type,
                  robust_loop, lambda_, tol, max_iter, delta, nanifoutside, gray_as_rgb=False,
-                 record_trajectory=False, write_di_iw=False, blocks_per_pair=0):
+                 record_trajectory=False, write_di_iw=False, blocks_per_pair=0, host_loop=False):
         require_gpu()
         flags = (FLAG_RECORD_TRAJECTORY if record_trajectory else 0) | (
-            FLAG_WRITE_DI_IW if write_di_iw else 0)
+            FLAG_WRITE_DI_IW if write_di_iw else 0) | (FLAG_HOST_LOOP if host_loop else 0)
         self.cfg = Config(batch=batch, height=height, width=width, channels=channels,
                           gray_as_rgb=1 if gray_as_rgb else 0, nscales=nscales, nu=nu,
                           transform_type=int(transform_type), robust_type=int(robust_type),

@@ -929,6 +929,43 @@ int ica_resample_operator(int32_t n_in, int32_t n_out, int32_t* taps_out, int32_
   return ICA_OK;
 }
 
+// The banded operator of zoom.zoom_out (src/zoom.py:29-60) along one axis of length n_in, built on the host in fp64
+// (no device needed); same output convention as ica_resample_operator.
+int ica_zoom_out_operator(int32_t n_in, double factor, int32_t* n_out, int32_t* taps_out, int32_t* start_out,
+                          float* weights_out, int32_t weights_capacity) {
+  if (n_in < 1 || !(factor > 0.0 && factor < 1.0) || !taps_out || !n_out) { set_error("bad argument"); return ICA_ERR_INVALID; }
+  Resample1D r;
+  build_zoom_out_1d(n_in, factor, 0.6 /* constants.ZOOM_SIGMA_ZERO */, &r);
+  *taps_out = r.taps; *n_out = r.n_out;
+  if (start_out) for (int o = 0; o < r.n_out; ++o) start_out[o] = r.start[o];
+  if (weights_out) {
+    if ((long long)weights_capacity < (long long)r.n_out * r.taps) { set_error("weights buffer too small"); return ICA_ERR_INVALID; }
+    for (size_t i = 0; i < r.weights.size(); ++i) weights_out[i] = r.weights[i];
+  }
+  return ICA_OK;
+}
+
+int ica_apply_operators_host(const float* image, int32_t height, int32_t width, int32_t channels,
+                             const int32_t* ystart, const float* yweights, int32_t ytaps, int32_t ny_out,
+                             const int32_t* xstart, const float* xweights, int32_t xtaps, int32_t nx_out,
+                             int32_t clip_to_input_range, float* out);
+
+// zoom.zoom_out (src/zoom.py:29-60) of one float32 image [H][W][C]: both operators built here (C++), applied by the
+// pyramid kernels; out is [round(H f)][round(W f)][C], no clipping (the reference function does not clip).
+int ica_zoom_out_host(const float* image, int32_t height, int32_t width, int32_t channels, double factor, float* out,
+                      int32_t* out_h, int32_t* out_w) {
+  if (!image || !out || height < 1 || width < 1 || (channels != 1 && channels != 3) || !(factor > 0.0 && factor < 1.0)) {
+    set_error("bad argument"); return ICA_ERR_INVALID;
+  }
+  Resample1D ry, rx;
+  build_zoom_out_1d(height, factor, 0.6, &ry);
+  build_zoom_out_1d(width, factor, 0.6, &rx);
+  if (out_h) *out_h = ry.n_out;
+  if (out_w) *out_w = rx.n_out;
+  return ica_apply_operators_host(image, height, width, channels, ry.start.data(), ry.weights.data(), ry.taps, ry.n_out,
+                                  rx.start.data(), rx.weights.data(), rx.taps, rx.n_out, 0, out);
+}
+
 // out = A_y * image * A_x^T for caller-supplied banded operators (rows of `taps` weights starting at start[o]); the
 // two-pass / fused kernels of the pyramid do the work.  Used by the Python mirror of zoom.zoom_out.
 int ica_apply_operators_host(const float* image, int32_t height, int32_t width, int32_t channels,

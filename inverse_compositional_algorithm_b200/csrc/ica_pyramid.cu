@@ -122,6 +122,104 @@ void build_resample_1d(int n_in, int n_out, Resample1D* out, double rel_threshol
   }
 }
 
+// The IPOL-style level of the reference's zoom.zoom_out (src/zoom.py:29-60; dead code there, PARITY UNPINNED) along one
+// axis, as a banded operator built exactly in fp64 like build_resample_1d:
+//   scipy.ndimage.gaussian_filter(sigma = sigma_zero * sqrt(1/factor^2 - 1)): defaults mode='reflect', truncate 4
+//   scipy.ndimage.map_coordinates(order=3, mode='nearest') at o / factor: pad 12 samples with the edge value,
+//   cubic-B-spline prefilter with scipy's 'reflect' initialisation (ni_splines.c, the one it uses for mode nearest),
+//   B-spline evaluation at floor(x)-1 .. floor(x)+2, indices clamped to the padded line.
+void build_zoom_out_1d(int n_in, double factor, double sigma_zero, Resample1D* out, double rel_threshold) {
+  const int n_out = std::max(round_half_even((double)n_in * factor), 1);
+  const double sigma = sigma_zero * sqrt(std::max(0.0, 1.0 / (factor * factor) - 1.0));
+  std::vector<double> gk;
+  int radius = 0;
+  if (sigma > 1e-15) {
+    radius = (int)(4.0 * sigma + 0.5);
+    gk.resize(2 * radius + 1);
+    double sum = 0.0;
+    for (int i = -radius; i <= radius; ++i) { gk[i + radius] = exp(-0.5 / (sigma * sigma) * i * i); sum += gk[i + radius]; }
+    for (auto& w : gk) w /= sum;
+  }
+  const int N = n_in + 2 * kSplinePad;
+  const double z = sqrt(3.0) - 2.0;
+  auto reflect = [n_in](int i) {   // scipy 'reflect': (d c b a | a b c d | d c b a)
+    const int period = 2 * n_in;
+    i %= period; if (i < 0) i += period;
+    return i < n_in ? i : period - 1 - i;
+  };
+  // banded storage around each output's centre (Gaussian radius + prefilter tails, |z|^k < 1e-9 at k = 16)
+  const int RB = radius + 24;
+  const int BWD = 2 * RB + 1;
+  std::vector<double> band((size_t)n_out * BWD, 0.0);
+  std::vector<int> bstart(n_out);
+  for (int o = 0; o < n_out; ++o) bstart[o] = (int)floor((double)o / factor) - RB;
+  std::vector<double> g(n_in), c(N);
+  for (int j = 0; j < n_in; ++j) {
+    // Gaussian response of the impulse at j with reflect extension: g[i] = sum_k gk[k] * [reflect(i + k) == j]
+    std::fill(g.begin(), g.end(), 0.0);
+    if (radius > 0) {
+      for (int i = std::max(0, j - radius); i <= std::min(n_in - 1, j + radius); ++i) {
+        double v = 0.0;
+        for (int k = -radius; k <= radius; ++k) if (reflect(i + k) == j) v += gk[k + radius];
+        g[i] = v;
+      }
+    } else {
+      g[j] = 1.0;
+    }
+    for (int i = 0; i < N; ++i) c[i] = 6.0 * g[std::min(std::max(i - kSplinePad, 0), n_in - 1)];   // edge padding, gain
+    {  // _init_causal_reflect
+      const double c0 = c[0];
+      const double zn = pow(z, (double)N);
+      double zi = z;
+      double acc = c[0] + zn * c[N - 1];
+      for (int i = 1; i < N; ++i) { acc += zi * (c[i] + zn * c[N - 1 - i]); zi *= z; }
+      c[0] = acc * z / (1.0 - zn * zn) + c0;
+    }
+    for (int i = 1; i < N; ++i) c[i] += z * c[i - 1];
+    c[N - 1] *= z / (z - 1.0);   // _init_anticausal_reflect
+    for (int i = N - 2; i >= 0; --i) c[i] = z * (c[i + 1] - c[i]);
+    const int olo = std::max(0, (int)floor((j - RB - 2) * factor) - 1);
+    const int ohi = std::min(n_out - 1, (int)ceil((j + RB + 2) * factor) + 1);
+    for (int o = olo; o <= ohi; ++o) {
+      const int col = j - bstart[o];
+      if (col < 0 || col >= BWD) continue;
+      const double x = (double)o / factor + kSplinePad;
+      const double fl = floor(x);
+      const double t = x - fl;
+      const double w[4] = {(1 - t) * (1 - t) * (1 - t) / 6.0, (3 * t * t * t - 6 * t * t + 4) / 6.0,
+                           (-3 * t * t * t + 3 * t * t + 3 * t + 1) / 6.0, t * t * t / 6.0};
+      double sacc = 0.0;
+      for (int k = 0; k < 4; ++k) sacc += w[k] * c[std::min(std::max((int)fl - 1 + k, 0), N - 1)];
+      band[(size_t)o * BWD + col] = sacc;
+    }
+  }
+  double mx = 0.0;
+  for (double v : band) mx = std::max(mx, fabs(v));
+  const double thr = rel_threshold * mx;
+  std::vector<int> first(n_out), last(n_out);
+  int taps = 1;
+  for (int o = 0; o < n_out; ++o) {
+    int fi = BWD, la = -1;
+    for (int k = 0; k < BWD; ++k) if (fabs(band[(size_t)o * BWD + k]) > thr) { fi = std::min(fi, k); la = std::max(la, k); }
+    if (la < 0) { fi = RB; la = RB; }
+    first[o] = bstart[o] + fi; last[o] = bstart[o] + la;
+    taps = std::max(taps, la - fi + 1);
+  }
+  taps = std::min(taps, n_in);
+  out->n_in = n_in; out->n_out = n_out; out->taps = taps;
+  out->start.resize(n_out);
+  out->weights.assign((size_t)n_out * taps, 0.f);
+  for (int o = 0; o < n_out; ++o) {
+    int st = first[o] - (taps - (last[o] - first[o] + 1)) / 2;
+    st = std::max(0, std::min(st, n_in - taps));
+    out->start[o] = st;
+    for (int k = 0; k < taps; ++k) {
+      const int col = st + k - bstart[o];
+      out->weights[(size_t)o * taps + k] = (col >= 0 && col < BWD) ? (float)band[(size_t)o * BWD + col] : 0.f;
+    }
+  }
+}
+
 // Rows of a banded operator whose weights are identical up to a shift of 2 samples per output
 // (exact 2:1 levels away from the borders): start[o] = 2*o + s0 and the same `taps` weights.
 void detect_uniform_rows(const Resample1D& r, FastRows* f) {

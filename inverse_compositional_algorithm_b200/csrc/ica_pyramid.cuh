@@ -29,6 +29,8 @@ struct DeviceResample {
 int round_half_even(double v);
 int zoomed_size(int n, double factor);   // src/zoom.py:8-22
 void build_resample_1d(int n_in, int n_out, Resample1D* out, double rel_threshold = 1e-9);
+// zoom.zoom_out (src/zoom.py:29-60) along one axis: Gaussian (reflect) + cubic-spline resampling at o / factor (nearest)
+void build_zoom_out_1d(int n_in, double factor, double sigma_zero, Resample1D* out, double rel_threshold = 1e-9);
 void detect_uniform_rows(const Resample1D& r, FastRows* f);
 int max_taps();
 

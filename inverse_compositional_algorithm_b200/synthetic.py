@@ -144,3 +144,17 @@ def make_batch_torch(batch: int, height: int, width: int, channels: int, transfo
         I1[b0:b0 + nb] = w1.permute(0, 2, 3, 1)
         I2[b0:b0 + nb] = tex[:, :, margin:margin + height, margin:margin + width].permute(0, 2, 3, 1)
     return I1.contiguous(), I2.contiguous(), p_all
+
+
+def make_large_gray_pair(seed: int, height: int, width: int, shift=(3, -2), noise_sigma: float = 1.0):
+    """Cheap deterministic pair for very large single images (BASELINE config 5, 8192 x 8192 gray): an 8-bit smooth
+    random texture ``I2`` and ``I1 = I2`` moved by an integer ``shift`` (rows, columns) plus noise, so that
+    ``I1(x, y) ~ I2(x - shift[1], y - shift[0])``.  Returns float32 ``(H, W, 1)`` images holding 8-bit values."""
+    rng = np.random.default_rng(SEED0 + int(seed))
+    tex = rng.standard_normal((height, width), dtype=np.float32)
+    tex = ndi.gaussian_filter(tex, sigma=2.0, mode="wrap")
+    lo, hi = float(tex.min()), float(tex.max())
+    i2 = np.round((tex - lo) * (255.0 / (hi - lo))).astype(np.float32)
+    i1 = np.roll(i2, shift, axis=(0, 1)) + noise_sigma * rng.standard_normal((height, width), dtype=np.float32)
+    i1 = np.clip(np.round(i1), 0.0, 255.0).astype(np.float32)
+    return i1[:, :, None], i2[:, :, None]

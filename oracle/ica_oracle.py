@@ -462,6 +462,89 @@ def ica_pyramidal(I1, I2, p, ttype, nscales, nu, TOL, rtype, lambda_, nanifoutsi
     return ps[0], error, DI, Iw
 
 
+# ------------------------------------------------- one iteration on a very large image
+def hessian_b_rowblocked(I1, I2, p, ttype, rtype, lam, nanifoutside, delta, channel_mult=1.0, rows=96):
+    """H and b of ONE iteration of the robust loop (inverse_compositional_algorithm.py:227-246) for images too
+    large to materialise ``J`` / ``DIJ`` (12.9 GB + 8.6 GB at 8192^2): the same float64 arithmetic as
+    :func:`warp_bicubic`, :func:`gradient_with_frame`, :func:`jacobian`, :func:`steepest_descent_images`,
+    :func:`robust_error_function`, :func:`hessian_robust` and :func:`independent_vector_robust`, evaluated on
+    blocks of ``rows`` image rows and summed.  ``I1``/``I2`` are ``(ny, nx, nz)`` (any float dtype, converted per
+    block); ``channel_mult = 3`` makes a one-channel image stand for its RGB replication (the
+    channel sums t2, H and b triple).  Returns ``(H, b)``."""
+    ny, nx, nz = I1.shape
+    n = nparams(ttype)
+    m = np.eye(3) if all(abs(v) < 1e-10 for v in p) else params2matrix(p, ttype)
+    lo, hi = float(np.min(I2)), float(np.max(I2))          # skimage clip range (SURVEY Q1)
+    frame = nanifoutside is True and delta > 0
+    H = np.zeros((n, n))
+    b = np.zeros(n)
+    jj = np.arange(nx, dtype=np.float64)[None, :]
+    for r0 in range(0, ny, rows):
+        r1 = min(ny, r0 + rows)
+        ii = np.arange(r0, r1, dtype=np.float64)[:, None]
+        # skimage _transform_projective, same operation order as skimage_restated.project_grid
+        xx = m[0, 0] * jj + m[0, 1] * ii + m[0, 2]
+        yy = m[1, 0] * jj + m[1, 1] * ii + m[1, 2]
+        zz = m[2, 0] * jj + m[2, 1] * ii + m[2, 2]
+        c, r = xx / zz, yy / zz
+        rf, cf = np.floor(r), np.floor(c)
+        xr, xc = r - rf, c - cf
+        ri, ci = rf.astype(np.int64), cf.astype(np.int64)
+        # rows of I1 with one row of halo for the central differences
+        a0, a1 = max(r0 - 1, 0), min(r1 + 1, ny)
+        I1b = np.asarray(I1[a0:a1], dtype=np.float64)
+        cur = I1b[r0 - a0:r0 - a0 + (r1 - r0)]
+        Ix = np.zeros_like(cur)
+        Iy = np.zeros_like(cur)
+        Ix[:, 1:-1] = 0.5 * (cur[:, 2:] - cur[:, :-2])
+        for k, y in enumerate(range(r0, r1)):
+            if 1 <= y <= ny - 2:
+                Iy[k] = 0.5 * (I1b[y + 1 - a0] - I1b[y - 1 - a0])
+        if frame:
+            ys = np.arange(r0, r1)
+            bad_rows = (ys < delta) | (ys >= ny - delta)
+            Ix[bad_rows] = np.nan
+            Iy[bad_rows] = np.nan
+            for g in (Ix, Iy):
+                g[:, :delta] = np.nan
+                g[:, -delta:] = np.nan
+        DI = np.empty_like(cur)
+        for ch in range(nz):
+            plane = I2[:, :, ch]
+            fr = []
+            for a in range(4):
+                f = [np.asarray(sk._taps(plane, ri - 1 + a, ci - 1 + bb, np.nan), dtype=np.float64) for bb in range(4)]
+                fr.append(sk._keys_cubic(xc, *f))
+            iw = sk._keys_cubic(xr, *fr)
+            np.clip(iw, lo, hi, out=iw)
+            DI[:, :, ch] = iw - cur[:, :, ch]
+        d0 = _zero_nonfinite(DI)
+        t2 = channel_mult * np.einsum("ijc,ijc->ij", d0, d0)
+        rho = np.where(np.isfinite(t2), rhop(t2, lam, rtype), 0.0)
+        J = jacobian_rows(ttype, nx, r0, r1)
+        D = _zero_nonfinite(steepest_descent_images(Ix, Iy, J, n))
+        H += channel_mult * np.einsum("ij,ijck,ijcm->km", rho, D, D, optimize=True)
+        b += channel_mult * np.einsum("ij,ijck,ijc->k", rho, D, d0, optimize=True)
+    return H, b
+
+
+def jacobian_rows(ttype, nx, r0, r1):
+    """:func:`jacobian` restricted to image rows ``[r0, r1)``."""
+    n = nparams(ttype)
+    J = np.zeros((r1 - r0, nx, 2 * n))
+    y, x = np.mgrid[r0:r1, 0:nx]
+    cols = {
+        TRANSLATION: {0: 1.0, 3: 1.0},
+        EUCLIDEAN: {0: 1.0, 2: -y, 4: 1.0, 5: x},
+        SIMILARITY: {0: 1.0, 2: x, 3: -y, 5: 1.0, 6: y, 7: x},
+        AFFINITY: {0: 1.0, 2: x, 3: y, 7: 1.0, 10: x, 11: y},
+        HOMOGRAPHY: {0: x, 1: y, 2: 1.0, 6: -x * x, 7: -x * y, 11: x, 12: y, 13: 1.0, 14: -x * y, 15: -y * y},
+    }[ttype]
+    for k, v in cols.items():
+        J[..., k] = v
+    return J
+
+
 # ------------------------------------------------------------------- accuracy metric
 def end_point_error(pa, pb, ttype, nx, ny):
     """mean and max over the image domain of ||x'(x;pa) - x'(x;pb)||."""

@@ -14,6 +14,11 @@ pytestmark = pytest.mark.gpu
 
 REL_1E5 = 1e-5
 EPE_TOL = 1e-3
+# per-iteration |dp| against the float64 oracle / reference: relative, plus an absolute floor for the last iterations
+# of a scale, whose |dp| (~1e-4) is the difference of nearly equal numbers
+DP_RTOL, DP_ATOL = 1e-4, 2e-7
+HB8192_DP_RTOL = 1e-3      # one solve of an ill-conditioned 8 x 8 system; the loop itself is self-correcting
+NOTEBOOK_ERR_RTOL = 2e-3   # the notebooks' stored |Dp| lines (was 0.05 in round 1)
 
 
 @pytest.fixture(scope="module")
@@ -183,6 +188,8 @@ def test_trajectory_matches_oracle(nat, reference_runs, idx):
         assert _epe(row[4:4 + n], w[3:3 + n], t.value, int(nx[s]), int(ny[s])) <= EPE_TOL
         if not np.isnan(w[2]):
             np.testing.assert_allclose(row[3], w[2], rtol=1e-12)  # lambda schedule
+    # per-iteration |dp| (float32 images on the device, float64 in the reference: the budget is their rounding)
+    np.testing.assert_allclose(traj[:, 2], want[:, 1], rtol=DP_RTOL, atol=DP_ATOL)
     plan.close()
 
 
@@ -208,7 +215,10 @@ def test_notebook_pyramidal_charbonnier(nat, rubber_whale, notebook_runs, sample
     n = orc.nparams(ttype)
     assert len(traj) == len(entries)
     assert _epe(p[0, :n], entries[-1]["p"], ttype, 584, 388) <= EPE_TOL
-    np.testing.assert_allclose(err[0], entries[-1]["err"], rtol=0.05)
+    np.testing.assert_allclose(err[0], entries[-1]["err"], rtol=NOTEBOOK_ERR_RTOL)
+    # every stored line of the notebook: |Dp| and p, iteration by iteration
+    for row, e in zip(traj, entries):
+        np.testing.assert_allclose(row[2], e["err"], rtol=NOTEBOOK_ERR_RTOL, atol=DP_ATOL)
     plan.close()
 
 
@@ -227,7 +237,7 @@ def test_notebook_single_scale_robust_translation(nat, rubber_whale, notebook_ru
         lambda_=0.0, nanifoutside=True, delta=10, verbose=False)
     assert pr is p  # the single-scale functions mutate their argument
     assert _epe(p, entries[-1]["p"], orc.TRANSLATION, 584, 388) <= EPE_TOL
-    np.testing.assert_allclose(err, entries[-1]["err"], rtol=0.05)
+    np.testing.assert_allclose(err, entries[-1]["err"], rtol=NOTEBOOK_ERR_RTOL)
 
 
 def test_quadratic_single_scale_matches_oracle(nat, rubber_whale):
@@ -418,46 +428,6 @@ def test_row_sharded_nccl_two_gpus(nat, tmp_path):
     assert _epe(r0["p"], ref_p[0], t.value, 512, 384) <= 1e-6
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("ICA_SLOW_TESTS"), reason="minutes of CPU oracle time (set ICA_SLOW_TESTS=1)")
-def test_non_converging_pair_matches_oracle(nat):
-    """A pair of the bench workload on which the algorithm does NOT converge (30 iterations at every scale,
-    final motion far from the ground truth): the CUDA path must fail the same way as the oracle, iteration for
-    iteration, until chaos takes over -- compare the trajectories scale by scale."""
-    import torch
-    from inverse_compositional_algorithm_b200 import _native, synthetic
-    from inverse_compositional_algorithm_b200.transformation import TransformType
-    t = TransformType.HOMOGRAPHY
-    B = 32
-    I1, I2, p_gt = synthetic.make_batch_torch(B, 1024, 1024, 3, [t] * B, seed=1001, device="cuda")
-    I1 = I1.round_().clamp_(0, 255); I2 = I2.round_().clamp_(0, 255)
-    plan = _native.Plan(batch=B, height=1024, width=1024, channels=3, nscales=5, nu=0.5, transform_type=t.value,
-                        robust_type=3, robust_loop=True, lambda_=0.0, tol=1e-3, max_iter=30, delta=10,
-                        nanifoutside=True, gray_as_rgb=False)
-    p = torch.zeros((B, 8), dtype=torch.float64, device="cuda")
-    plan.run_device(I1.data_ptr(), I2.data_ptr(), p.data_ptr(), torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
-    pr, err, iters = plan.results()
-    bad = int(np.argmax(iters.sum(1)))
-    assert iters[bad].min() == 30
-    single = _native.Plan(batch=1, height=1024, width=1024, channels=3, nscales=5, nu=0.5, transform_type=t.value,
-                          robust_type=3, robust_loop=True, lambda_=0.0, tol=1e-3, max_iter=30, delta=10,
-                          nanifoutside=True, gray_as_rgb=False, record_trajectory=True)
-    p1 = torch.zeros((1, 8), dtype=torch.float64, device="cuda")
-    a, b = I1[bad:bad + 1].contiguous(), I2[bad:bad + 1].contiguous()
-    single.run_device(a.data_ptr(), b.data_ptr(), p1.data_ptr(), torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
-    traj = single.trajectory()[0]
-    trace = []
-    po, eo, _, _ = orc.ica_pyramidal(a[0].cpu().numpy().astype(np.float64), b[0].cpu().numpy().astype(np.float64),
-                                     np.zeros(8), t.value, 5, 0.5, 1e-3, orc.LORENTZIAN, 0.0, True, 10, trace=trace)
-    assert len(traj) == len(trace) == 150
-    # per-iteration |dp| of the coarsest scale (first 30 entries): same path while the iteration is stable
-    g = traj[:30, 2]
-    o = np.array([tr[2] for tr in trace[:30]])
-    print("gpu |dp|", g[:8], "oracle |dp|", o[:8], "final epe gpu-vs-oracle", _epe(pr[bad], po, t.value, 1024, 1024))
-    assert np.allclose(g[:5], o[:5], rtol=1e-3)
-
-
 @pytest.mark.parametrize("shape,channels,ttype_name,rtype", [((93, 121), 3, "HOMOGRAPHY", 3), ((77, 101), 1, "AFFINITY", 0),
                                                              ((64, 67), 3, "SIMILARITY", 4)])
 def test_unaligned_shapes_match_oracle(nat, shape, channels, ttype_name, rtype):
@@ -583,33 +553,6 @@ def test_layer_shaped_front_end(nat, rubber_whale):
     assert layer.iterations.shape == (3, 3)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("ICA_SLOW_TESTS"), reason="minutes of CPU oracle time (set ICA_SLOW_TESTS=1)")
-@pytest.mark.parametrize("config", ["c3", "c4"])
-def test_full_size_configs_match_oracle(nat, config):
-    """BASELINE configs 3 and 4 at full size against the oracle on a couple of pairs: 640x480 gray, similarity /
-    affinity, quadratic, 5 scales; 1024^2 RGB homography, Geman-McClure, 20 % occlusion, 5 scales."""
-    from inverse_compositional_algorithm_b200 import synthetic
-    from inverse_compositional_algorithm_b200.inverse_compositional_algorithm import register_batch
-    from inverse_compositional_algorithm_b200.transformation import TransformType
-    if config == "c3":
-        h, w, c, types, rtype, occ = 480, 640, 1, [TransformType.SIMILARITY, TransformType.AFFINITY], 0, 0.0
-    else:
-        h, w, c, types, rtype, occ = 1024, 1024, 3, [TransformType.HOMOGRAPHY, TransformType.HOMOGRAPHY], 2, 0.2
-    pairs = [synthetic.make_pair(300 + i, h, w, c, t, occlusion=occ) for i, t in enumerate(types)]
-    I1 = np.round(np.stack([a for a, _, _ in pairs])); I2 = np.round(np.stack([b for _, b, _ in pairs]))
-    p, err, iters = register_batch(I1, I2, types, nscales=5, robust_type=rtype, delta=10)
-    for i, t in enumerate(types):
-        a, b = (np.repeat(x, 3, 2) if c == 1 else x for x in (I1[i], I2[i]))
-        trace = []
-        po, eo, _, _ = orc.ica_pyramidal(a.astype(np.float64), b.astype(np.float64), np.zeros(t.nparams()), t.value, 5, 0.5,
-                                         1e-3, rtype, 0.0, True, 10, trace=trace)
-        epe = _epe(p[i, :t.nparams()], po, t.value, w, h)
-        print(config, t.name, "EPE vs oracle", epe, "iterations", int(iters[i].sum()), len(trace),
-              "EPE vs ground truth", _epe(p[i, :t.nparams()], pairs[i][2], t.value, w, h))
-        assert epe <= EPE_TOL
-        assert int(iters[i].sum()) == len(trace)
-
-
 def test_device_resident_entry_matches_host_entry(nat):
     """`register_batch_device` (torch CUDA tensors, read in place) gives bit for bit what `register_batch` gives from
     host arrays."""
@@ -729,3 +672,71 @@ def test_drivers_are_thread_safe(nat):
     for i in range(4):
         for rep in range(3):
             assert np.array_equal(got[i][rep], want[i])
+
+
+# ------------------------------------------------------------------ BASELINE configs at full size (committed oracle goldens)
+@pytest.fixture(scope="module")
+def fullsize_runs(golden_dir):
+    import os
+    return dict(np.load(os.path.join(golden_dir, "fullsize_runs.npz")))
+
+
+@pytest.mark.parametrize("name", ["c3_sim", "c3_aff", "c4_a", "c4_b", "c2_a", "c2_diverge"])
+def test_full_size_runs_match_oracle_goldens(nat, fullsize_runs, name):
+    """BASELINE configs 2, 3 and 4 at FULL size (640x480 gray similarity / affinity quadratic; 1024^2 RGB homography
+    Geman-McClure with 20 % occlusion; 1024^2 RGB homography Lorentzian) plus a 1024^2 pair whose motion lies outside
+    the capture range (30 iterations at every scale): final parameters, per-scale iteration counts and the
+    per-iteration |dp| against oracle runs committed by ``oracle/make_golden_fullsize.py`` (inputs are regenerated
+    from their seeds and checksummed)."""
+    from oracle import make_golden_fullsize as mg
+    from inverse_compositional_algorithm_b200 import _native
+    g = fullsize_runs
+    seed, H, W, C, t, rt, occ, kw = mg.RUNS[name]
+    I1, I2, _ = mg.make_inputs(name)
+    assert np.array_equal(g[name + "/checksum"], [I1.sum(dtype=np.float64), I2.sum(dtype=np.float64)]), "inputs differ from the golden run's"
+    plan = _native.Plan(batch=1, height=H, width=W, channels=C, nscales=mg.NSCALES, nu=mg.NU, transform_type=t.value,
+                        robust_type=rt, robust_loop=rt != 0, lambda_=mg.LAMBDA, tol=mg.TOL, max_iter=30, delta=mg.DELTA,
+                        nanifoutside=True, gray_as_rgb=(C == 1), record_trajectory=True)
+    p, err, iters, _, _ = plan.run_host(I1[None].astype(np.uint8), I2[None].astype(np.uint8))   # 8-bit through the ABI
+    traj = plan.trajectory()[0]
+    plan.close()
+    want = g[name + "/traj"]
+    n = t.nparams()
+    assert np.array_equal(iters[0], g[name + "/iters"]), (iters[0], g[name + "/iters"])
+    assert len(traj) == len(want)
+    if name == "c2_diverge":
+        # no convergence: MAX_ITER at every scale on both sides; the (chaotic) path is compared while it is stable
+        assert iters[0].min() == 30
+        np.testing.assert_allclose(traj[:10, 2], want[:10, 2], rtol=1e-3)
+        return
+    epe = _epe(p[0, :n], g[name + "/p"], t.value, W, H)
+    dev = np.max(np.abs(traj[:, 2] - want[:, 2]) / np.maximum(np.abs(want[:, 2]), 1e-3))
+    print(name, "EPE vs oracle", epe, "iterations", iters[0].tolist(), "max |dp| deviation (rel. to max(|dp|, 1e-3))", dev)
+    assert epe <= EPE_TOL
+    np.testing.assert_allclose(traj[:, 2], want[:, 2], rtol=DP_RTOL, atol=DP_ATOL)
+    np.testing.assert_allclose(err[0], g[name + "/err"], rtol=DP_RTOL, atol=DP_ATOL)
+
+
+def test_hessian_b_8192_wide_gray_vs_rowblocked_oracle(nat, golden_dir):
+    """One evaluation of the fused kernel at BASELINE config 5's size (8192 x 8192 gray, homography, Lorentzian)
+    against the row-blocked float64 oracle (``oracle/make_golden_8192.py``): this is where fp32 per-lane x-moment
+    sums (x^4 ~ 4.5e15) would show.  H entry-wise relative to its diagonal scale, dp = H^-1 b relative."""
+    import os
+    from inverse_compositional_algorithm_b200 import synthetic
+    g = dict(np.load(os.path.join(golden_dir, "hb_8192.npz")))
+    name = "8192_lorentzian"
+    seed, H, W, rt, lam, delta = g[name + "/cfg"]
+    I1, I2 = synthetic.make_large_gray_pair(int(seed), int(H), int(W))
+    assert np.array_equal(g[name + "/checksum"], [I1.sum(dtype=np.float64), I2.sum(dtype=np.float64)]), "inputs differ from the golden run's"
+    Hg, bg = nat.hessian_b(I1, I2, orc.HOMOGRAPHY, g[name + "/p"], int(rt), float(lam), int(delta), True, gray_as_rgb=True)
+    Hw, bw, dpw = g[name + "/H"], g[name + "/b"], g[name + "/dp"]
+    scale = np.sqrt(np.outer(np.diag(Hw), np.diag(Hw)))
+    h_err = float(np.max(np.abs(Hg - Hw) / scale))
+    dpg = np.linalg.solve(Hg, bg)
+    dp_err = float(np.max(np.abs(dpg - dpw) / np.abs(dpw)))
+    # the error of dp that matters to the loop: the displacement it produces over the image domain
+    epe = _epe(dpg, dpw, orc.HOMOGRAPHY, int(W), int(H))
+    print("8192^2: max |dH|/sqrt(HiiHjj) =", h_err, " max rel |d dp| =", dp_err, " EPE(dp_gpu, dp_oracle) =", epe, "px")
+    assert h_err <= 1e-5
+    assert dp_err <= HB8192_DP_RTOL
+    assert epe <= 1e-4

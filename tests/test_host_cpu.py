@@ -125,6 +125,21 @@ def test_pyramid_operator_matches_scipy(nat, n_in, n_out):
                                    A[hi - 2, 2 * (hi - 2) + s0:2 * (hi - 2) + s0 + taps], atol=1e-8)
 
 
+@pytest.mark.parametrize("n_in,n_out", [(600, 24), (1000, 30), (1500, 40)])
+def test_resample_operator_strong_downscaling(nat, n_in, n_out):
+    """nu around 0.04-0.06: the Gaussian radius (4 sigma = 2 (1/nu - 1)) exceeds the 48 columns the band builder used to
+    keep: the band is now sized from the radius and the operator still matches scipy."""
+    from scipy import ndimage as ndi
+    A, taps, _ = nat.resample_operator(n_in, n_out)
+    x = np.random.default_rng(n_in).uniform(0, 255, (n_in, 2))
+    f = n_in / n_out
+    g = ndi.gaussian_filter1d(x, (f - 1) / 2, axis=0, mode="constant", cval=0)
+    want = ndi.zoom(g, (1 / f, 1), order=3, mode="grid-constant", cval=0, grid_mode=True)
+    assert np.abs(A @ x - want).max() / np.abs(want).max() < 2e-6
+    if n_in / n_out > 26:
+        assert taps > 97      # wider than the old fixed band of 2 * 48 + 1 columns
+
+
 def test_configuration_handler_roundtrip(tmp_path):
     from inverse_compositional_algorithm_b200 import configuration_handler as cfh
     from inverse_compositional_algorithm_b200 import TransformType, RobustErrorFunctionType
@@ -211,7 +226,7 @@ def test_sharded_registration_gloo_world2(tmp_path):
 
 
 def test_zoom_out_operator_reproduces_scipy_chain():
-    """Host logic of zoom.zoom_out: the banded 1-D operator (built by pushing the identity through scipy) applied along
+    """Host logic of zoom.zoom_out: the banded 1-D operator (built in C++: build_zoom_out_1d) applied along
     both axes equals the direct Gaussian + cubic-spline resampling of the oracle."""
     from oracle import ica_oracle as orc
     from inverse_compositional_algorithm_b200.zoom import zoom_out_operator
