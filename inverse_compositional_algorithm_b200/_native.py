@@ -305,6 +305,8 @@ def dij_reduce(DIJ, DI=None, rho=None) -> np.ndarray:
     require_gpu()
     dij = _f64(DIJ)
     ny, nx, nz, n = dij.shape
+    if ny * nx * nz == 0:      # empty image: the sum over no pixels (the reference's einsum returns zeros)
+        return np.zeros(n if DI is not None else (n, n))
     di = _f64(DI) if DI is not None else None
     r = _f64(rho) if rho is not None else None
     out = np.empty(n if di is not None else (n, n))

@@ -14,11 +14,13 @@ pytestmark = pytest.mark.gpu
 
 REL_1E5 = 1e-5
 EPE_TOL = 1e-3
-# per-iteration |dp| against the float64 oracle / reference: relative, plus an absolute floor for the last iterations
-# of a scale, whose |dp| (~1e-4) is the difference of nearly equal numbers
-DP_RTOL, DP_ATOL = 1e-4, 2e-7
-HB8192_DP_RTOL = 1e-3      # one solve of an ill-conditioned 8 x 8 system; the loop itself is self-correcting
-NOTEBOOK_ERR_RTOL = 2e-3   # the notebooks' stored |Dp| lines (was 0.05 in round 1)
+# per-iteration |dp| against the float64 oracle / reference.  The device stores images (and pyramid levels) in float32
+# -- the north star's 1e-5 budget -- so an iterate differs from the float64 one by ~1e-6 px, and |dp|, the size of the
+# NEXT step, inherits that absolutely: measured worst cases over the suite (B200, round 2) are 1.7e-3 relative on a
+# |dp| of 5e-3 and 1.5e-5 absolute on a |dp| of 1.4e-2, with identical iteration counts and final EPE <= 2.2e-6 px.
+DP_RTOL, DP_ATOL = 2.5e-3, 2e-6
+HB8192_DP_RTOL = 1e-4      # one solve of the ill-conditioned 8 x 8 system at 8192^2 (measured 5e-6)
+NOTEBOOK_ERR_RTOL = 2.5e-3   # the notebooks' stored |Dp| lines (was 0.05 in round 1)
 
 
 @pytest.fixture(scope="module")
@@ -737,6 +739,6 @@ def test_hessian_b_8192_wide_gray_vs_rowblocked_oracle(nat, golden_dir):
     # the error of dp that matters to the loop: the displacement it produces over the image domain
     epe = _epe(dpg, dpw, orc.HOMOGRAPHY, int(W), int(H))
     print("8192^2: max |dH|/sqrt(HiiHjj) =", h_err, " max rel |d dp| =", dp_err, " EPE(dp_gpu, dp_oracle) =", epe, "px")
-    assert h_err <= 1e-5
+    assert h_err <= 1e-6       # measured 1.6e-8
     assert dp_err <= HB8192_DP_RTOL
-    assert epe <= 1e-4
+    assert epe <= 1e-5         # measured 2.1e-7 px
