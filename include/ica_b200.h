@@ -193,6 +193,15 @@ ICA_API int ica_zoom_out_operator(int32_t n_in, double factor, int32_t* n_out, i
                                   float* weights_out, int32_t weights_capacity);
 ICA_API int ica_zoom_out_host(const float* image, int32_t height, int32_t width, int32_t channels, double factor,
                               float* out, int32_t* out_h, int32_t* out_w);
+/* Synthetic pairs with a known ground truth, generated on the device (the reference fabricates its test
+   pairs with transformation.transform_image, src/transformation.py:266-318, inside the notebooks): smooth random
+   texture, I2 = its centre crop, I1(x) = texture(x'(x; p_gt)) + noise (+ an occluding square of uniform noise), values
+   in [0, 255], optionally rounded to 8-bit.  Counter-based randomness: a value depends on (seed, pair_offset + pair,
+   position) only.  I1/I2: float32 [B][H][W][C] device buffers; ttypes [B], p_gt [B][8], occ_xy [B][2] (or NULL) host. */
+ICA_API int ica_generate_pairs_device(float* I1_dev, float* I2_dev, int32_t batch, int32_t height, int32_t width,
+                                      int32_t channels, const int32_t* ttypes, const double* p_gt, const int32_t* occ_xy,
+                                      int32_t occ_side, uint64_t seed, int32_t pair_offset, int32_t margin,
+                                      double noise_sigma, int32_t quantize, void* stream);
 /* zoom.zoom_size (src/zoom.py:8-22), round-half-to-even */
 ICA_API int ica_zoom_size(int32_t nx, int32_t ny, double factor, int32_t* nxx, int32_t* nyy);
 /* Gradient of I1 + frame (ica.py:81-93): Ix, Iy float32 [H][W][C]; NaN on the frame */

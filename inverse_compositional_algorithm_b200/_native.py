@@ -85,6 +85,8 @@ SIGNATURES = {
     "ica_rescale_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _PI, _PI]),
     "ica_resample_operator": (C.c_int, [C.c_int32, C.c_int32, _PI, _PI, _P, C.c_int32, _PI]),
     "ica_zoom_size": (C.c_int, [C.c_int32, C.c_int32, C.c_double, _PI, _PI]),
+    "ica_generate_pairs_device": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _PI, _P, _PI, C.c_int32,
+                                            C.c_uint64, C.c_int32, C.c_int32, C.c_double, C.c_int32, _P]),
     "ica_zoom_out_operator": (C.c_int, [C.c_int32, C.c_double, _PI, _PI, _PI, _P, C.c_int32]),
     "ica_zoom_out_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _PI, _PI]),
     "ica_gradient_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
@@ -243,6 +245,22 @@ def zoom_out(image, factor: float) -> np.ndarray:
                                   C.byref(oh), C.byref(ow)))
     assert (oh.value, ow.value) == out.shape[:2]
     return out
+
+
+def generate_pairs_device(I1_ptr: int, I2_ptr: int, batch: int, height: int, width: int, channels: int, ttypes, p_gt,
+                          occ_xy=None, occ_side: int = 0, seed: int = 0, pair_offset: int = 0, margin: int = 64,
+                          noise_sigma: float = 1.0, quantize: bool = True, stream: int = 0) -> None:
+    """Fills the device buffers ``I1``/``I2`` (float32 ``[B][H][W][C]``) with synthetic pairs (csrc/ica_generate.cu)."""
+    require_gpu()
+    tt = np.ascontiguousarray(ttypes, dtype=np.int32)
+    pg = np.zeros((batch, MAX_PARAMS))
+    pgi = np.asarray(p_gt, dtype=np.float64).reshape(batch, -1)
+    pg[:, :pgi.shape[1]] = pgi
+    occ = np.ascontiguousarray(occ_xy, dtype=np.int32) if occ_xy is not None else None
+    check(lib().ica_generate_pairs_device(_P(I1_ptr), _P(I2_ptr), int(batch), int(height), int(width), int(channels),
+                                          tt.ctypes.data_as(_PI), _ptr(pg), occ.ctypes.data_as(_PI) if occ is not None else None,
+                                          int(occ_side), C.c_uint64(int(seed)), int(pair_offset), int(margin), float(noise_sigma),
+                                          1 if quantize else 0, _P(stream)))
 
 
 def inverse_hessian(H: np.ndarray) -> np.ndarray:

@@ -14,11 +14,19 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "libica_b200.so")
-SOURCES = ["ica_iterate.cu", "ica_pyramid.cu", "ica_capi.cu", "ica_helpers.cu"]
+SOURCES = ["ica_iterate.cu", "ica_pyramid.cu", "ica_capi.cu", "ica_helpers.cu", "ica_generate.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
 ]
+
+
+if os.environ.get("ICA_TIMELINE"):      # profiling build: per-CTA timeline instrumentation in the iterate kernel
+    NVCC_FLAGS.append("-DICA_TIMELINE=1")
+
+
+if os.environ.get("ICA_NVCC_EXTRA"):    # tuning hook: extra -D flags (tile window rows, pipeline stages, ...)
+    NVCC_FLAGS.extend(os.environ["ICA_NVCC_EXTRA"].split())
 
 
 def _nvcc() -> str:

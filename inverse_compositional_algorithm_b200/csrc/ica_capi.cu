@@ -48,7 +48,10 @@ struct ica_plan {
   int* item_pair = nullptr;
   unsigned int* solve_ticket = nullptr;
   int* loop_count = nullptr;
-  long long* tstamp = nullptr;      // [2] + kernel_ns [2]
+  long long* kernel_ns = nullptr;   // [2] accumulated streaming-phase time of the iterate kernel (ns), launches
+  SchedHdr* hdr = nullptr;          // [2] headers of the double-buffered work lists
+  unsigned int* pair_ticket = nullptr;   // [B]
+  int fused = 0;                    // solve inside the iterate kernel (one launch per iteration; opt-in, ICA_FUSE=1)
   int* h_loop = nullptr;            // pinned: {iterations, pad} and kernel ns copied after a run
   long long* h_kns = nullptr;       // pinned [2]
   cudaGraph_t graph = nullptr;
@@ -97,6 +100,7 @@ struct ica_plan {
   cudaStream_t stream = nullptr;  // own stream of the host entry
   size_t device_bytes = 0;
   long long launches = 0;
+  int last_launches_per_iter = 2;    // 1 when the last run used the fused solve
   // optional timing
   int timing = 0;
   cudaEvent_t ev_host0 = nullptr, ev_host1 = nullptr, ev_h2d_done = nullptr;  // bracket ica_plan_run_host on its stream
@@ -282,14 +286,15 @@ void fill_iter_params(const ica_plan* pl, const float* /*I1*/, const float* /*I2
   P->traj_cap = pl->traj_cap;
   P->chunk_start = pl->chunk_start;
   P->item_pair = pl->item_pair;
+  P->hdr = pl->hdr;
+  P->pair_ticket = pl->pair_ticket;
+  P->fused = 0;                      // the callers that run the fused loop set it
   P->solve_ticket = pl->solve_ticket;
   P->asm_tab = pl->asm_tab;
   P->cond_handle = 0;
   P->loop_count = pl->loop_count;
-  P->work_counter = pl->loop_count + 1;
   P->max_launches = pl->nscales * pl->cfg.max_iter;
-  P->tstamp = pl->tstamp;
-  P->kernel_ns = pl->tstamp + 2;
+  P->kernel_ns = pl->kernel_ns;
   P->shard_rank = pl->shard_rank; P->shard_n = pl->shard_n;
   P->solve_mode = 0; P->ext_moments = nullptr;
   P->B = pl->B;
@@ -326,9 +331,10 @@ int ensure_loop_graph(ica_plan* pl, const float* I1, const float* I2) {
   IterParams P;
   fill_iter_params(pl, I1, I2, &P);
   P.cond_handle = (unsigned long long)handle;
+  P.fused = pl->fused;
   ICA_CUDA_CHECK(cudaStreamBeginCaptureToGraph(pl->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
   cudaError_t e1 = launch_iterate(P, pl->C, pl->dh, pl->grid, pl->stream);
-  cudaError_t e2 = launch_solve(P, pl->dh, pl->stream);
+  cudaError_t e2 = pl->fused ? cudaSuccess : launch_solve(P, pl->dh, pl->stream);   // fused: the iterate kernel solves
   cudaGraph_t captured = nullptr;
   cudaError_t e3 = cudaStreamEndCapture(pl->stream, &captured);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
@@ -417,7 +423,7 @@ int ica_plan_destroy(ica_plan* pl) {
   if (!pl) return ICA_OK;
   cudaFree(pl->pyr1); cudaFree(pl->pyr2); cudaFree(pl->tmp); cudaFree(pl->tmaps_dev); cudaFree(pl->pad1); cudaFree(pl->pad2);
   for (int s = 0; s < ICA_MAX_SCALES; ++s) { free_resample(&pl->ry[s]); free_resample(&pl->rx[s]); }
-  cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->item_pair); cudaFree(pl->solve_ticket); cudaFree(pl->asm_tab); cudaFree(pl->loop_count); cudaFree(pl->tstamp);
+  cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->item_pair); cudaFree(pl->solve_ticket); cudaFree(pl->asm_tab); cudaFree(pl->loop_count); cudaFree(pl->kernel_ns); cudaFree(pl->hdr); cudaFree(pl->pair_ticket);
   if (pl->h_loop) cudaFreeHost(pl->h_loop);
   if (pl->h_kns) cudaFreeHost(pl->h_kns);
   if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
@@ -504,16 +510,26 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   TRY(dev_alloc(pl, &pl->state, (size_t)pl->B));
   TRY(dev_alloc(pl, &pl->mm, (size_t)pl->B * pl->nscales * 2));
   TRY(dev_alloc(pl, &pl->partials, (size_t)pl->B * pl->max_chunks * kAccStride));
-  TRY(dev_alloc(pl, &pl->chunk_start, (size_t)pl->B + 1));
-  TRY(dev_alloc(pl, &pl->item_pair, (size_t)pl->B * pl->max_chunks));
+  TRY(dev_alloc(pl, &pl->chunk_start, 2 * ((size_t)pl->B + 1)));                 // double-buffered work lists
+  TRY(dev_alloc(pl, &pl->item_pair, 2 * (size_t)pl->B * pl->max_chunks));
+  TRY(dev_alloc(pl, &pl->hdr, 2));
+  TRY_CUDA(cudaMemset(pl->hdr, 0, 2 * sizeof(SchedHdr)));
+  TRY(dev_alloc(pl, &pl->pair_ticket, (size_t)pl->B));
+  TRY_CUDA(cudaMemset(pl->pair_ticket, 0, (size_t)pl->B * sizeof(unsigned int)));
   TRY(dev_alloc(pl, &pl->solve_ticket, 1));
   TRY(dev_alloc(pl, &pl->loop_count, 2));
-  TRY(dev_alloc(pl, &pl->tstamp, 4));
-  TRY_CUDA(cudaMemset(pl->tstamp, 0, 4 * sizeof(long long)));
+  TRY_CUDA(cudaMemset(pl->loop_count, 0, 2 * sizeof(int)));
+  TRY(dev_alloc(pl, &pl->kernel_ns, 2));
+  TRY_CUDA(cudaMemset(pl->kernel_ns, 0, 2 * sizeof(long long)));
   TRY_CUDA(cudaMallocHost((void**)&pl->h_loop, 2 * sizeof(int)));
   TRY_CUDA(cudaMallocHost((void**)&pl->h_kns, 2 * sizeof(long long)));
   pl->h_loop[0] = 0; pl->h_kns[0] = 0; pl->h_kns[1] = 0;
   pl->use_graph = (cfg->flags & ICA_FLAG_HOST_LOOP) ? 0 : (getenv("ICA_NO_GRAPH") ? 0 : 1);
+  // Fused solve (the CTA that finishes a pair's last chunk solves it inside the iterate kernel: one launch per
+  // iteration) is available but off by default: measured on B200 (round 2, profiles/README.md) it is SLOWER than the
+  // separate 512-thread solve launch -- 28.5 vs 26.9 ms per 256-pair step, 2.39 vs 2.12 ms for a single pair -- the
+  // solve is a latency chain that runs worse at the iterate kernel's 80 registers, and it stalls a streaming CTA.
+  pl->fused = getenv("ICA_FUSE") ? 1 : 0;
   TRY(dev_alloc(pl, &pl->asm_tab, (size_t)6 * 72));
   TRY(upload_assembly(pl));
   TRY_CUDA(cudaMemset(pl->solve_ticket, 0, sizeof(unsigned int)));
@@ -568,7 +584,7 @@ int ica_plan_level_shapes(const ica_plan* pl, int32_t* nx_out, int32_t* ny_out) 
 size_t ica_plan_device_bytes(const ica_plan* pl) { return pl ? pl->device_bytes : 0; }
 int64_t ica_plan_last_launch_count(const ica_plan* pl) {
   // valid once the run's stream work has completed (the iteration count is copied back asynchronously)
-  return pl ? pl->launches + 2ll * pl->h_loop[0] : 0;
+  return pl ? pl->launches + (long long)pl->last_launches_per_iter * pl->h_loop[0] : 0;
 }
 
 int ica_plan_enable_timing(ica_plan* pl, int32_t enable) {
@@ -638,7 +654,7 @@ int ica_plan_shard_begin(ica_plan* pl, const float* I1, const float* I2, const d
   pl->last_I1 = I1; pl->last_I2 = I2;
   if (int rc = prepare_level0(pl, I1, I2, stream)) return rc;
   if (int rc = build_pyramids(pl, I1, I2, stream)) return rc;
-  ICA_LAUNCH_CHECK(launch_init_state(pl->state, p_in, pl->ttypes_dev, pl->B, pl->nscales, pl->cfg.lambda_, pl->n_active, stream));
+  ICA_LAUNCH_CHECK(launch_init_state(pl->state, p_in, pl->ttypes_dev, pl->B, pl->nscales, pl->cfg.lambda_, pl->n_active, pl->pair_ticket, stream));
   IterParams P;
   fill_iter_params(pl, I1, I2, &P);
   ICA_LAUNCH_CHECK(launch_schedule(P, stream));
@@ -699,13 +715,17 @@ int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* 
   if (int rc = prepare_level0(pl, I1, I2, stream)) return rc;
   if (int rc = build_pyramids(pl, I1, I2, stream)) return rc;
   ICA_LAUNCH_CHECK(launch_init_state(pl->state, p_inout, pl->ttypes_dev, pl->B, pl->nscales, pl->cfg.lambda_,
-                                     pl->n_active, stream));
+                                     pl->n_active, pl->pair_ticket, stream));
   pl->launches += 1;
   IterParams P;
   fill_iter_params(pl, I1, I2, &P);
   const int max_launches = pl->nscales * pl->cfg.max_iter;
   ICA_LAUNCH_CHECK(launch_schedule(P, stream));   // work list of the first iteration
   pl->launches += 1;
+  // timing mode 2 brackets every iterate launch with CUDA events: keep the solve in its own launch there
+  const bool fused = pl->fused && pl->timing < 2;
+  P.fused = fused ? 1 : 0;
+  pl->last_launches_per_iter = fused ? 1 : 2;
   if (pl->use_graph && pl->timing < 2) {
     // device-side loop: CUDA-graph while node, condition set by the solve kernel
     if (int rc = ensure_loop_graph(pl, I1, I2)) return rc;
@@ -721,7 +741,7 @@ int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* 
       ICA_LAUNCH_CHECK(launch_iterate(P, pl->C, pl->dh, pl->grid, stream));
       if (timed) cudaEventRecord(pl->ev_iter[pl->n_ev_iter++], stream);
       // per-pair solve / compose; its last block publishes the next work list and the number of unfinished pairs
-      ICA_LAUNCH_CHECK(launch_solve(P, pl->dh, stream));
+      if (!fused) ICA_LAUNCH_CHECK(launch_solve(P, pl->dh, stream));
       if (it + 1 >= next_poll && it + 1 < max_launches) {
         ICA_CUDA_CHECK(cudaMemcpyAsync(pl->h_n_active, pl->n_active, sizeof(int), cudaMemcpyDeviceToHost, stream));
         ICA_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -732,7 +752,7 @@ int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* 
   }
   // iterations executed and time spent in the iterate kernel (device-side counters), read lazily by the getters
   ICA_CUDA_CHECK(cudaMemcpyAsync(pl->h_loop, pl->loop_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  ICA_CUDA_CHECK(cudaMemcpyAsync(pl->h_kns, pl->tstamp + 2, 2 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+  ICA_CUDA_CHECK(cudaMemcpyAsync(pl->h_kns, pl->kernel_ns, 2 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
   ICA_LAUNCH_CHECK(launch_export_results(pl->state, pl->B, p_inout, pl->err_dev, pl->iters_dev, pl->nscales, stream));
   pl->launches += 1;
   if (pl->cfg.flags & ICA_FLAG_WRITE_DI_IW) {
@@ -1150,7 +1170,7 @@ int ica_hessian_b_host(const float* I1, const float* I2, int32_t height, int32_t
   if (!rc) rc = prepare_level0(pl, pl->in1_dev, pl->in2_dev, 0);
   if (!rc) rc = build_pyramids(pl, pl->in1_dev, pl->in2_dev, 0);
   if (!rc) {
-    e = launch_init_state(pl->state, pl->p_dev, pl->ttypes_dev, 1, 1, cfg.lambda_, pl->n_active, 0);
+    e = launch_init_state(pl->state, pl->p_dev, pl->ttypes_dev, 1, 1, cfg.lambda_, pl->n_active, pl->pair_ticket, 0);
     IterParams P;
     fill_iter_params(pl, pl->in1_dev, pl->in2_dev, &P);
     P.dbg_Hb = d_dbg;

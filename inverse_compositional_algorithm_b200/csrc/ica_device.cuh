@@ -84,6 +84,16 @@ __device__ __forceinline__ void keys_weights(float t, float& w0, float& w1, floa
   w3 = t2 * fmaf(0.5f, t, -0.5f);
 }
 
+// The same weights for two coordinates at once in packed fp32 (lane's two pixels): identical arithmetic per half.
+__device__ __forceinline__ void keys_weights2(float2 t, float2& w0, float2& w1, float2& w2, float2& w3) {
+  const float2 one = make_float2(1.0f, 1.0f), half = make_float2(0.5f, 0.5f), mhalf = make_float2(-0.5f, -0.5f);
+  const float2 t2 = __fmul2_rn(t, t);
+  w0 = __fmul2_rn(t, __ffma2_rn(t, __ffma2_rn(mhalf, t, one), mhalf));
+  w1 = __ffma2_rn(t2, __ffma2_rn(make_float2(1.5f, 1.5f), t, make_float2(-2.5f, -2.5f)), one);
+  w2 = __fmul2_rn(t, __ffma2_rn(t, __ffma2_rn(make_float2(-1.5f, -1.5f), t, make_float2(2.0f, 2.0f)), half));
+  w3 = __fmul2_rn(t2, __ffma2_rn(half, t, mhalf));
+}
+
 // rho'(t2) of src/image_optimisation.py:17-53 (TRUNCATED_QUADRATIC element-wise)
 __device__ __forceinline__ float rho_prime(float t2, float lambda2, int rtype) {
   switch (rtype) {

@@ -38,6 +38,13 @@ namespace ica {
 
 namespace {
 
+// Per-CTA timeline stamps and wait accounting (tools/timeline.py) are compiled in only with -DICA_TIMELINE=1
+// (ICA_TIMELINE=1 python -m inverse_compositional_algorithm_b200.build): they cost registers in the per-pixel loop.
+#ifdef ICA_TIMELINE
+constexpr bool kTimeline = true;
+#else
+constexpr bool kTimeline = false;
+#endif
 constexpr int kBlocksPerSM = 2;      // 2 CTAs x 12 warps per SM at 80 registers per thread (16 warps at 64 registers measured 9 % slower)
 constexpr int kConsumerWarps = 11;   // + 1 producer warp = 12 warps: warps are allocated in groups of 4
 constexpr int kRowsPerWarp = 1;      // rows of a tile per consumer warp
@@ -47,7 +54,16 @@ constexpr int TW = 64;            // tile width  (2 pixels per lane: x0+lane, x0
 constexpr int TH = kRowsPerWarp * kConsumerWarps;   // tile height (row y0 + warp + rr * kConsumerWarps for warp, rr)
 constexpr int HALO = 4;           // the I1 patch starts at x0-4: the inner coordinate of a TMA box must be a multiple of 16 bytes
 constexpr int S1ROWS = TH + 2;
-constexpr int BH_MAX = 30;        // rows of the staged I2 window; taller windows (strong rotation / zoom) take the global-memory path
+#ifndef ICA_BH
+#define ICA_BH 30
+#endif
+#ifndef ICA_STAGES_RGB
+#define ICA_STAGES_RGB 2
+#endif
+#ifndef ICA_STAGES_GRAY
+#define ICA_STAGES_GRAY 4
+#endif
+constexpr int BH_MAX = ICA_BH;    // rows of the staged I2 window; taller windows (strong rotation / zoom) take the global-memory path
 
 template <int DH> struct RowVals { static constexpr int K = 3 * (DH + 1) + 2 * (DH / 2 + 1); };
 
@@ -61,21 +77,22 @@ template <int C> struct Stage {
   static constexpr int kFloats = (BH_MAX * S2W + S1ROWS * S1W + 31) / 32 * 32;   // I2 window, then I1 patch; 128-byte multiple
   // staged tiles in flight per CTA: RGB tiles are compute-heavy (a third stage measured no gain); gray tiles are consumed
   // in ~2 us, where two stages leave the consumers waiting for the producer 11-17 % of the time
-  static constexpr int kStages = C == 3 ? 2 : 4;
+  static constexpr int kStages = C == 3 ? ICA_STAGES_RGB : ICA_STAGES_GRAY;
 };
 
-// Everything a consumer needs to know about a staged tile (written by the producer).
-struct TileCtl {
+// Everything a consumer needs to know about a staged tile (written by the producer), grouped so that a consumer
+// fetches it with a few 128-bit shared loads where it needs it (the register file is the scarce resource of this
+// kernel: nothing tile-constant is kept in registers across the tap loads).  The warp coefficients are stored
+// duplicated, (c, c): they are operands of packed fp32 arithmetic on the lane's two pixels.
+struct __align__(16) TileCtl {
+  float2 c2[8];           // d00, m01, m02, m10, d11, m12, m20, m21 of WarpCoef, each as (c, c)
+  int4 geo;               // x0, y0, nx, ny
+  int4 win;               // bx0, by0, bw - 3, bh - 3: the staged I2 window as corner + unsigned limits (0, 0: no window)
+  int4 msk;               // gxlo, gxspan: columns with an in-frame x-gradient; fxlo, fxspan: columns inside the frame
+  int4 flg;               // need_h, last, stop, pitch
+  float4 fl;              // lo, hi: clip range of I2 at this level; lambda^2; unused
   double m64[9];          // warp matrix in fp64 (tie-break path of project_px)
-  WarpCoef coef;
-  float lo, hi;           // clip range of I2 at this level
-  float lambda2;
   int pair, chunk, nch, scale;
-  int need_h, first, last;
-  int x0, y0;
-  int bx0, by0, bw, bh, fits;
-  int nx, ny, pitch;
-  int stop;
   const float* I2;        // global image, for the pixels whose taps leave the staged window
 };
 
@@ -115,12 +132,23 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0,
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
+// 128-bit shared loads that stay where they are written (volatile asm): tile constants are fetched at the point of use
+__device__ __forceinline__ int4 lds_i4(const void* p) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(const void* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
 __device__ __forceinline__ void fence_tensormap_acquire(const void* tmap) {
   asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(tmap) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define ICA_STAMP(slot) do { if (P.dbg_time && it == 0 && tid == 0) P.dbg_time[blockIdx.x * 16 + (slot)] = gtime(); } while (0)
+#define ICA_STAMP(slot) do { if (kTimeline && P.dbg_time && it == 0 && tid == 0) P.dbg_time[blockIdx.x * 16 + (slot)] = gtime(); } while (0)
 // barrier among the consumer threads only (the producer warp never joins it)
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
 
@@ -167,29 +195,42 @@ __device__ __noinline__ float sample_global_slow(const float* __restrict__ img, 
 template <int C>
 __device__ __forceinline__ void producer_loop(const IterParams& P, float* stages, int stage_floats,
                                               unsigned long long* full, unsigned long long* empty, TileCtl* tctl,
-                                              double* pm64, int total_chunks, int lane) {
+                                              double* pm64, int par, int lane) {
   constexpr int S1W = Stage<C>::S1W, S2W = Stage<C>::S2W, kStages = Stage<C>::kStages;
   unsigned k = 0;   // tiles staged so far by this CTA
-  const bool pdbg = P.dbg_time != nullptr && lane == 0;   // profiling hook: cycles spent fetching work / waiting for a free stage
+  SchedHdr* const hdr = P.hdr + par;
+  const int* const item_pair = P.item_pair + (long long)par * P.B * P.max_chunks;
+  const int* const chunk_start = P.chunk_start + (long long)par * (P.B + 1);
+  const bool pdbg = kTimeline && P.dbg_time != nullptr && lane == 0;   // profiling hook: cycles spent fetching work / waiting for a free stage
   long long pd_fetch = 0, pd_empty = 0, pd_proj = 0, pd_ctl = 0, pd_issue = 0;
   for (;;) {
     // dynamic work distribution: chunks are handed out by an atomic counter (reset by the scheduler)
     const long long pf0 = pdbg ? clock64() : 0;
     int item = 0;
-    if (lane == 0) item = atomicAdd(P.work_counter, 1);
+    if (lane == 0) item = atomicAdd(&hdr->counter, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= total_chunks) break;
-    const int pair = __ldg(P.item_pair + item);
-    const int chunk = item - __ldg(P.chunk_start + pair);
-    const PairState& st = P.state[pair];
-    const int s = st.scale;
-    if (lane == 0) warp_matrix(st.p, st.ttype, pm64);
+    // (the total is re-read: with the fused solve a CTA that starts late may find the list of the NEXT iteration here)
+    if (item >= __ldcg(&hdr->total)) break;
+    const int pair = __ldcg(item_pair + item);
+    const int chunk = item - __ldcg(chunk_start + pair);
+    // the pair's state was written by the solve of the previous iteration, possibly during this very launch: read
+    // it from L2, never through a (per-SM, possibly stale) L1 line
+    const PairState* stp = P.state + pair;
+    const int s = __ldcg(&stp->scale);
+    const int st_ttype = __ldcg(&stp->ttype), st_iter = __ldcg(&stp->iter);
+    const double st_lambda = __ldcg(&stp->lambda_it);
+    if (lane == 0) {
+      double pp[ICA_MAX_PARAMS];
+#pragma unroll
+      for (int i = 0; i < ICA_MAX_PARAMS; ++i) pp[i] = __ldcg(&stp->p[i]);
+      warp_matrix(pp, st_ttype, pm64);
+    }
     __syncwarp();
     const WarpCoef coef = make_warp_coef(pm64);
     const MinMaxKeys mm = P.mm[(pair * P.nscales + s) * 2 + 1];
     const float lo = key_float(mm.lo), hi = key_float(mm.hi);
-    const float lambda2 = (float)(st.lambda_it * st.lambda_it);
-    const int need_h = (P.robust_loop || st.iter == 0) ? 1 : 0;
+    const float lambda2 = (float)(st_lambda * st_lambda);
+    const int need_h = (P.robust_loop || st_iter == 0) ? 1 : 0;
     const LevelDesc L = P.lv[s];
     const int nx = L.nx, ny = L.ny, pitch = L.pitch;
     const float* __restrict__ I2 = s == 0 ? P.I2_0 + (long long)pair * P.in_stride
@@ -206,7 +247,7 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stages
     const int t_begin = t_first + (int)((long long)chunk * ntiles / nch);
     const int t_end = t_first + (int)((long long)(chunk + 1) * ntiles / nch);
 
-    if (P.dbg_time && k == 0 && lane == 0) P.dbg_time[blockIdx.x * 16 + 9] = gtime();
+    if (kTimeline && P.dbg_time && k == 0 && lane == 0) P.dbg_time[blockIdx.x * 16 + 9] = gtime();
     if (pdbg) pd_fetch += clock64() - pf0;
     for (int tile = t_begin; tile < t_end; ++tile, ++k) {
       const int sidx = k % kStages;
@@ -242,14 +283,23 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stages
       if (tile < t_begin + kStages) {   // first use of this stage's control block by the chunk: per-chunk constants
         if (lane < 9) tc.m64[lane] = pm64[lane];
         if (lane == 0) {
-          tc.coef = coef; tc.lo = lo; tc.hi = hi; tc.lambda2 = lambda2;
-          tc.pair = pair; tc.chunk = chunk; tc.nch = nch; tc.scale = s; tc.need_h = need_h;
-          tc.nx = nx; tc.ny = ny; tc.pitch = pitch; tc.I2 = I2; tc.stop = 0;
+          tc.c2[0] = make_float2(coef.d00, coef.d00); tc.c2[1] = make_float2(coef.m01, coef.m01);
+          tc.c2[2] = make_float2(coef.m02, coef.m02); tc.c2[3] = make_float2(coef.m10, coef.m10);
+          tc.c2[4] = make_float2(coef.d11, coef.d11); tc.c2[5] = make_float2(coef.m12, coef.m12);
+          tc.c2[6] = make_float2(coef.m20, coef.m20); tc.c2[7] = make_float2(coef.m21, coef.m21);
+          tc.fl = make_float4(lo, hi, lambda2, 0.0f);
+          // columns inside the discarded frame (ica.py:85-93) and, of those, the ones with a central x-difference
+          const int fxlo = P.frame ? P.delta : 0;
+          const int fxspan = max(0, nx - 2 * fxlo);
+          const int gxlo = max(fxlo, 1), gxhi = min(fxlo + fxspan, nx - 1);
+          tc.msk = make_int4(gxlo, max(0, gxhi - gxlo), fxlo, fxspan);
+          tc.pair = pair; tc.chunk = chunk; tc.nch = nch; tc.scale = s; tc.I2 = I2;
         }
       }
       if (lane == 0) {
-        tc.first = tile == t_begin; tc.last = tile + 1 == t_end;
-        tc.x0 = x0; tc.y0 = y0; tc.bx0 = bx0; tc.by0 = by0; tc.bw = bw; tc.bh = bh; tc.fits = fits ? 1 : 0;
+        tc.geo = make_int4(x0, y0, nx, ny);
+        tc.win = fits ? make_int4(bx0, by0, bw - 3, bh - 3) : make_int4(0, 0, 0, 0);
+        tc.flg = make_int4(need_h, tile + 1 == t_end ? 1 : 0, 0, pitch);
       }
       const long long pt3 = pdbg ? clock64() : 0;
       __syncwarp();                       // the control block is complete before the arrival below
@@ -273,326 +323,32 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stages
     const int sidx = k % kStages;
     const unsigned use = k / kStages;
     if (use >= 1) mbar_wait(&empty[sidx], (use - 1) & 1);
-    if (lane == 0) { tctl[sidx].stop = 1; mbar_arrive(&full[sidx]); }
+    if (lane == 0) { tctl[sidx].flg = make_int4(0, 1, 1, 0); mbar_arrive(&full[sidx]); }
   }
 }
 
-// ============================================================ the kernel
-template <int C, int DH>
-__global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(const IterParams P) {
-  constexpr int K = RowVals<DH>::K;
-  constexpr int HW = DH + 1;        // x-powers kept for the Hessian moments
-  constexpr int BWN = DH / 2 + 1;   // x-powers kept for the b moments
-  constexpr int S1W = Stage<C>::S1W;
-  constexpr int S2W = Stage<C>::S2W;
-  constexpr int NENT = K * kYPow;
-  constexpr int kStages = Stage<C>::kStages;
+// ============================================================ scheduling and the per-pair solve
+// Both run either in the stand-alone kernels (ica_schedule_kernel, ica_solve_kernel: host-driven loop, row-sharded
+// mode, parity hooks) or, fused, inside ica_iterate_kernel by the consumer warps of the CTA that finishes a pair's last
+// chunk.  BlockSync abstracts the barrier: the whole block, or the consumer warps only (named barrier 1).
+struct SyncBlock { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+struct SyncConsumers { __device__ __forceinline__ void operator()() const { consumer_sync(); } };
 
-  extern __shared__ __align__(128) float smem[];
-  float* const stages = smem;                      // kStages x Stage<C>::kFloats
-  __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages];
-  __shared__ TileCtl tctl[kStages];
-  __shared__ double s_pm64[9];
-
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
-  const int total_chunks = P.chunk_start[P.B];
-  if ((int)blockIdx.x >= total_chunks) return;
-  if (tid == 0) atomicMin(reinterpret_cast<long long*>(&P.tstamp[0]), gtime());
-
-  if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], kConsumerWarps); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (warp == kConsumerWarps) {
-    producer_loop<C>(P, stages, Stage<C>::kFloats, s_full, s_empty, tctl, s_pm64, total_chunks, lane);
-    return;
-  }
-
-  // ------------------------------------------------------------------ consumers
-  const int delta = P.delta;
-  const bool frame = P.frame != 0;
-  const bool robust = P.robust_loop != 0;
-  const float chm = P.ch_mult;
-  const int rtype = P.robust_type;
-  // fp64 accumulators of the chunk in progress, double-buffered over consecutive chunks: [2][kConsumerWarps][K][kYPow]
-  double* const accs0 = reinterpret_cast<double*>(smem + kStages * Stage<C>::kFloats);
-  constexpr int kAccSet = kConsumerWarps * K * kYPow;
-  // the transposing reduction leaves moment k on the lanes k << kTrShift .. ; the first of them owns the fp64 accumulators
-  constexpr int kTrN = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
-  constexpr int kTrShift = kTrN == 8 ? 2 : (kTrN == 16 ? 1 : 0);
-  const int midx = lane >> kTrShift;
-  const bool mown = (lane & ((1 << kTrShift) - 1)) == 0 && midx < K;
-  double* myacc = accs0 + (warp * K + (mown ? midx : 0)) * kYPow;    // this lane's slot in the current set
-  unsigned k = 0;
-  int nitems = 0;
-  const bool dbg = P.dbg_time != nullptr && tid == 0;       // profiling hook: cycles warp 0 spends waiting / in chunk epilogues
-  long long dbg_wait = 0, dbg_epi = 0;
-  const long long dbg_t0 = dbg ? clock64() : 0;
-
-  if (P.dbg_time && tid == 0) P.dbg_time[blockIdx.x * 16 + 0] = gtime();
-  // Per-lane x-moment accumulators of the image row `vrow` (-1: empty).  Consecutive tiles of a chunk usually lie on
-  // the same tile row, so a warp keeps adding pixels of the same image row and pays the cross-lane reduction and
-  // the fp64 fold once per row segment of the chunk instead of once per tile.
-  float v[K];
-#pragma unroll
-  for (int i = 0; i < K; ++i) v[i] = 0.0f;
-  int vrow = -1;
-  // once per row segment: a transposing shuffle reduction leaves the row's moment k on the lane that owns it (fixed
-  // summation order), which folds in y^b in fp64; the fp64 accumulators live in shared memory
-  auto flush_row = [&]() {
-    float t32[kTrN];
-#pragma unroll
-    for (int i = 0; i < kTrN; ++i) t32[i] = i < K ? v[i] : 0.0f;
-#pragma unroll
-    for (int i = 0; i < K; ++i) v[i] = 0.0f;
-    const float tot = warp_transpose_reduce<kTrN>(t32, lane);
-    if (mown) {
-      const double yd = (double)vrow, t = (double)tot;
-      double yp = 1.0;
-#pragma unroll
-      for (int b = 0; b < kYPow; ++b) { myacc[b] = fma(t, yp, myacc[b]); yp *= yd; }
-    }
-    vrow = -1;
-  };
-  for (int it = 0;; ++it) {
-    if (mown) {
-#pragma unroll
-      for (int b = 0; b < kYPow; ++b) myacc[b] = 0.0;
-    }
-    int pair, chunk, nch, s, nx, ny;
-    bool need_h;
-    bool last;
-    bool stop = false;
-    do {
-      const int sidx = k % kStages;
-      const long long w0 = dbg ? clock64() : 0;
-      mbar_wait(&s_full[sidx], (k / kStages) & 1);
-      if (dbg) dbg_wait += clock64() - w0;
-      if (tctl[sidx].stop) { stop = true; break; }   // uniform: the producer ran out of work
-      if (k == 0) ICA_STAMP(1);
-      // Tile constants stay in shared memory and are re-read (volatile) where they are used: the
-      // register file is the scarce resource of this kernel, it must hold the tap loads in flight.
-      const volatile TileCtl* tcv = &tctl[sidx];
-      const float* s2 = stages + sidx * Stage<C>::kFloats;
-      const float* s1 = s2 + BH_MAX * S2W;
-#pragma unroll 1
-      for (int rr = 0; rr < TH / kConsumerWarps; ++rr) {
-        const int ly = warp + rr * kConsumerWarps;
-        const int y = tcv->y0 + ly;
-        const int ny = tcv->ny;
-        if (vrow >= 0 && vrow != y) flush_row();
-        if (y < ny) {
-          vrow = y;
-          const int nx = tcv->nx;
-          const bool need_hr = tcv->need_h != 0;
-          // moments of one pixel: v[] += (rho' S, rho' v) * x^a
-          auto add_moments = [&](float scl, float sxx, float sxy, float syy, float vx, float vy, float xf) {
-            if (need_hr) {
-              float wq[3] = {scl * sxx, scl * sxy, scl * syy};
-#pragma unroll
-              for (int q = 0; q < 3; ++q) {
-                float xp = 1.0f;
-#pragma unroll
-                for (int a = 0; a < HW; ++a) { v[q * HW + a] = fmaf(wq[q], xp, v[q * HW + a]); xp *= xf; }
-              }
-            }
-            float uq[2] = {scl * vx, scl * vy};
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              float xp = 1.0f;
-#pragma unroll
-              for (int a = 0; a < BWN; ++a) { v[3 * HW + q * BWN + a] = fmaf(uq[q], xp, v[3 * HW + q * BWN + a]); xp *= xf; }
-            }
-          };
-          // ---- the lane's two pixels A = (x0+lane, y), B = (x0+32+lane, y): projection
-          const int xA = tcv->x0 + lane, xB = xA + 32;
-          int cxA, cyA, cxB, cyB; float txA, tyA, txB, tyB;
-          bool pokA, pokB;
-          {
-            WarpCoef coef;
-            coef.d00 = tcv->coef.d00; coef.m01 = tcv->coef.m01; coef.m02 = tcv->coef.m02; coef.m10 = tcv->coef.m10;
-            coef.d11 = tcv->coef.d11; coef.m12 = tcv->coef.m12; coef.m20 = tcv->coef.m20; coef.m21 = tcv->coef.m21;
-            pokA = project_px(coef, tctl[sidx].m64, xA, y, cxA, cyA, txA, tyA);
-            pokB = project_px(coef, tctl[sidx].m64, xB, y, cxB, cyB, txB, tyB);
-          }
-          bool insmA, insmB;
-          int offA, offB;    // float offsets of the first tap inside the staged I2 window
-          {
-            const int bx0 = tcv->bx0, by0 = tcv->by0, bw = tcv->bw, bh = tcv->bh;
-            const bool fits = tcv->fits != 0;
-            // 0 <= c - 1 - b0 <= extent - 4, as one unsigned comparison per axis (extent >= 4 whenever fits)
-            const unsigned lx = (unsigned)(bw - 4), lyy = (unsigned)(bh - 4);
-            insmA = fits && (unsigned)(cxA - 1 - bx0) <= lx && (unsigned)(cyA - 1 - by0) <= lyy;
-            insmB = fits && (unsigned)(cxB - 1 - bx0) <= lx && (unsigned)(cyB - 1 - by0) <= lyy;
-            offA = (cyA - 1 - by0) * S2W + (cxA - 1 - bx0) * C;
-            offB = (cyB - 1 - by0) * S2W + (cxB - 1 - bx0) * C;
-          }
-          const bool fastlane = pokA && pokB && insmA && insmB && xB < nx;
-          if (__all_sync(0xffffffffu, fastlane)) {
-            // ===== straight-line path: both pixels in one instruction stream, packed fp32 (FFMA2)
-            // phase 1: the 2 x 16 taps of every channel -> warped values (few live registers besides the loads)
-            float2 iw[C];
-            {
-              float2 wx[4], wy[4];
-              {
-                float a0, a1, a2, a3, b0, b1, b2, b3;
-                keys_weights(txA, a0, a1, a2, a3); keys_weights(txB, b0, b1, b2, b3);
-                wx[0] = make_float2(a0, b0); wx[1] = make_float2(a1, b1); wx[2] = make_float2(a2, b2); wx[3] = make_float2(a3, b3);
-                keys_weights(tyA, a0, a1, a2, a3); keys_weights(tyB, b0, b1, b2, b3);
-                wy[0] = make_float2(a0, b0); wy[1] = make_float2(a1, b1); wy[2] = make_float2(a2, b2); wy[3] = make_float2(a3, b3);
-              }
-              const float* tA = s2 + offA;
-              const float* tB = s2 + offB;
-#pragma unroll
-              for (int ch = 0; ch < C; ++ch) {
-                float2 acc2 = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float* rA = tA + q * S2W + ch;
-                  const float* rB = tB + q * S2W + ch;
-                  float2 h = __fmul2_rn(wx[0], make_float2(rA[0], rB[0]));
-                  h = __ffma2_rn(wx[1], make_float2(rA[C], rB[C]), h);
-                  h = __ffma2_rn(wx[2], make_float2(rA[2 * C], rB[2 * C]), h);
-                  h = __ffma2_rn(wx[3], make_float2(rA[3 * C], rB[3 * C]), h);
-                  acc2 = __ffma2_rn(wy[q], h, acc2);
-                }
-                iw[ch] = acc2;
-              }
-            }
-            // phase 2: residual, gradient of I1 (masks fold the 1/2, the frame and the image border), S, v
-            const int delta_ = delta;
-            const bool yin = !frame || (y >= delta_ && y < ny - delta_);
-            const bool frA = yin && (!frame || (xA >= delta_ && xA < nx - delta_));
-            const bool frB = yin && (!frame || (xB >= delta_ && xB < nx - delta_));
-            const bool gyrow = y >= 1 && y <= ny - 2;
-            const float2 mgx = make_float2((frA && xA >= 1 && xA <= nx - 2) ? 0.5f : 0.0f, (frB && xB >= 1 && xB <= nx - 2) ? 0.5f : 0.0f);
-            const float2 mgy = make_float2((frA && gyrow) ? 0.5f : 0.0f, (frB && gyrow) ? 0.5f : 0.0f);
-            const float2 nmgx = make_float2(-mgx.x, -mgx.y), nmgy = make_float2(-mgy.x, -mgy.y);
-            const float* cA = s1 + (ly + 1) * S1W + (lane + HALO) * C;
-            const float* cB = cA + 32 * C;
-            const float lo = tcv->lo, hi = tcv->hi;
-            float2 sxx = make_float2(0.f, 0.f), sxy = sxx, syy = sxx, vx = sxx, vy = sxx, t2 = sxx;
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-              const bool vA = iw[ch].x == iw[ch].x, vB = iw[ch].y == iw[ch].y;   // NaN footprint
-              const float iwA = fminf(fmaxf(iw[ch].x, lo), hi), iwB = fminf(fmaxf(iw[ch].y, lo), hi);
-              const float2 gx = __ffma2_rn(make_float2(cA[ch + C], cB[ch + C]), mgx, __fmul2_rn(make_float2(cA[ch - C], cB[ch - C]), nmgx));
-              const float2 gy = __ffma2_rn(make_float2(cA[ch + S1W], cB[ch + S1W]), mgy, __fmul2_rn(make_float2(cA[ch - S1W], cB[ch - S1W]), nmgy));
-              const float2 di = make_float2(vA ? iwA - cA[ch] : 0.0f, vB ? iwB - cB[ch] : 0.0f);   // non-finite -> 0 (io.py:72, 134)
-              if (need_hr) { sxx = __ffma2_rn(gx, gx, sxx); sxy = __ffma2_rn(gx, gy, sxy); syy = __ffma2_rn(gy, gy, syy); }
-              vx = __ffma2_rn(gx, di, vx); vy = __ffma2_rn(gy, di, vy);
-              t2 = __ffma2_rn(di, di, t2);
-            }
-            // phase 3: robust weight and moments.  A gray image stands for its x3 replication
-            // (SURVEY Q12): every channel sum triples
-            const float lambda2 = tcv->lambda2;
-            const float rhoA = robust ? rho_prime(t2.x * chm, lambda2, rtype) : 1.0f;
-            const float rhoB = robust ? rho_prime(t2.y * chm, lambda2, rtype) : 1.0f;
-            add_moments(rhoA * chm, sxx.x, sxy.x, syy.x, vx.x, vy.x, (float)xA);
-            add_moments(rhoB * chm, sxx.y, sxy.y, syy.y, vx.y, vy.y, (float)xB);
-          } else {
-            // ===== generic path: image edges, windows that do not fit, degenerate projections
-            const bool yin = !frame || (y >= delta && y < ny - delta);
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-              const int x = half ? xB : xA;
-              if (x >= nx) continue;
-              const int lx = lane + half * 32;
-              const int cx = half ? cxB : cxA, cy = half ? cyB : cyA;
-              const bool pok = half ? pokB : pokA, insm = half ? insmB : insmA;
-              float wxs[4], wys[4];
-              keys_weights(half ? txB : txA, wxs[0], wxs[1], wxs[2], wxs[3]);
-              keys_weights(half ? tyB : tyA, wys[0], wys[1], wys[2], wys[3]);
-              const bool inframe = yin && (!frame || (x >= delta && x < nx - delta));
-              const float* t2base = s2 + (half ? offB : offA);
-              const float* c1 = s1 + (ly + 1) * S1W + (lx + HALO) * C;
-              const bool gxok = inframe && x >= 1 && x <= nx - 2;
-              const bool gyok = inframe && y >= 1 && y <= ny - 2;
-              const float lo = tcv->lo, hi = tcv->hi;
-              float sxx = 0.f, sxy = 0.f, syy = 0.f, vx = 0.f, vy = 0.f, t2 = 0.f;
-#pragma unroll
-              for (int ch = 0; ch < C; ++ch) {
-                float iwv;
-                if (!pok) {
-                  iwv = __int_as_float(0x7fc00000);
-                } else if (insm) {
-                  float a = 0.0f;
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const float* r = t2base + q * S2W + ch;
-                    float hsum = wxs[0] * r[0] + wxs[1] * r[C] + wxs[2] * r[2 * C] + wxs[3] * r[3 * C];
-                    a = fmaf(wys[q], hsum, a);
-                  }
-                  iwv = a;
-                } else {
-                  iwv = sample_global_slow<C>(tctl[sidx].I2, tcv->pitch, nx, ny, cx, cy, ch, wxs[0], wxs[1], wxs[2], wxs[3], wys[0], wys[1], wys[2], wys[3]);
-                }
-                const bool valid = iwv == iwv;             // NaN footprint
-                iwv = fminf(fmaxf(iwv, lo), hi);           // clip (only used when valid)
-                const float i1c = c1[ch];
-                const float gx = gxok ? 0.5f * (c1[ch + C] - c1[ch - C]) : 0.0f;
-                const float gy = gyok ? 0.5f * (c1[ch + S1W] - c1[ch - S1W]) : 0.0f;
-                const float di = valid ? iwv - i1c : 0.0f; // non-finite -> 0 (io.py:72, 134)
-                if (need_hr) { sxx = fmaf(gx, gx, sxx); sxy = fmaf(gx, gy, sxy); syy = fmaf(gy, gy, syy); }
-                vx = fmaf(gx, di, vx); vy = fmaf(gy, di, vy);
-                t2 = fmaf(di, di, t2);
-              }
-              const float rho = robust ? rho_prime(t2 * chm, tcv->lambda2, rtype) : 1.0f;
-              add_moments(rho * chm, sxx, sxy, syy, vx, vy, (float)x);
-            }
-          }
-        }
-      }
-      pair = tcv->pair; chunk = tcv->chunk; nch = tcv->nch; s = tcv->scale; nx = tcv->nx; ny = tcv->ny;
-      need_h = tcv->need_h != 0; last = tcv->last != 0;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[sidx]);   // this warp is done with the stage (and its TileCtl)
-      ++k;
-    } while (!last);
-    if (stop) break;
-    if (vrow >= 0) flush_row();   // the chunk's last row segment
-    ++nitems;
-    ICA_STAMP(2);
-    const long long e0 = dbg ? clock64() : 0;
-
-    // ---------------- chunk partial: [K][kYPow] doubles, warps summed in fixed order.  One barrier per chunk: the
-    // next chunk accumulates into the other set, and this set is only zeroed again after the next chunk's barrier,
-    // which the summing threads reach after they are done with it.
-    consumer_sync();
-    {
-      const double* accs = accs0 + (nitems & 1 ? 0 : kAccSet);   // nitems was just incremented: the set of this chunk
-      double* out = P.partials + ((long long)pair * P.max_chunks + chunk) * kAccStride;
-      for (int i = tid; i < NENT; i += kConsumerThreads) {
-        double sum = 0.0;
-#pragma unroll
-        for (int w = 0; w < kConsumerWarps; ++w) sum += accs[w * NENT + i];
-        out[i] = sum;
-      }
-    }
-    myacc += (nitems & 1) ? kAccSet : -kAccSet;     // the other set for the next chunk
-    if (dbg) dbg_epi += clock64() - e0;
-  }
-  if (dbg) {
-    long long* d = P.dbg_time + blockIdx.x * 16;
-    d[3] = dbg_wait; d[4] = dbg_epi; d[5] = 0; d[6] = clock64() - dbg_t0; d[15] = k;
-  }
-  if (P.dbg_time && tid == 32) { P.dbg_time[blockIdx.x * 16 + 13] = gtime(); P.dbg_time[blockIdx.x * 16 + 14] = nitems; }
-  if (tid == 32) atomicMax(reinterpret_cast<long long*>(&P.tstamp[1]), gtime());
-}
-
-// Work list of the next launch: chunk_start[b] = exclusive prefix sum of chunks per pair,
-// chunk_start[B] = total, item_pair[i] = pair of work item i; also publishes the number of
-// unfinished pairs.  Executed by one whole block (any size that is a multiple of 32, <= 1024).
-__device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal, bool first) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nthr = blockDim.x, nwarp = nthr >> 5;
+// Work list of the NEXT iteration into the buffer `np`: chunk_start[b] = exclusive prefix sum of chunks per pair,
+// chunk_start[B] = total, item_pair[i] = pair of work item i; publishes the number of unfinished pairs, advances the
+// iteration counter (which selects the buffer the next launch reads) and sets the condition of the CUDA-graph while
+// node.  Executed by `nthr` threads (a multiple of 32, <= 1024) that share `sync`.
+template <typename Sync>
+__device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal, bool first, int tid, int nthr, Sync sync) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const int nwarp = nthr >> 5;
   const int B = P.B;
-  if (tid == 0) { s_scal[0] = 0; s_scal[1] = 0; }   // carry, active pairs
-  __syncthreads();
+  const int cnt_old = first ? -1 : __ldcg(P.loop_count);
+  const int np = (cnt_old + 1) & 1;
+  int* const chunk_start = P.chunk_start + (long long)np * (B + 1);
+  int* const item_pair = P.item_pair + (long long)np * B * P.max_chunks;
+  if (tid == 0) { s_scal[0] = 0; s_scal[1] = 0; s_scal[2] = 0; }   // carry, active pairs, pairs with work
+  sync();
   for (int base = 0; base < B; base += nthr) {
     const int b = base + tid;
     int c = 0;
@@ -603,11 +359,12 @@ __device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal, bo
       act = s >= 0;
     }
     const unsigned actmask = __ballot_sync(0xffffffffu, act);
+    const unsigned workmask = __ballot_sync(0xffffffffu, c > 0);
     int incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
     if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
+    sync();
     if (warp == 0) {
       const int w = lane < nwarp ? s_warp[lane] : 0;
       int wi = w;
@@ -615,77 +372,85 @@ __device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal, bo
       for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
       s_warp[lane] = wi - w;   // exclusive
     }
-    __syncthreads();
+    sync();
     const int excl = s_scal[0] + s_warp[warp] + incl - c;
-    if (b < B) P.chunk_start[b] = excl;
+    if (b < B) chunk_start[b] = excl;
     // the items of a pair are written by the whole warp (up to 256-1024 per pair: one thread would take microseconds)
 #pragma unroll 1
     for (int src = 0; src < 32; ++src) {
       const int cb = __shfl_sync(0xffffffffu, c, src), eb = __shfl_sync(0xffffffffu, excl, src);
-      for (int i = lane; i < cb; i += 32) P.item_pair[eb + i] = base + (warp << 5) + src;
+      for (int i = lane; i < cb; i += 32) item_pair[eb + i] = base + (warp << 5) + src;
     }
     if (lane == 0 && actmask) atomicAdd(&s_scal[1], __popc(actmask));
-    __syncthreads();
+    if (lane == 0 && workmask) atomicAdd(&s_scal[2], __popc(workmask));
+    sync();
     if (tid == nthr - 1) s_scal[0] = excl + c;
-    __syncthreads();
+    sync();
   }
+  __threadfence();     // the list is complete before the header and the iteration counter announce it
+  sync();
   if (tid == 0) {
-    P.chunk_start[B] = s_scal[0];
+    chunk_start[B] = s_scal[0];
     *P.n_active = s_scal[1];
-    // device-side bookkeeping of the loop: iterations done, time spent in the iterate kernel, and the
-    // condition of the CUDA-graph while node (no host round trip until every pair has converged)
+    SchedHdr* hn = P.hdr + np;
+    hn->total = s_scal[0]; hn->npairs = s_scal[2]; hn->counter = 0;
+    hn->t0 = 0x7fffffffffffffffll; hn->t1 = 0;
+    // device-side bookkeeping of the loop: iterations done, time spent in the streaming phase of the iterate kernel
     int cnt = 0;
-    if (first) { *P.loop_count = 0; P.kernel_ns[0] = 0; P.kernel_ns[1] = 0; }
+    if (first) { P.kernel_ns[0] = 0; P.kernel_ns[1] = 0; }
     else {
-      cnt = *P.loop_count + 1; *P.loop_count = cnt;
-      const long long t0 = P.tstamp[0], t1 = P.tstamp[1];
+      cnt = cnt_old + 1;
+      const SchedHdr* ho = P.hdr + (cnt_old & 1);
+      const long long t0 = __ldcg(&ho->t0), t1 = __ldcg(&ho->t1);
       if (t1 > t0 && t1 > 0) { P.kernel_ns[0] += t1 - t0; P.kernel_ns[1] += 1; }
     }
-    P.tstamp[0] = 0x7fffffffffffffffll; P.tstamp[1] = 0;
-    *P.work_counter = 0;
+    *P.solve_ticket = 0;
+    __threadfence();
+    *P.loop_count = cnt;
+    // the condition of the CUDA-graph while node: no host round trip until every pair has converged
     if (!first && P.cond_handle) cudaGraphSetConditional(P.cond_handle, (s_scal[1] > 0 && cnt < P.max_launches) ? 1u : 0u);
   }
 }
 
-__global__ void __launch_bounds__(1024) ica_schedule_kernel(const IterParams P) {
+__global__ void __launch_bounds__(1024) ica_schedule_kernel(const __grid_constant__ IterParams P) {
   __shared__ int s_warp[32];
-  __shared__ int s_scal[2];
-  schedule_block(P, s_warp, s_scal, true);
+  __shared__ int s_scal[4];
+  schedule_block(P, s_warp, s_scal, true, (int)threadIdx.x, (int)blockDim.x, SyncBlock());
 }
 
+// K3: sums a pair's chunk partials in a fixed order, assembles H and b, de.inverse_hessian + io.parametric_solve +
+// tr.update_transform, the lambda schedule, the stopping rule and zm.zoom_in_parameters at a scale change
+// (ica.py:223-259, 102-131).  NW warps of the calling block take part (tid in [0, 32 NW)); s_part is scratch for
+// NW x NENT doubles.  Returns false when the caller must not go on to the scheduling step (row-sharded mode 1).
+struct SolveShared {
+  double mom[kAccStride];
+  double aug[ICA_MAX_PARAMS][2 * ICA_MAX_PARAMS + 1];
+  double vec[2 * ICA_MAX_PARAMS];
+  PairState st;                    // the pair's state is staged here and written back once
+  int warp_scan[32];
+  int scal[4];
+  unsigned int ticket;
+};
 
-// K3: one block per image pair, after the iterate kernel: sums the pair's chunk partials in a fixed
-// order, assembles H and b, de.inverse_hessian + io.parametric_solve + tr.update_transform, the
-// lambda schedule, the stopping rule and zm.zoom_in_parameters at a scale change
-// (ica.py:223-259, 102-131).  The last block to finish builds the work list of the next
-// iteration (what ica_schedule_kernel does for the first one), so an iteration is two launches.
-constexpr int kSolveThreads = 512;
-constexpr int kSolveWarps = kSolveThreads / 32;
-
-template <int DH>
-__global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterParams P) {
+template <int DH, int NW, typename Sync>
+__device__ bool solve_pair(const IterParams& P, int pair, int tid, double* s_part, SolveShared& sh, Sync sync, bool stamp) {
   constexpr int K = RowVals<DH>::K;
   constexpr int HW = DH + 1;
   constexpr int NENT = K * kYPow;
   constexpr int kStateWords = (int)(sizeof(PairState) / 8);
   static_assert(sizeof(PairState) % 8 == 0, "PairState is copied as 8-byte words");
-  __shared__ double s_part[kSolveWarps * NENT];
-  __shared__ double s_mom[kAccStride];
-  __shared__ double s_aug[ICA_MAX_PARAMS][2 * ICA_MAX_PARAMS + 1];
-  __shared__ double s_vec[2 * ICA_MAX_PARAMS];
-  __shared__ __align__(8) PairState s_st;       // the pair's state is staged here and written back once
-  __shared__ int s_warp[32];
-  __shared__ int s_scal[2];
-  __shared__ unsigned int s_ticket;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int pair = blockIdx.x;
-#define SOLVE_STAMP(slot) do { if (P.dbg_time && blockIdx.x == 0 && tid == 0) P.dbg_time[(long long)P.dbg_row * 16 + (slot)] = gtime(); } while (0)
+  static_assert(NW * 32 >= kAccStride && NW * 32 >= kStateWords, "one thread per moment / state word");
+  double* const s_mom = sh.mom;
+  double (*s_aug)[2 * ICA_MAX_PARAMS + 1] = sh.aug;
+  double* const s_vec = sh.vec;
+  const int lane = tid & 31, warp = tid >> 5;
+#define SOLVE_STAMP(slot) do { if (kTimeline && stamp && P.dbg_time && tid == 0) P.dbg_time[(long long)P.dbg_row * 16 + (slot)] = gtime(); } while (0)
   SOLVE_STAMP(0);
   if (tid < kStateWords)
-    reinterpret_cast<unsigned long long*>(&s_st)[tid] = __ldcg(reinterpret_cast<const unsigned long long*>(&P.state[pair]) + tid);
-  __syncthreads();
+    reinterpret_cast<unsigned long long*>(&sh.st)[tid] = __ldcg(reinterpret_cast<const unsigned long long*>(&P.state[pair]) + tid);
+  sync();
   SOLVE_STAMP(1);
-  PairState& st = s_st;
+  PairState& st = sh.st;
   const int s = st.scale;
   const bool robust = P.robust_loop != 0;
   if (s >= 0) {   // the pair took part in the iteration that just ran
@@ -705,10 +470,10 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
     }
     if (P.solve_mode == 2) {   // row-sharded: the moments were summed over ranks by the caller's allreduce
       if (tid < NENT) s_mom[tid] = P.ext_moments[(long long)pair * kAccStride + tid];
-      __syncthreads();
+      sync();
     } else {
       // fixed summation order: warp w sums its contiguous range of chunks, then warps in order
-      const int c0 = (int)((long long)warp * nch / kSolveWarps), c1 = (int)((long long)(warp + 1) * nch / kSolveWarps);
+      const int c0 = (int)((long long)warp * nch / NW), c1 = (int)((long long)(warp + 1) * nch / NW);
       const double* src = P.partials + (long long)pair * P.max_chunks * kAccStride;
       constexpr int NJ = (NENT + 31) / 32;
       constexpr int UN = 8;                                    // chunks in flight per lane
@@ -736,20 +501,20 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
       }
 #pragma unroll
       for (int j = 0; j < NJ; ++j) { const int e = lane + 32 * j; if (e < NENT) s_part[warp * NENT + e] = sum[j]; }
-      __syncthreads();
+      sync();
       if (tid < NENT) {
         double tsum = 0.0;
 #pragma unroll
-        for (int w = 0; w < kSolveWarps; ++w) tsum += s_part[w * NENT + tid];
+        for (int w = 0; w < NW; ++w) tsum += s_part[w * NENT + tid];
         // quadratic loop after the first iteration of a scale: the H moments were not gathered
         s_mom[tid] = (!need_h && tid < 3 * HW * kYPow) ? 0.0 : tsum;
       }
-      __syncthreads();
+      sync();
     }
     SOLVE_STAMP(2);
     if (P.solve_mode == 1) {   // row-sharded: publish this rank's moment sums and stop
       if (tid < kAccStride) P.ext_moments[(long long)pair * kAccStride + tid] = tid < NENT ? s_mom[tid] : 0.0;
-      return;
+      return false;
     }
     if (warp == 0) {   // the n x n part is one warp's job
       // assemble H (n x n) and b (n): every entry is a fixed +-1 combination of at most 4 moments
@@ -863,35 +628,431 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const IterPara
         }
       }
     }
-    __syncthreads();
+    sync();
     SOLVE_STAMP(5);
     if (!P.dbg_Hb && tid < kStateWords)
-      reinterpret_cast<unsigned long long*>(&P.state[pair])[tid] = reinterpret_cast<const unsigned long long*>(&s_st)[tid];
+      reinterpret_cast<unsigned long long*>(&P.state[pair])[tid] = reinterpret_cast<const unsigned long long*>(&sh.st)[tid];
   }
   else if (P.solve_mode == 1) {
     if (tid < kAccStride) P.ext_moments[(long long)pair * kAccStride + tid] = 0.0;
+    return false;
+  }
+  return true;
+#undef SOLVE_STAMP
+}
+
+// After a pair's solve: the caller whose pair completes the iteration (`expected` solves) builds the next work list.
+template <typename Sync>
+__device__ void finish_iteration(const IterParams& P, SolveShared& sh, unsigned expected, int tid, int nthr, Sync sync) {
+  __threadfence();      // the pair's new state is visible before the ticket
+  sync();
+  if (tid == 0) sh.ticket = atomicAdd(P.solve_ticket, 1u);
+  sync();
+  if (sh.ticket != expected - 1) return;
+  __threadfence();
+  schedule_block(P, sh.warp_scan, sh.scal, false, tid, nthr, sync);
+}
+
+// The fused tail of the iterate kernel, out of line: its register needs (fp64 Gauss-Jordan, compositions) must not
+// leak into the allocation of the per-pixel loop.
+template <int DH>
+__device__ __noinline__ void fused_tail(const IterParams& P, int pair, int tid, double* scratch, SolveShared* sh, unsigned expected) {
+  solve_pair<DH, kConsumerWarps>(P, pair, tid, scratch, *sh, SyncConsumers(), false);
+  finish_iteration(P, *sh, expected, tid, kConsumerThreads, SyncConsumers());
+}
+
+constexpr int kSolveThreads = 512;
+constexpr int kSolveWarps = kSolveThreads / 32;
+
+// Stand-alone K3: one block per image pair, launched after the iterate kernel (host-driven loop, row-sharded mode,
+// parity hooks).  The last block to finish builds the work list of the next iteration.
+template <int DH>
+__global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const __grid_constant__ IterParams P) {
+  constexpr int NENT = RowVals<DH>::K * kYPow;
+  __shared__ double s_part[kSolveWarps * NENT];
+  __shared__ __align__(8) SolveShared sh;
+  const int tid = threadIdx.x;
+  if (!solve_pair<DH, kSolveWarps>(P, (int)blockIdx.x, tid, s_part, sh, SyncBlock(), blockIdx.x == 0)) return;
+  finish_iteration(P, sh, gridDim.x, tid, kSolveThreads, SyncBlock());
+}
+
+// ============================================================ the kernel
+template <int C, int DH>
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(const __grid_constant__ IterParams P) {
+  constexpr int K = RowVals<DH>::K;
+  constexpr int HW = DH + 1;        // x-powers kept for the Hessian moments
+  constexpr int BWN = DH / 2 + 1;   // x-powers kept for the b moments
+  constexpr int S1W = Stage<C>::S1W;
+  constexpr int S2W = Stage<C>::S2W;
+  constexpr int NENT = K * kYPow;
+  constexpr int kStages = Stage<C>::kStages;
+
+  extern __shared__ __align__(128) float smem[];
+  float* const stages = smem;                      // kStages x Stage<C>::kFloats
+  __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages];
+  __shared__ TileCtl tctl[kStages];
+  __shared__ double s_pm64[9];
+  __shared__ __align__(8) SolveShared s_solve;     // fused solve / scheduling (the CTA that finishes a pair's last chunk)
+  __shared__ int s_par, s_last;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  // which of the two work lists this launch consumes: one thread decides for the CTA (with the fused solve the counter
+  // can advance while a late CTA of the same launch starts; such a CTA simply works on the next iteration's list)
+  if (tid == 0) {
+    s_par = __ldcg(P.loop_count) & 1;
+    for (int i = 0; i < kStages; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], kConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int par = s_par;
+  SchedHdr* const hdr = P.hdr + par;
+  if ((int)blockIdx.x >= __ldcg(&hdr->total)) return;
+  if (tid == 0) atomicMin(&hdr->t0, gtime());
+
+  if (warp == kConsumerWarps) {
+    producer_loop<C>(P, stages, Stage<C>::kFloats, s_full, s_empty, tctl, s_pm64, par, lane);
     return;
   }
-  // ---- the last block builds the next work list
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_ticket = atomicAdd(P.solve_ticket, 1u);
-  __syncthreads();
-  if (s_ticket != gridDim.x - 1) return;
-  __threadfence();
-  SOLVE_STAMP(6);
-  schedule_block(P, s_warp, s_scal, false);
-  if (tid == 0) *P.solve_ticket = 0;
-  SOLVE_STAMP(7);
+
+  // ------------------------------------------------------------------ consumers
+  const int delta = P.delta;
+  const bool frame = P.frame != 0;
+  const bool robust = P.robust_loop != 0;
+  const float chm = P.ch_mult;
+  const int rtype = P.robust_type;
+  // fp64 accumulators of the chunk in progress, double-buffered over consecutive chunks: [2][kConsumerWarps][K][kYPow]
+  double* const accs0 = reinterpret_cast<double*>(smem + kStages * Stage<C>::kFloats);
+  constexpr int kAccSet = kConsumerWarps * K * kYPow;
+  // the transposing reduction leaves moment k on the lanes k << kTrShift .. ; the first of them owns the fp64 accumulators
+  constexpr int kTrN = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
+  constexpr int kTrShift = kTrN == 8 ? 2 : (kTrN == 16 ? 1 : 0);
+  const int midx = lane >> kTrShift;
+  const bool mown = (lane & ((1 << kTrShift) - 1)) == 0 && midx < K;
+  double* myacc = accs0 + (warp * K + (mown ? midx : 0)) * kYPow;    // this lane's slot in the current set
+  unsigned k = 0;
+  int nitems = 0;
+  const bool dbg = kTimeline && P.dbg_time != nullptr && tid == 0;       // profiling hook: cycles warp 0 spends waiting / in chunk epilogues
+  long long dbg_wait = 0, dbg_epi = 0;
+  const long long dbg_t0 = dbg ? clock64() : 0;
+
+  if (kTimeline && P.dbg_time && tid == 0) P.dbg_time[blockIdx.x * 16 + 0] = gtime();
+  // Per-lane x-moment accumulators of the image row `vrow` (-1: empty).  Consecutive tiles of a chunk usually lie on
+  // the same tile row, so a warp keeps adding pixels of the same image row and pays the cross-lane reduction and
+  // the fp64 fold once per row segment of the chunk instead of once per tile.
+  float v[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) v[i] = 0.0f;
+  int vrow = -1;
+  // once per row segment: a transposing shuffle reduction leaves the row's moment k on the lane that owns it (fixed
+  // summation order), which folds in y^b in fp64; the fp64 accumulators live in shared memory
+  auto flush_row = [&]() {
+    float t32[kTrN];
+#pragma unroll
+    for (int i = 0; i < kTrN; ++i) t32[i] = i < K ? v[i] : 0.0f;
+#pragma unroll
+    for (int i = 0; i < K; ++i) v[i] = 0.0f;
+    const float tot = warp_transpose_reduce<kTrN>(t32, lane);
+    if (mown) {
+      const double yd = (double)vrow, t = (double)tot;
+      double yp = 1.0;
+#pragma unroll
+      for (int b = 0; b < kYPow; ++b) { myacc[b] = fma(t, yp, myacc[b]); yp *= yd; }
+    }
+    vrow = -1;
+  };
+  for (int it = 0;; ++it) {
+    if (mown) {
+#pragma unroll
+      for (int b = 0; b < kYPow; ++b) myacc[b] = 0.0;
+    }
+    int pair = 0, chunk = 0, nch = 1;
+    bool last;
+    bool stop = false;
+    do {
+      const int sidx = k % kStages;
+      const long long w0 = dbg ? clock64() : 0;
+      mbar_wait(&s_full[sidx], (k / kStages) & 1);
+      if (dbg) dbg_wait += clock64() - w0;
+      const TileCtl* tc = &tctl[sidx];
+      {
+        const int4 flg = lds_i4(&tc->flg);             // need_h, last, stop, pitch
+        if (flg.z) { stop = true; break; }             // uniform: the producer ran out of work
+        last = flg.y != 0;
+      }
+      if (k == 0) ICA_STAMP(1);
+      const float* s2 = stages + sidx * Stage<C>::kFloats;
+      const float* s1 = s2 + BH_MAX * S2W;
+#pragma unroll 1
+      for (int rr = 0; rr < TH / kConsumerWarps; ++rr) {
+        const int ly = warp + rr * kConsumerWarps;
+        const int4 geo = lds_i4(&tc->geo);             // x0, y0, nx, ny
+        const int y = geo.y + ly;
+        if (vrow >= 0 && vrow != y) flush_row();
+        if (y < geo.w) {
+          vrow = y;
+          const int nx = geo.z, ny = geo.w;
+          const bool need_hr = lds_i4(&tc->flg).x != 0;
+          // moments of one pixel: v[] += (rho' S, rho' v) * x^a.  Consecutive powers share a packed FFMA2 (the weight
+          // is its broadcast operand): element by element the same fmaf as the scalar form.
+          auto add_moments = [&](float scl, float sxx, float sxy, float syy, float vx, float vy, float xf) {
+            const float x2 = xf * xf;
+            const float2 xp01 = make_float2(1.0f, xf);
+            const float2 xp23 = make_float2(x2, x2 * xf);
+            const float x4 = x2 * x2;
+            auto acc = [&](int base, int npow, float w) {
+              const float2 w2 = make_float2(w, w);
+              if (npow >= 2) {
+                const float2 r = __ffma2_rn(w2, xp01, make_float2(v[base], v[base + 1]));
+                v[base] = r.x; v[base + 1] = r.y;
+              } else {
+                v[base] = fmaf(w, 1.0f, v[base]);
+              }
+              if (npow == 3) v[base + 2] = fmaf(w, x2, v[base + 2]);
+              if (npow >= 4) {
+                const float2 r = __ffma2_rn(w2, xp23, make_float2(v[base + 2], v[base + 3]));
+                v[base + 2] = r.x; v[base + 3] = r.y;
+              }
+              if (npow == 5) v[base + 4] = fmaf(w, x4, v[base + 4]);
+            };
+            if (need_hr) {
+              acc(0 * HW, HW, scl * sxx); acc(1 * HW, HW, scl * sxy); acc(2 * HW, HW, scl * syy);
+            }
+            acc(3 * HW, BWN, scl * vx); acc(3 * HW + BWN, BWN, scl * vy);
+          };
+          // ---- the lane's two pixels A = (x0+lane, y), B = (x0+32+lane, y): projection in packed fp32 (same
+          // arithmetic per pixel as project_px; no validity test: a staged window implies z > 0 and bounded
+          // displacements over the whole tile, and lanes without a window take the generic path below)
+          const int xA = geo.x + lane, xB = xA + 32;
+          int cxA, cyA, cxB, cyB;
+          float2 tx2, ty2;
+          {
+            const float4 q0 = lds_f4(&tc->c2[0]), q1 = lds_f4(&tc->c2[2]), q2 = lds_f4(&tc->c2[4]), q3 = lds_f4(&tc->c2[6]);
+            const float fy = (float)y, fxa = (float)xA;
+            const float2 fy2 = make_float2(fy, fy), nfy2 = make_float2(-fy, -fy);
+            const float2 fx2 = make_float2(fxa, fxa + 32.0f), nfx2 = make_float2(-fxa, -(fxa + 32.0f));
+            const float2 zm1 = __ffma2_rn(make_float2(q3.x, q3.y), fx2, __fmul2_rn(make_float2(q3.z, q3.w), fy2));
+            float2 nx_ = __ffma2_rn(make_float2(q0.x, q0.y), fx2, __ffma2_rn(make_float2(q0.z, q0.w), fy2, make_float2(q1.x, q1.y)));
+            float2 ny_ = __ffma2_rn(make_float2(q1.z, q1.w), fx2, __ffma2_rn(make_float2(q2.x, q2.y), fy2, make_float2(q2.z, q2.w)));
+            nx_ = __ffma2_rn(nfx2, zm1, nx_);
+            ny_ = __ffma2_rn(nfy2, zm1, ny_);
+            const float zA = 1.0f + zm1.x, zB = 1.0f + zm1.y;
+            const float2 rz = make_float2(fast_rcp(zA), fast_rcp(zB));
+            const float2 dx2 = __fmul2_rn(nx_, rz), dy2 = __fmul2_rn(ny_, rz);
+            const float flxA = floorf(dx2.x), flxB = floorf(dx2.y), flyA = floorf(dy2.x), flyB = floorf(dy2.y);
+            tx2 = make_float2(dx2.x - flxA, dx2.y - flxB);
+            ty2 = make_float2(dy2.x - flyA, dy2.y - flyB);
+            cxA = xA + (int)flxA; cxB = xB + (int)flxB; cyA = y + (int)flyA; cyB = y + (int)flyB;
+            // tie band of project_px, one test for both pixels (the wider of the two bands)
+            const float amax = fmaxf(fabsf(dx2.x) + fabsf(dy2.x), fabsf(dx2.y) + fabsf(dy2.y));
+            const float kTie = fmaf(1.0e-6f, amax, 2.5e-4f);
+            const float tmin = fminf(fminf(tx2.x, tx2.y), fminf(ty2.x, ty2.y));
+            const float tmax = fmaxf(fmaxf(tx2.x, tx2.y), fmaxf(ty2.x, ty2.y));
+            if (tmin < kTie || tmax > 1.0f - kTie) {
+              // (rare) a coordinate next to an integer: the exact fp64 evaluation decides the tap set
+              WarpCoef coef;
+              coef.d00 = q0.x; coef.m01 = q0.z; coef.m02 = q1.x; coef.m10 = q1.z; coef.d11 = q2.x; coef.m12 = q2.z; coef.m20 = q3.x; coef.m21 = q3.z;
+              float a, b;
+              project_px(coef, tc->m64, xA, y, cxA, cyA, a, b); tx2.x = a; ty2.x = b;
+              project_px(coef, tc->m64, xB, y, cxB, cyB, a, b); tx2.y = a; ty2.y = b;
+            }
+          }
+          bool insmA, insmB;
+          int offA, offB;    // float offsets of the first tap inside the staged I2 window
+          {
+            const int4 win = lds_i4(&tc->win);   // bx0, by0, bw - 3, bh - 3 (0, 0 without a window)
+            // 0 <= c - 1 - b0 <= extent - 4, as one unsigned comparison per axis
+            const int oxA = cxA - 1 - win.x, oyA = cyA - 1 - win.y, oxB = cxB - 1 - win.x, oyB = cyB - 1 - win.y;
+            insmA = (unsigned)oxA < (unsigned)win.z && (unsigned)oyA < (unsigned)win.w;
+            insmB = (unsigned)oxB < (unsigned)win.z && (unsigned)oyB < (unsigned)win.w;
+            offA = oyA * S2W + oxA * C;
+            offB = oyB * S2W + oxB * C;
+          }
+          const bool fastlane = insmA && insmB && xB < nx;
+          if (__all_sync(0xffffffffu, fastlane)) {
+            // ===== straight-line path: both pixels in one instruction stream, packed fp32 (FFMA2)
+            // phase 1: the 2 x 16 taps of every channel -> warped values (few live registers besides the loads)
+            float2 iw[C];
+            {
+              float2 wx[4], wy[4];
+              keys_weights2(tx2, wx[0], wx[1], wx[2], wx[3]);
+              keys_weights2(ty2, wy[0], wy[1], wy[2], wy[3]);
+              const float* tA = s2 + offA;
+              const float* tB = s2 + offB;
+#pragma unroll
+              for (int ch = 0; ch < C; ++ch) {
+                float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float* rA = tA + q * S2W + ch;
+                  const float* rB = tB + q * S2W + ch;
+                  float2 h = __fmul2_rn(wx[0], make_float2(rA[0], rB[0]));
+                  h = __ffma2_rn(wx[1], make_float2(rA[C], rB[C]), h);
+                  h = __ffma2_rn(wx[2], make_float2(rA[2 * C], rB[2 * C]), h);
+                  h = __ffma2_rn(wx[3], make_float2(rA[3 * C], rB[3 * C]), h);
+                  acc2 = __ffma2_rn(wy[q], h, acc2);
+                }
+                iw[ch] = acc2;
+              }
+            }
+            // phase 2: residual, gradient of I1 (masks fold the 1/2, the frame and the image border), S, v
+            float2 mgx, mgy;
+            {
+              const int4 msk = lds_i4(&tc->msk);   // gxlo, gxspan, fxlo, fxspan
+              const bool yin = !frame || (y >= delta && y < ny - delta);
+              const bool gyrow = yin && y >= 1 && y <= ny - 2;
+              mgx = make_float2((yin && (unsigned)(xA - msk.x) < (unsigned)msk.y) ? 0.5f : 0.0f,
+                                (yin && (unsigned)(xB - msk.x) < (unsigned)msk.y) ? 0.5f : 0.0f);
+              mgy = make_float2((gyrow && (unsigned)(xA - msk.z) < (unsigned)msk.w) ? 0.5f : 0.0f,
+                                (gyrow && (unsigned)(xB - msk.z) < (unsigned)msk.w) ? 0.5f : 0.0f);
+            }
+            const float2 nmgx = make_float2(-mgx.x, -mgx.y), nmgy = make_float2(-mgy.x, -mgy.y);
+            const float* cA = s1 + (ly + 1) * S1W + (lane + HALO) * C;
+            const float* cB = cA + 32 * C;
+            const float4 fl = lds_f4(&tc->fl);     // lo, hi, lambda^2
+            float2 sxx = make_float2(0.f, 0.f), sxy = sxx, syy = sxx, vx = sxx, vy = sxx, t2 = sxx;
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+              const bool vA = iw[ch].x == iw[ch].x, vB = iw[ch].y == iw[ch].y;   // NaN footprint
+              const float iwA = fminf(fmaxf(iw[ch].x, fl.x), fl.y), iwB = fminf(fmaxf(iw[ch].y, fl.x), fl.y);
+              const float2 gx = __ffma2_rn(make_float2(cA[ch + C], cB[ch + C]), mgx, __fmul2_rn(make_float2(cA[ch - C], cB[ch - C]), nmgx));
+              const float2 gy = __ffma2_rn(make_float2(cA[ch + S1W], cB[ch + S1W]), mgy, __fmul2_rn(make_float2(cA[ch - S1W], cB[ch - S1W]), nmgy));
+              const float2 di = make_float2(vA ? iwA - cA[ch] : 0.0f, vB ? iwB - cB[ch] : 0.0f);   // non-finite -> 0 (io.py:72, 134)
+              if (need_hr) { sxx = __ffma2_rn(gx, gx, sxx); sxy = __ffma2_rn(gx, gy, sxy); syy = __ffma2_rn(gy, gy, syy); }
+              vx = __ffma2_rn(gx, di, vx); vy = __ffma2_rn(gy, di, vy);
+              t2 = __ffma2_rn(di, di, t2);
+            }
+            // phase 3: robust weight and moments.  A gray image stands for its x3 replication
+            // (SURVEY Q12): every channel sum triples
+            const float rhoA = robust ? rho_prime(t2.x * chm, fl.z, rtype) : 1.0f;
+            const float rhoB = robust ? rho_prime(t2.y * chm, fl.z, rtype) : 1.0f;
+            add_moments(rhoA * chm, sxx.x, sxy.x, syy.x, vx.x, vy.x, (float)xA);
+            add_moments(rhoB * chm, sxx.y, sxy.y, syy.y, vx.y, vy.y, (float)xB);
+          } else {
+            // ===== generic path: image edges, windows that do not fit, degenerate projections
+            const bool yin = !frame || (y >= delta && y < ny - delta);
+            const int4 win = lds_i4(&tc->win);
+            const float4 fl = lds_f4(&tc->fl);
+            WarpCoef coef;
+            coef.d00 = tc->c2[0].x; coef.m01 = tc->c2[1].x; coef.m02 = tc->c2[2].x; coef.m10 = tc->c2[3].x;
+            coef.d11 = tc->c2[4].x; coef.m12 = tc->c2[5].x; coef.m20 = tc->c2[6].x; coef.m21 = tc->c2[7].x;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+              const int x = half ? xB : xA;
+              if (x >= nx) continue;
+              const int lx = lane + half * 32;
+              int cx, cy; float tx, ty;
+              const bool pok = project_px(coef, tc->m64, x, y, cx, cy, tx, ty);
+              const int ox = cx - 1 - win.x, oy = cy - 1 - win.y;
+              const bool insm = (unsigned)ox < (unsigned)win.z && (unsigned)oy < (unsigned)win.w;
+              float wxs[4], wys[4];
+              keys_weights(tx, wxs[0], wxs[1], wxs[2], wxs[3]);
+              keys_weights(ty, wys[0], wys[1], wys[2], wys[3]);
+              const bool inframe = yin && (!frame || (x >= delta && x < nx - delta));
+              const float* t2base = s2 + oy * S2W + ox * C;
+              const float* c1 = s1 + (ly + 1) * S1W + (lx + HALO) * C;
+              const bool gxok = inframe && x >= 1 && x <= nx - 2;
+              const bool gyok = inframe && y >= 1 && y <= ny - 2;
+              const float lo = fl.x, hi = fl.y;
+              float sxx = 0.f, sxy = 0.f, syy = 0.f, vx = 0.f, vy = 0.f, t2 = 0.f;
+#pragma unroll
+              for (int ch = 0; ch < C; ++ch) {
+                float iwv;
+                if (!pok) {
+                  iwv = __int_as_float(0x7fc00000);
+                } else if (insm) {
+                  float a = 0.0f;
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float* r = t2base + q * S2W + ch;
+                    float hsum = wxs[0] * r[0] + wxs[1] * r[C] + wxs[2] * r[2 * C] + wxs[3] * r[3 * C];
+                    a = fmaf(wys[q], hsum, a);
+                  }
+                  iwv = a;
+                } else {
+                  iwv = sample_global_slow<C>(tc->I2, lds_i4(&tc->flg).w, nx, ny, cx, cy, ch, wxs[0], wxs[1], wxs[2], wxs[3], wys[0], wys[1], wys[2], wys[3]);
+                }
+                const bool valid = iwv == iwv;             // NaN footprint
+                iwv = fminf(fmaxf(iwv, lo), hi);           // clip (only used when valid)
+                const float i1c = c1[ch];
+                const float gx = gxok ? 0.5f * (c1[ch + C] - c1[ch - C]) : 0.0f;
+                const float gy = gyok ? 0.5f * (c1[ch + S1W] - c1[ch - S1W]) : 0.0f;
+                const float di = valid ? iwv - i1c : 0.0f; // non-finite -> 0 (io.py:72, 134)
+                if (need_hr) { sxx = fmaf(gx, gx, sxx); sxy = fmaf(gx, gy, sxy); syy = fmaf(gy, gy, syy); }
+                vx = fmaf(gx, di, vx); vy = fmaf(gy, di, vy);
+                t2 = fmaf(di, di, t2);
+              }
+              const float rho = robust ? rho_prime(t2 * chm, fl.z, rtype) : 1.0f;
+              add_moments(rho * chm, sxx, sxy, syy, vx, vy, (float)x);
+            }
+          }
+        }
+      }
+      if (last) { pair = tc->pair; chunk = tc->chunk; nch = tc->nch; }   // (before the stage and its TileCtl are released)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sidx]);   // this warp is done with the stage (and its TileCtl)
+      ++k;
+    } while (!last);
+    if (stop) break;
+    if (vrow >= 0) flush_row();   // the chunk's last row segment
+    ++nitems;
+    ICA_STAMP(2);
+    const long long e0 = dbg ? clock64() : 0;
+
+    // ---------------- chunk partial: [K][kYPow] doubles, warps summed in fixed order.  One barrier per chunk: the
+    // next chunk accumulates into the other set, and this set is only zeroed again after the next chunk's barrier,
+    // which the summing threads reach after they are done with it.
+    consumer_sync();
+    {
+      const double* accs = accs0 + (nitems & 1 ? 0 : kAccSet);   // nitems was just incremented: the set of this chunk
+      double* out = P.partials + ((long long)pair * P.max_chunks + chunk) * kAccStride;
+      for (int i = tid; i < NENT; i += kConsumerThreads) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; ++w) sum += accs[w * NENT + i];
+        out[i] = sum;
+      }
+    }
+    myacc += (nitems & 1) ? kAccSet : -kAccSet;     // the other set for the next chunk
+    if (tid == 0) atomicMax(&hdr->t1, gtime());     // end of the streaming phase so far (bench: kernel time)
+    if (P.fused) {
+      // ---------------- fused K3: the CTA that completes the pair's last chunk sums the pair's partials, solves,
+      // composes and -- if it was the iteration's last pair -- builds the next work list; everybody else moves on.
+      __threadfence();                              // this CTA's partial is visible before its ticket
+      consumer_sync();
+      if (tid == 0) {
+        const unsigned t = atomicAdd(&P.pair_ticket[pair], 1u);
+        s_last = (t == (unsigned)nch - 1u) ? 1 : 0;
+        if (s_last) P.pair_ticket[pair] = 0;        // for the next iteration
+      }
+      consumer_sync();
+      if (s_last) {
+        __threadfence();
+        // scratch: the accumulator set the NEXT chunk will use is idle now (it is zeroed at the top of the loop)
+        double* scratch = accs0 + ((nitems & 1) ? kAccSet : 0);
+        const unsigned expected = (unsigned)__ldcg(&hdr->npairs);
+        fused_tail<DH>(P, pair, tid, scratch, &s_solve, expected);
+        consumer_sync();
+      }
+    }
+    if (dbg) dbg_epi += clock64() - e0;
+  }
+  if (dbg) {
+    long long* d = P.dbg_time + blockIdx.x * 16;
+    d[3] = dbg_wait; d[4] = dbg_epi; d[5] = 0; d[6] = clock64() - dbg_t0; d[15] = k;
+  }
+  if (kTimeline && P.dbg_time && tid == 32) { P.dbg_time[blockIdx.x * 16 + 13] = gtime(); P.dbg_time[blockIdx.x * 16 + 14] = nitems; }
 }
 
 // Resets the per-pair state at the start of a run (ica.py:319-337: ps[0] = p, ps[s>0] = 0;
 // the coarse-to-fine loop starts at the coarsest scale).
 __global__ void ica_init_state_kernel(PairState* state, const double* p_in, const int* ttypes,
-                                      int B, int nscales, double lambda_cfg, int* n_active) {
+                                      int B, int nscales, double lambda_cfg, int* n_active, unsigned int* pair_ticket) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b == 0) *n_active = B;
   if (b >= B) return;
+  if (pair_ticket) pair_ticket[b] = 0;
   PairState& st = state[b];
   const int tt = ttypes[b];
   const int n = nparams_of(tt);
@@ -1082,8 +1243,8 @@ cudaError_t launch_iterate(const IterParams& P, int channels, int dh, int grid, 
 }
 
 cudaError_t launch_init_state(PairState* state, const double* p_in, const int* ttypes, int B, int nscales,
-                              double lambda_cfg, int* n_active, cudaStream_t stream) {
-  ica_init_state_kernel<<<(B + 127) / 128, 128, 0, stream>>>(state, p_in, ttypes, B, nscales, lambda_cfg, n_active);
+                              double lambda_cfg, int* n_active, unsigned int* pair_ticket, cudaStream_t stream) {
+  ica_init_state_kernel<<<(B + 127) / 128, 128, 0, stream>>>(state, p_in, ttypes, B, nscales, lambda_cfg, n_active, pair_ticket);
   return cudaGetLastError();
 }
 

@@ -7,6 +7,15 @@ namespace ica {
 // H[k][l] (entry k*8+l) and b[k] (entry 64+k) as +-1 combinations of at most 4 moment sums
 struct AsmEntry { int idx[4]; float coef[4]; };
 
+// Header of one (double-buffered) work list
+struct SchedHdr {
+  int total;              // work items of the list
+  int npairs;             // pairs that own at least one item
+  int counter;            // next unclaimed item (dynamic work distribution)
+  int pad_;
+  long long t0, t1;       // %globaltimer: first CTA start / last chunk done of the launch that consumed the list
+};
+
 struct IterParams {
   const float* I1_0;      // level-0 inputs [B][H][W][C]
   const float* I2_0;
@@ -24,17 +33,21 @@ struct IterParams {
   long long* dbg_time;    // nullptr, or [grid][16] globaltimer stamps of each CTA's first item (profiling hook)
   double* dbg_Hb;         // nullptr, or 72 doubles: H (<=64) then b (8); state left untouched
   int* n_active;
-  int* chunk_start;       // [B+1] work list of the current launch (ica_schedule_kernel)
-  int* item_pair;         // [B*max_chunks] pair of each work item
+  // Work lists are double-buffered by the parity of *loop_count (the number of iterations scheduled so far): the list
+  // of iteration i+1 is written while stragglers of iteration i may still poll the counter of list i.
+  int* chunk_start;       // [2][B+1] exclusive prefix sums of the chunks per pair
+  int* item_pair;         // [2][B*max_chunks] pair of each work item
+  SchedHdr* hdr;          // [2] totals, work counter and time stamps of each list
+  unsigned int* pair_ticket;   // [B] chunks of a pair that are done in the current iteration (fused solve)
+  int fused;              // 1: the CTA that finishes a pair's last chunk solves it inside the iterate kernel (no solve launch)
   const AsmEntry* asm_tab;      // [6 transform codes][72]
   const void* tmaps;            // CUtensorMap [B][nscales][2] (I1 zero-filled, I2 NaN-filled boxes), 128 bytes each
   unsigned long long cond_handle;   // cudaGraphConditionalHandle of the while node (0 outside a graph)
   int* loop_count;              // iterations executed in this run (device)
-  int* work_counter;            // next unclaimed work item of the current iterate launch
   int max_launches;
-  long long* tstamp;            // [2] min start / max end (%globaltimer) of the current iterate launch
-  long long* kernel_ns;         // [2] accumulated iterate-kernel time (ns) and number of launches of this run
-  unsigned int* solve_ticket;   // blocks of the solve kernel that are done (the last one schedules)
+  long long* kernel_ns;         // [2] accumulated time of the streaming phase of the iterate kernel (ns: first CTA start ->
+                                //     last chunk partial written) and number of launches of this run
+  unsigned int* solve_ticket;   // pairs solved in the current iteration (the last one schedules the next)
   int shard_rank, shard_n;      // row-sharded mode: this rank's band of tile rows (0, 1 = whole image)
   int solve_mode;               // 0: sum partials + solve; 1: sum partials -> ext_moments only; 2: solve from ext_moments
   double* ext_moments;          // [B][kAccStride] moment sums exchanged between ranks (row-sharded mode)
@@ -61,7 +74,7 @@ cudaError_t launch_schedule(const IterParams& P, cudaStream_t stream);
 cudaError_t launch_solve(const IterParams& P, int dh, cudaStream_t stream);
 cudaError_t launch_iterate(const IterParams& P, int channels, int dh, int grid, cudaStream_t stream);
 cudaError_t launch_init_state(PairState* state, const double* p_in, const int* ttypes, int B, int nscales,
-                              double lambda_cfg, int* n_active, cudaStream_t stream);
+                              double lambda_cfg, int* n_active, unsigned int* pair_ticket, cudaStream_t stream);
 cudaError_t launch_export_results(const PairState* state, int B, double* p_out, double* err_out, int* iters_out,
                                   int nscales, cudaStream_t stream);
 cudaError_t launch_warp_out(const float* I1_0, const float* I2_0, long long in_stride, int nx, int ny, int channels,

@@ -1,4 +1,5 @@
-"""Per-CTA timeline of one iterate launch (profiling hook).  Runs a 1-pair registration limited
+"""Per-CTA timeline of one iterate launch (profiling hook; needs a library built with ICA_TIMELINE=1:
+``ICA_TIMELINE=1 python -m inverse_compositional_algorithm_b200.build --force``).  Runs a 1-pair registration limited
 to a given number of launches so that the last launch is the one of interest."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -38,8 +39,9 @@ print("block_end percentiles (us):", [round(float(np.percentile(end, q)) / 1e3, 
 print("items per block:", np.unique(act[:, 14], return_counts=True))
 
 sr = solve_row
-print("solve kernel block 0 (us since its start): staged %.2f sums %.2f assembled %.2f gj %.2f updated %.2f ticket %.2f scheduled %.2f" % tuple((sr[i] - sr[0]) / 1e3 for i in range(1, 8)))
-print("iterate max end -> solve start: %.2f us" % ((sr[0] - act[:, 13].max()) / 1e3))
+if sr[0] > 0:   # stamps of the stand-alone solve kernel (ICA_NO_FUSE=1); the fused solve runs inside the iterate kernel
+    print("solve kernel block 0 (us since its start): staged %.2f sums %.2f assembled %.2f gj %.2f updated %.2f" % tuple((sr[i] - sr[0]) / 1e3 for i in range(1, 6)))
+    print("iterate max end -> solve start: %.2f us" % ((sr[0] - act[:, 13].max()) / 1e3))
 
 # cycle accumulators of the LAST launch (consumer warp 0 / producer lane 0), as fractions of the CTA's consumer lifetime
 tot = act[:, 6].astype(np.float64)
