@@ -52,6 +52,9 @@ typedef enum {
 /* flags for ica_config.flags */
 #define ICA_FLAG_RECORD_TRAJECTORY 1u /* keep (scale, iter, |dp|, lambda, p) per iteration */
 #define ICA_FLAG_WRITE_DI_IW 2u       /* produce the DI / Iw images the reference returns */
+/* ica_plan_run_host dtype modifier: the host images are RGB [B][H][W][3] and the (one-channel) plan registers their
+   luminance Y = 0.2125 R + 0.7154 G + 0.0721 B (skimage.color.rgb2gray weights), converted on the device */
+#define ICA_DTYPE_RGB_TO_LUMA 0x10
 #define ICA_FLAG_HOST_LOOP 8u         /* drive the iteration loop from the host (polling) instead of the
                                          default CUDA-graph while node whose condition is set on the device */
 
@@ -129,6 +132,21 @@ ICA_API int ica_plan_shard_partial(ica_plan* plan, double* moments_dev, void* st
 /* n_active_out may be NULL (no synchronisation); otherwise the stream is synchronised */
 ICA_API int ica_plan_shard_solve(ica_plan* plan, const double* moments_dev, int32_t* n_active_out, void* stream);
 ICA_API int ica_plan_shard_finish(ica_plan* plan, double* p_out_dev, void* stream);
+
+/* Row-sharded mode with the exchange INSIDE the device-side loop (no NCCL call, no host round trip per iteration):
+   every rank owns an exchange buffer that the other ranks map through CUDA IPC (NVLink peer access); the solve kernel
+   stores the band's 105 moment sums into every rank's buffer, raises a sequence flag, waits for the other ranks' flags
+   and adds the sums in rank order.  One process per GPU.
+     ica_plan_xchg_create(plan, world, rank, handle64)   allocate + export this rank's buffer (64-byte IPC handle)
+     <all-gather the handles among the ranks>
+     ica_plan_xchg_connect(plan, handles[world][64])     map the peers
+     ica_plan_run_row_sharded(plan, I1, I2, p, stream)   whole registration, one graph launch; identical p on all ranks
+     ica_plan_xchg_stats(plan, &mean_us, &count, &error) exchange latency (publish -> all ranks seen); error != 0: a peer
+                                                         did not answer within 4 s                                       */
+ICA_API int ica_plan_xchg_create(ica_plan* plan, int32_t world, int32_t rank, void* ipc_handle_out64);
+ICA_API int ica_plan_xchg_connect(ica_plan* plan, const void* ipc_handles);
+ICA_API int ica_plan_run_row_sharded(ica_plan* plan, const float* I1_dev, const float* I2_dev, double* p_inout_dev, void* stream);
+ICA_API int ica_plan_xchg_stats(ica_plan* plan, double* mean_us_out, int64_t* count_out, int32_t* error_out);
 
 /* Same, from HOST buffers (what the Python drop-in calls): copies inputs host->device, runs,
    copies results back, synchronises.  dtype: 0 = float32, 1 = uint8, 2 = float64 (converted

@@ -23,6 +23,7 @@ FLAG_WRITE_DI_IW = 2
 FLAG_HOST_LOOP = 8
 
 DTYPE_F32, DTYPE_U8, DTYPE_F64 = 0, 1, 2
+DTYPE_RGB_TO_LUMA = 0x10     # modifier: RGB host images, one-channel plan registers their luminance
 
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_ALLOC = -1, -2, -3, -4
 
@@ -63,6 +64,10 @@ SIGNATURES = {
     "ica_plan_shard_partial": (C.c_int, [_P, _P, _P]),
     "ica_plan_shard_solve": (C.c_int, [_P, _P, _PI, _P]),
     "ica_plan_shard_finish": (C.c_int, [_P, _P, _P]),
+    "ica_plan_xchg_create": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "ica_plan_xchg_connect": (C.c_int, [_P, _P]),
+    "ica_plan_run_row_sharded": (C.c_int, [_P, _P, _P, _P, _P]),
+    "ica_plan_xchg_stats": (C.c_int, [_P, _PD, C.POINTER(C.c_int64), _PI]),
     "ica_plan_run_host": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "ica_plan_last_host_run_ms": (C.c_int, [_P, _PF]),
     "ica_plan_debug_timeline": (C.c_int, [_P, _P, C.c_int32]),
@@ -504,6 +509,24 @@ class Plan:
     def shard_finish(self, p_ptr: int, stream: int = 0):
         check(lib().ica_plan_shard_finish(self._h, _P(p_ptr), _P(stream)))
 
+    # ---- row-sharded mode, exchange inside the device loop (peer memory over NVLink)
+    def xchg_create(self, world: int, rank: int) -> bytes:
+        h = (C.c_ubyte * 64)()
+        check(lib().ica_plan_xchg_create(self._h, int(world), int(rank), C.cast(h, _P)))
+        return bytes(h)
+
+    def xchg_connect(self, handles: bytes):
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        check(lib().ica_plan_xchg_connect(self._h, C.cast(buf, _P)))
+
+    def run_row_sharded(self, I1_ptr: int, I2_ptr: int, p_ptr: int, stream: int = 0):
+        check(lib().ica_plan_run_row_sharded(self._h, _P(I1_ptr), _P(I2_ptr), _P(p_ptr), _P(stream)))
+
+    def xchg_stats(self):
+        us, n, err = C.c_double(), C.c_int64(), C.c_int32()
+        check(lib().ica_plan_xchg_stats(self._h, C.byref(us), C.byref(n), C.byref(err)))
+        return {"mean_us": us.value, "count": n.value, "error": err.value}
+
     def results(self):
         p = np.zeros((self.batch, MAX_PARAMS))
         err = np.zeros(self.batch)
@@ -511,11 +534,15 @@ class Plan:
         check(lib().ica_plan_get_results(self._h, _ptr(p), _ptr(err), _ptr(iters)))
         return p, err, iters
 
-    def run_host(self, I1: np.ndarray, I2: np.ndarray, p0=None, want_images=False):
-        """``I1``/``I2``: arrays [B][H][W][C] of dtype float32, uint8 or float64 (C-contiguous)."""
+    def run_host(self, I1: np.ndarray, I2: np.ndarray, p0=None, want_images=False, rgb_to_luma=False):
+        """``I1``/``I2``: arrays [B][H][W][C] of dtype float32, uint8 or float64 (C-contiguous).  With ``rgb_to_luma`` the
+        inputs are RGB ``[B][H][W][3]`` and the (one-channel) plan registers their luminance, computed on the device."""
         shape = (self.batch, self.height, self.width, self.channels)
-        if I1.shape != shape or I2.shape != shape:
-            raise ValueError(f"expected image batches of shape {shape}, got {I1.shape} / {I2.shape}")
+        in_shape = (self.batch, self.height, self.width, 3) if rgb_to_luma else shape
+        if rgb_to_luma and self.channels != 1:
+            raise ValueError("rgb_to_luma needs a one-channel plan")
+        if I1.shape != in_shape or I2.shape != in_shape:
+            raise ValueError(f"expected image batches of shape {in_shape}, got {I1.shape} / {I2.shape}")
         if I1.dtype != I2.dtype:
             raise ValueError("I1 and I2 must share a dtype")
         code = {np.dtype(np.float32): DTYPE_F32, np.dtype(np.uint8): DTYPE_U8,
@@ -538,8 +565,8 @@ class Plan:
             DI = np.empty(shape, dtype=np.float32)
             Iw = np.empty(shape, dtype=np.float32)
             di_ptr, iw_ptr = _ptr(DI), _ptr(Iw)
-        check(lib().ica_plan_run_host(self._h, _ptr(I1), _ptr(I2), code, _ptr(p), _ptr(err),
-                                      _ptr(iters), di_ptr, iw_ptr))
+        check(lib().ica_plan_run_host(self._h, _ptr(I1), _ptr(I2), code | (DTYPE_RGB_TO_LUMA if rgb_to_luma else 0),
+                                      _ptr(p), _ptr(err), _ptr(iters), di_ptr, iw_ptr))
         return p, err, iters, DI, Iw
 
     def run_host_ptrs(self, I1_ptr: int, I2_ptr: int, dtype_code: int, p: np.ndarray,

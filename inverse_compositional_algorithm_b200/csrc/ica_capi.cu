@@ -51,6 +51,17 @@ struct ica_plan {
   long long* kernel_ns = nullptr;   // [2] accumulated streaming-phase time of the iterate kernel (ns), launches
   SchedHdr* hdr = nullptr;          // [2] headers of the double-buffered work lists
   unsigned int* pair_ticket = nullptr;   // [B]
+  // row-sharded mode with the exchange in the device-side loop (peer memory, CUDA IPC)
+  double* xbuf = nullptr;            // this rank's exchange buffer [2][world][B][kXSlot]
+  double** x_peers_dev = nullptr;    // device array [world] of every rank's buffer as mapped here
+  void* x_peer_ptr[64] = {nullptr};  // host copy (peers opened with cudaIpcOpenMemHandle; own buffer at [rank])
+  int x_world = 0, x_rank = 0;
+  unsigned long long x_seq = 0;      // sequence numbers consumed so far
+  unsigned long long* x_seq_dev = nullptr;   // device: sequence base of the current run
+  unsigned long long* x_seq_host = nullptr;  // pinned staging of it
+  int* x_error = nullptr;
+  long long* x_ns = nullptr;         // [2] device: accumulated exchange time, exchanges
+  int graph_mode = -1;               // solve mode the loop graph was built for
   int fused = 0;                    // solve inside the iterate kernel (one launch per iteration; opt-in, ICA_FUSE=1)
   int* h_loop = nullptr;            // pinned: {iterations, pad} and kernel ns copied after a run
   long long* h_kns = nullptr;       // pinned [2]
@@ -297,6 +308,8 @@ void fill_iter_params(const ica_plan* pl, const float* /*I1*/, const float* /*I2
   P->kernel_ns = pl->kernel_ns;
   P->shard_rank = pl->shard_rank; P->shard_n = pl->shard_n;
   P->solve_mode = 0; P->ext_moments = nullptr;
+  P->x_peers = pl->x_peers_dev; P->x_world = pl->x_world; P->x_rank = pl->x_rank; P->x_seq_base = pl->x_seq_dev;
+  P->x_error = pl->x_error; P->x_ns = pl->x_ns;
   P->B = pl->B;
   P->max_chunks = pl->max_chunks;
   P->robust_type = pl->cfg.robust_type;
@@ -312,9 +325,9 @@ void fill_iter_params(const ica_plan* pl, const float* /*I1*/, const float* /*I2
 // CUDA graph of the iteration loop: one conditional WHILE node whose body is {iterate, solve}; the solve
 // kernel's scheduling block sets the condition on the device, so the whole coarse-to-fine loop of every
 // pair runs without a host round trip.  Rebuilt when the image pointers or the moment degree change.
-int ensure_loop_graph(ica_plan* pl, const float* I1, const float* I2) {
+int ensure_loop_graph(ica_plan* pl, const float* I1, const float* I2, int solve_mode = 0) {
   I1 = pl->k2_I1; I2 = pl->k2_I2;   // the graph bakes K2's view of level 0
-  if (pl->graph_exec && pl->graph_I1 == I1 && pl->graph_I2 == I2 && pl->graph_dh == pl->dh) return ICA_OK;
+  if (pl->graph_exec && pl->graph_I1 == I1 && pl->graph_I2 == I2 && pl->graph_dh == pl->dh && pl->graph_mode == solve_mode) return ICA_OK;
   if (pl->graph_exec) { cudaGraphExecDestroy(pl->graph_exec); pl->graph_exec = nullptr; }
   if (pl->graph) { cudaGraphDestroy(pl->graph); pl->graph = nullptr; }
   ICA_CUDA_CHECK(cudaGraphCreate(&pl->graph, 0));
@@ -331,10 +344,11 @@ int ensure_loop_graph(ica_plan* pl, const float* I1, const float* I2) {
   IterParams P;
   fill_iter_params(pl, I1, I2, &P);
   P.cond_handle = (unsigned long long)handle;
-  P.fused = pl->fused;
+  P.fused = solve_mode == 0 ? pl->fused : 0;
+  P.solve_mode = solve_mode;
   ICA_CUDA_CHECK(cudaStreamBeginCaptureToGraph(pl->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
   cudaError_t e1 = launch_iterate(P, pl->C, pl->dh, pl->grid, pl->stream);
-  cudaError_t e2 = pl->fused ? cudaSuccess : launch_solve(P, pl->dh, pl->stream);   // fused: the iterate kernel solves
+  cudaError_t e2 = P.fused ? cudaSuccess : launch_solve(P, pl->dh, pl->stream);   // fused: the iterate kernel solves
   cudaGraph_t captured = nullptr;
   cudaError_t e3 = cudaStreamEndCapture(pl->stream, &captured);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
@@ -342,7 +356,7 @@ int ensure_loop_graph(ica_plan* pl, const float* I1, const float* I2) {
     return ICA_ERR_CUDA;
   }
   ICA_CUDA_CHECK(cudaGraphInstantiate(&pl->graph_exec, pl->graph, 0));
-  pl->graph_I1 = I1; pl->graph_I2 = I2; pl->graph_dh = pl->dh;
+  pl->graph_I1 = I1; pl->graph_I2 = I2; pl->graph_dh = pl->dh; pl->graph_mode = solve_mode;
   return ICA_OK;
 }
 
@@ -423,6 +437,9 @@ int ica_plan_destroy(ica_plan* pl) {
   if (!pl) return ICA_OK;
   cudaFree(pl->pyr1); cudaFree(pl->pyr2); cudaFree(pl->tmp); cudaFree(pl->tmaps_dev); cudaFree(pl->pad1); cudaFree(pl->pad2);
   for (int s = 0; s < ICA_MAX_SCALES; ++s) { free_resample(&pl->ry[s]); free_resample(&pl->rx[s]); }
+  for (int r = 0; r < pl->x_world; ++r) if (r != pl->x_rank && pl->x_peer_ptr[r]) cudaIpcCloseMemHandle(pl->x_peer_ptr[r]);
+  cudaFree(pl->xbuf); cudaFree(pl->x_peers_dev); cudaFree(pl->x_error); cudaFree(pl->x_ns); cudaFree(pl->x_seq_dev);
+  if (pl->x_seq_host) cudaFreeHost(pl->x_seq_host);
   cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->item_pair); cudaFree(pl->solve_ticket); cudaFree(pl->asm_tab); cudaFree(pl->loop_count); cudaFree(pl->kernel_ns); cudaFree(pl->hdr); cudaFree(pl->pair_ticket);
   if (pl->h_loop) cudaFreeHost(pl->h_loop);
   if (pl->h_kns) cudaFreeHost(pl->h_kns);
@@ -704,6 +721,113 @@ int ica_plan_shard_finish(ica_plan* pl, double* p_out, void* stream_) {
   return ICA_OK;
 }
 
+// ---- row-sharded mode with the per-iteration exchange INSIDE the device-side loop (BASELINE configs[4]): every rank
+// owns an exchange buffer; ica_plan_xchg_create returns its CUDA IPC handle, the caller gathers the handles of all ranks
+// (torch.distributed / MPI / a file -- 64 bytes each) and passes them to ica_plan_xchg_connect, which maps the peers'
+// buffers (NVLink peer access).  ica_plan_run_row_sharded then runs the whole registration as ONE graph launch per rank:
+// K2 on the rank's band, K3 adds the ranks' moment sums through the mapped buffers (no NCCL call, no host round trip).
+int ica_plan_xchg_create(ica_plan* pl, int32_t world, int32_t rank, void* ipc_handle_out64) {
+  if (!pl || world < 1 || world > 64 || rank < 0 || rank >= world) { set_error("invalid exchange group (rank %d of %d)", rank, world); return ICA_ERR_INVALID; }
+  if (int rc = enter_plan_device(pl)) return rc;
+  if (pl->xbuf) { set_error("the exchange buffer of this plan exists already"); return ICA_ERR_INVALID; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles travel as 64-byte records");
+  const size_t n = (size_t)2 * world * pl->B * kXSlot;
+  if (int rc = dev_alloc(pl, &pl->xbuf, n)) return rc;
+  ICA_CUDA_CHECK(cudaMemset(pl->xbuf, 0, n * sizeof(double)));
+  if (int rc = dev_alloc(pl, &pl->x_peers_dev, (size_t)world)) return rc;
+  if (int rc = dev_alloc(pl, &pl->x_error, 1)) return rc;
+  if (int rc = dev_alloc(pl, &pl->x_ns, 2)) return rc;
+  if (int rc = dev_alloc(pl, &pl->x_seq_dev, 1)) return rc;
+  ICA_CUDA_CHECK(cudaMallocHost((void**)&pl->x_seq_host, sizeof(unsigned long long)));
+  ICA_CUDA_CHECK(cudaMemset(pl->x_error, 0, sizeof(int)));
+  ICA_CUDA_CHECK(cudaMemset(pl->x_ns, 0, 2 * sizeof(long long)));
+  pl->x_world = world; pl->x_rank = rank;
+  pl->x_peer_ptr[rank] = pl->xbuf;
+  if (ipc_handle_out64) {
+    cudaIpcMemHandle_t h;
+    ICA_CUDA_CHECK(cudaIpcGetMemHandle(&h, pl->xbuf));
+    memcpy(ipc_handle_out64, &h, 64);
+  }
+  if (int rc = ica_plan_set_row_shard(pl, rank, world)) return rc;
+  if (world == 1) {
+    ICA_CUDA_CHECK(cudaMemcpy(pl->x_peers_dev, pl->x_peer_ptr, sizeof(void*), cudaMemcpyHostToDevice));
+  }
+  return ICA_OK;
+}
+
+int ica_plan_xchg_connect(ica_plan* pl, const void* ipc_handles /* [world][64] */) {
+  if (!pl || !pl->xbuf || !ipc_handles) { set_error("ica_plan_xchg_create must be called first"); return ICA_ERR_INVALID; }
+  if (int rc = enter_plan_device(pl)) return rc;
+  for (int r = 0; r < pl->x_world; ++r) {
+    if (r == pl->x_rank || pl->x_peer_ptr[r]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(ipc_handles) + (size_t)r * 64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e)); return ICA_ERR_CUDA; }
+    pl->x_peer_ptr[r] = p;
+  }
+  ICA_CUDA_CHECK(cudaMemcpy(pl->x_peers_dev, pl->x_peer_ptr, (size_t)pl->x_world * sizeof(void*), cudaMemcpyHostToDevice));
+  return ICA_OK;
+}
+
+// mean exchange time (publish -> all ranks' sums seen, i.e. wire latency + waiting for the slowest rank) in microseconds,
+// number of exchanges since the last call, and whether a peer timed out
+int ica_plan_xchg_stats(ica_plan* pl, double* mean_us_out, int64_t* count_out, int32_t* error_out) {
+  if (!pl || !pl->xbuf) { set_error("no exchange buffer"); return ICA_ERR_INVALID; }
+  if (int rc = enter_plan_device(pl)) return rc;
+  long long ns[2] = {0, 0}; int err = 0;
+  ICA_CUDA_CHECK(cudaDeviceSynchronize());
+  ICA_CUDA_CHECK(cudaMemcpy(ns, pl->x_ns, sizeof(ns), cudaMemcpyDeviceToHost));
+  ICA_CUDA_CHECK(cudaMemcpy(&err, pl->x_error, sizeof(int), cudaMemcpyDeviceToHost));
+  ICA_CUDA_CHECK(cudaMemset(pl->x_ns, 0, sizeof(ns)));
+  if (mean_us_out) *mean_us_out = ns[1] > 0 ? 1e-3 * (double)ns[0] / (double)ns[1] : 0.0;
+  if (count_out) *count_out = ns[1];
+  if (error_out) *error_out = err;
+  return ICA_OK;
+}
+
+int ica_plan_run_row_sharded(ica_plan* pl, const float* I1, const float* I2, double* p_inout, void* stream_) {
+  if (!pl || !I1 || !I2 || !p_inout) { set_error("NULL argument"); return ICA_ERR_INVALID; }
+  if (!pl->xbuf || !pl->x_peers_dev) { set_error("ica_plan_xchg_create / ica_plan_xchg_connect must be called first"); return ICA_ERR_INVALID; }
+  if (int rc = enter_plan_device(pl)) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  pl->launches = 0; pl->n_ev_iter = 0; pl->n_ev_pyr = 0;
+  pl->last_I1 = I1; pl->last_I2 = I2;
+  const int max_launches = pl->nscales * pl->cfg.max_iter;
+  // sequence numbers of this run's exchanges: every rank consumes the same range, so they agree without talking
+  ICA_CUDA_CHECK(cudaStreamSynchronize(stream));          // (a previous run on this stream may still read the staging word)
+  *pl->x_seq_host = pl->x_seq;
+  ICA_CUDA_CHECK(cudaMemcpyAsync(pl->x_seq_dev, pl->x_seq_host, sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+  pl->x_seq += (unsigned long long)max_launches + 2;
+  if (int rc = prepare_level0(pl, I1, I2, stream)) return rc;
+  if (int rc = build_pyramids(pl, I1, I2, stream)) return rc;
+  ICA_LAUNCH_CHECK(launch_init_state(pl->state, p_inout, pl->ttypes_dev, pl->B, pl->nscales, pl->cfg.lambda_, pl->n_active,
+                                     pl->pair_ticket, stream));
+  IterParams P;
+  fill_iter_params(pl, I1, I2, &P);
+  ICA_LAUNCH_CHECK(launch_schedule(P, stream));
+  pl->launches += 2;
+
+  pl->last_launches_per_iter = 2;
+  if (pl->use_graph) {
+    if (int rc = ensure_loop_graph(pl, I1, I2, 3)) return rc;
+    ICA_CUDA_CHECK(cudaGraphLaunch(pl->graph_exec, stream));
+  } else {
+    // host-driven variant (profilers): every rank launches the full count; finished iterations are empty
+    P.solve_mode = 3;
+    for (int it = 0; it < max_launches; ++it) {
+      ICA_LAUNCH_CHECK(launch_iterate(P, pl->C, pl->dh, pl->grid, stream));
+      ICA_LAUNCH_CHECK(launch_solve(P, pl->dh, stream));
+    }
+  }
+  ICA_CUDA_CHECK(cudaMemcpyAsync(pl->h_loop, pl->loop_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  ICA_CUDA_CHECK(cudaMemcpyAsync(pl->h_kns, pl->kernel_ns, 2 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+  ICA_LAUNCH_CHECK(launch_export_results(pl->state, pl->B, p_inout, pl->err_dev, pl->iters_dev, pl->nscales, stream));
+  pl->launches += 1;
+  return ICA_OK;
+}
+
 int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* p_inout, void* stream_) {
   if (!pl || !I1 || !I2 || !p_inout) { set_error("NULL argument"); return ICA_ERR_INVALID; }
   if (pl->shard_n != 1) { set_error("the plan is row-sharded: use ica_plan_shard_begin/partial/solve/finish"); return ICA_ERR_INVALID; }
@@ -785,15 +909,17 @@ static int wait_event_polite(cudaEvent_t ev) {
 
 // both images of the batch host -> device; u8 / f64 inputs go through two staging areas so that the two copies run
 // back to back and the link is released before the conversions to float32 are even scheduled
-static int upload_pair(ica_plan* pl, const void* h1, const void* h2, int dtype, cudaStream_t stream) {
-  const long long n = (long long)pl->B * pl->in_stride;
-  if (dtype == 0) {
+static int upload_pair(ica_plan* pl, const void* h1, const void* h2, int dtype_in, cudaStream_t stream) {
+  const bool luma = (dtype_in & ICA_DTYPE_RGB_TO_LUMA) != 0;   // RGB host images, one-channel plan
+  const int dtype = dtype_in & 0xf;
+  const long long n = (long long)pl->B * pl->in_stride * (luma ? 3 : 1);
+  if (dtype == 0 && !luma) {
     ICA_CUDA_CHECK(cudaMemcpyAsync(pl->in1_dev, h1, n * sizeof(float), cudaMemcpyHostToDevice, stream));
     ICA_CUDA_CHECK(cudaMemcpyAsync(pl->in2_dev, h2, n * sizeof(float), cudaMemcpyHostToDevice, stream));
     ICA_CUDA_CHECK(cudaEventRecord(pl->ev_h2d_done, stream));
     return ICA_OK;
   }
-  const size_t esz = dtype == 1 ? 1 : 8;
+  const size_t esz = dtype == 1 ? 1 : (dtype == 2 ? 8 : 4);
   const size_t area = ((size_t)n * esz + 255) / 256 * 256;
   if (pl->raw_bytes < 2 * area) {
     cudaFree(pl->raw_dev); pl->raw_dev = nullptr; pl->device_bytes -= pl->raw_bytes; pl->raw_bytes = 0;
@@ -809,7 +935,10 @@ static int upload_pair(ica_plan* pl, const void* h1, const void* h2, int dtype, 
   // conversion to float32 fused with the level-0 min/max of every image (saves the separate pass over level 0)
   const int ns = pl->nscales;
   ICA_LAUNCH_CHECK(launch_minmax_reset(pl->mm, pl->B * ns * 2, stream));
-  if (dtype == 1) {
+  if (luma) {
+    ICA_LAUNCH_CHECK(launch_convert_luma(r1, dtype, pl->in1_dev, pl->in_stride, pl->B, pl->mm + 0, ns * 2, stream));
+    ICA_LAUNCH_CHECK(launch_convert_luma(r2, dtype, pl->in2_dev, pl->in_stride, pl->B, pl->mm + 1, ns * 2, stream));
+  } else if (dtype == 1) {
     ICA_LAUNCH_CHECK(launch_convert_u8(r1, pl->in1_dev, pl->in_stride, pl->B, pl->mm + 0, ns * 2, stream));
     ICA_LAUNCH_CHECK(launch_convert_u8(r2, pl->in2_dev, pl->in_stride, pl->B, pl->mm + 1, ns * 2, stream));
   } else {
@@ -823,7 +952,8 @@ static int upload_pair(ica_plan* pl, const void* h1, const void* h2, int dtype, 
 int ica_plan_run_host(ica_plan* pl, const void* I1_host, const void* I2_host, int32_t dtype, double* p_inout_host,
                       double* err_out, int32_t* iters_out, float* DI_out, float* Iw_out) {
   if (!pl || !I1_host || !I2_host || !p_inout_host) { set_error("NULL argument"); return ICA_ERR_INVALID; }
-  if (dtype < 0 || dtype > 2) { set_error("dtype must be 0 (f32), 1 (u8) or 2 (f64)"); return ICA_ERR_INVALID; }
+  if ((dtype & ~(0xf | ICA_DTYPE_RGB_TO_LUMA)) || (dtype & 0xf) > 2) { set_error("dtype must be 0 (f32), 1 (u8) or 2 (f64), optionally | ICA_DTYPE_RGB_TO_LUMA"); return ICA_ERR_INVALID; }
+  if ((dtype & ICA_DTYPE_RGB_TO_LUMA) && pl->C != 1) { set_error("ICA_DTYPE_RGB_TO_LUMA needs a one-channel plan (the host images are RGB)"); return ICA_ERR_INVALID; }
   if ((DI_out || Iw_out) && !(pl->cfg.flags & ICA_FLAG_WRITE_DI_IW)) {
     set_error("DI/Iw requested but the plan was created without ICA_FLAG_WRITE_DI_IW"); return ICA_ERR_INVALID;
   }
@@ -845,7 +975,7 @@ int ica_plan_run_host(ica_plan* pl, const void* I1_host, const void* I2_host, in
   const int rc_run = ica_plan_run_device(pl, pl->in1_dev, pl->in2_dev, pl->p_dev, stream);
   pl->mm_ready = false;
   if (rc_run) return rc_run;
-  pl->launches += (dtype == 0 ? 0 : 3);   // key reset + the two conversion kernels
+  pl->launches += (dtype == 0 ? 0 : 3);   // key reset + the two conversion kernels (0 | luma counts too: dtype != 0)
   ICA_CUDA_CHECK(cudaMemcpyAsync(p_inout_host, pl->p_dev, (size_t)pl->B * ICA_MAX_PARAMS * sizeof(double),
                                  cudaMemcpyDeviceToHost, stream));
   if (err_out) ICA_CUDA_CHECK(cudaMemcpyAsync(err_out, pl->err_dev, pl->B * sizeof(double), cudaMemcpyDeviceToHost, stream));

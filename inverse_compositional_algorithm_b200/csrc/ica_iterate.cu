@@ -55,7 +55,7 @@ constexpr int TH = kRowsPerWarp * kConsumerWarps;   // tile height (row y0 + war
 constexpr int HALO = 4;           // the I1 patch starts at x0-4: the inner coordinate of a TMA box must be a multiple of 16 bytes
 constexpr int S1ROWS = TH + 2;
 #ifndef ICA_BH
-#define ICA_BH 30
+#define ICA_BH 24
 #endif
 #ifndef ICA_STAGES_RGB
 #define ICA_STAGES_RGB 2
@@ -432,6 +432,49 @@ struct SolveShared {
   unsigned int ticket;
 };
 
+// Row-sharded mode, exchange through peer memory (one process per GPU, buffers mapped with CUDA IPC over NVLink): every
+// rank stores its band's moment sums into its slot of EVERY rank's buffer, raises the slot's sequence flag, waits until
+// all slots of its own buffer carry this iteration's sequence number and adds them in rank order -- identical sums, and
+// therefore identical parameters, on all ranks with no host round trip and no collective launch.  Two slot sets
+// alternate by the parity of the sequence number: a rank can only start iteration i+2 after every rank has published
+// i+1, i.e. after every rank has finished reading iteration i.
+template <typename Sync>
+__device__ void exchange_moments(const IterParams& P, int pair, int tid, int nthr, double* s_mom, int nent, Sync sync) {
+  const int W = P.x_world, me = P.x_rank;
+  const unsigned long long seq = __ldcg(P.x_seq_base) + (unsigned long long)__ldcg(P.loop_count) + 1ull;
+  const long long par = (long long)(seq & 1ull);
+  const long long t0 = gtime();
+  for (int e = tid; e < W * nent; e += nthr) {
+    const int r = e / nent, k = e - r * nent;
+    double* dst = P.x_peers[r] + ((par * W + me) * P.B + pair) * kXSlot;
+    dst[k] = s_mom[k];
+  }
+  __threadfence_system();     // the sums are visible system-wide before the flags
+  sync();
+  if (tid < W) {
+    volatile unsigned long long* f =
+        reinterpret_cast<volatile unsigned long long*>(P.x_peers[tid] + ((par * W + me) * P.B + pair) * kXSlot + (kXSlot - 1));
+    *f = seq;
+  }
+  const double* mine = P.x_peers[me];
+  if (tid < W) {
+    const volatile unsigned long long* f =
+        reinterpret_cast<const volatile unsigned long long*>(mine + ((par * W + tid) * P.B + pair) * kXSlot + (kXSlot - 1));
+    while (*f != seq) {
+      if (gtime() - t0 > 4000000000ll) { *P.x_error = 1; break; }     // 4 s: a peer is gone; fail instead of hanging the GPU
+    }
+  }
+  __threadfence_system();
+  sync();
+  if (tid < nent) {
+    double a = 0.0;
+    for (int r = 0; r < W; ++r) a += *reinterpret_cast<const volatile double*>(mine + ((par * W + r) * P.B + pair) * kXSlot + tid);
+    s_mom[tid] = a;
+  }
+  sync();
+  if (tid == 0 && P.x_ns) { atomicAdd(reinterpret_cast<unsigned long long*>(&P.x_ns[0]), (unsigned long long)(gtime() - t0)); atomicAdd(reinterpret_cast<unsigned long long*>(&P.x_ns[1]), 1ull); }
+}
+
 template <int DH, int NW, typename Sync>
 __device__ bool solve_pair(const IterParams& P, int pair, int tid, double* s_part, SolveShared& sh, Sync sync, bool stamp) {
   constexpr int K = RowVals<DH>::K;
@@ -512,6 +555,7 @@ __device__ bool solve_pair(const IterParams& P, int pair, int tid, double* s_par
       sync();
     }
     SOLVE_STAMP(2);
+    if (P.solve_mode == 3) exchange_moments(P, pair, tid, NW * 32, s_mom, NENT, sync);   // row-sharded: add over ranks
     if (P.solve_mode == 1) {   // row-sharded: publish this rank's moment sums and stop
       if (tid < kAccStride) P.ext_moments[(long long)pair * kAccStride + tid] = tid < NENT ? s_mom[tid] : 0.0;
       return false;

@@ -7,6 +7,8 @@ namespace ica {
 // H[k][l] (entry k*8+l) and b[k] (entry 64+k) as +-1 combinations of at most 4 moment sums
 struct AsmEntry { int idx[4]; float coef[4]; };
 
+constexpr int kXSlot = 128;     // doubles per (rank, pair) exchange slot: 105 moment sums, the last word is the flag
+
 // Header of one (double-buffered) work list
 struct SchedHdr {
   int total;              // work items of the list
@@ -49,8 +51,16 @@ struct IterParams {
                                 //     last chunk partial written) and number of launches of this run
   unsigned int* solve_ticket;   // pairs solved in the current iteration (the last one schedules the next)
   int shard_rank, shard_n;      // row-sharded mode: this rank's band of tile rows (0, 1 = whole image)
-  int solve_mode;               // 0: sum partials + solve; 1: sum partials -> ext_moments only; 2: solve from ext_moments
+  int solve_mode;               // 0: sum partials + solve; 1: sum partials -> ext_moments only; 2: solve from ext_moments;
+                                // 3: sum partials, exchange them with the other ranks through peer memory, solve
   double* ext_moments;          // [B][kAccStride] moment sums exchanged between ranks (row-sharded mode)
+  // peer exchange (mode 3): x_peers[r] = rank r's exchange buffer [2 parities][x_world ranks][B pairs][kXSlot doubles],
+  // mapped into this process (CUDA IPC over NVLink); slot word kXSlot-1 is the sequence flag of the slot
+  double* const* x_peers;
+  int x_world, x_rank;
+  const unsigned long long* x_seq_base;   // device: first sequence number of this run (monotonic over the plan's life)
+  int* x_error;                      // set when a peer did not answer within the time-out
+  long long* x_ns;                   // [2] accumulated exchange time (publish -> all peers seen), exchanges
   int B;
   int max_chunks;         // partial slots per pair
   int traj_cap;

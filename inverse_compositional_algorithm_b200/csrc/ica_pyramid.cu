@@ -748,7 +748,51 @@ __global__ void __launch_bounds__(256) convert_minmax_kernel(const T* __restrict
   }
 }
 
+// RGB -> luminance ingest: host images are [H][W][3] of type T, the plan works on one channel.
+// Y = 0.2125 R + 0.7154 G + 0.0721 B (the weights of skimage.color.rgb2gray, the reference's image toolkit), evaluated
+// in float64 left to right and rounded once to float32; fused with the min/max of the result like the plain conversions.
+template <typename T>
+__global__ void __launch_bounds__(256) convert_luma_minmax_kernel(const T* __restrict__ in0, float* __restrict__ out0, long long npix,
+                                                                   MinMaxKeys* __restrict__ mm, int mm_stride) {
+  const T* in = in0 + (long long)blockIdx.y * npix * 3;
+  float* out = out0 + (long long)blockIdx.y * npix;
+  float fmin_ = 3.4e38f, fmax_ = -3.4e38f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+    const double r = (double)in[3 * i], g = (double)in[3 * i + 1], b = (double)in[3 * i + 2];
+    const float v = (float)__dadd_rn(__dadd_rn(__dmul_rn(0.2125, r), __dmul_rn(0.7154, g)), __dmul_rn(0.0721, b));
+    out[i] = v;
+    fmin_ = fminf(fmin_, v); fmax_ = fmaxf(fmax_, v);
+  }
+  unsigned kmin = 0xffffffffu, kmax = 0u;
+  if (fmin_ <= fmax_) { kmin = float_key(fmin_); kmax = float_key(fmax_); }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  }
+  __shared__ unsigned smin[8], smax[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { smin[warp] = kmin; smax[warp] = kmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { kmin = min(kmin, smin[w]); kmax = max(kmax, smax[w]); }
+    MinMaxKeys* k = mm + (long long)blockIdx.y * mm_stride;
+    if (kmin <= kmax) { atomicMin(&k->lo, kmin); atomicMax(&k->hi, kmax); }
+  }
+}
+
 }  // namespace
+
+// dtype: 0 = float32, 1 = uint8, 2 = float64 RGB input; out: float32 luminance, npix pixels per image
+cudaError_t launch_convert_luma(const void* in, int dtype, float* out, long long npix, int nimg, MinMaxKeys* mm, int mm_stride,
+                                cudaStream_t stream) {
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((npix + 256 * 8 - 1) / (256 * 8), 256));
+  const dim3 grid(blocks, nimg);
+  if (dtype == 1) convert_luma_minmax_kernel<unsigned char><<<grid, 256, 0, stream>>>(static_cast<const unsigned char*>(in), out, npix, mm, mm_stride);
+  else if (dtype == 2) convert_luma_minmax_kernel<double><<<grid, 256, 0, stream>>>(static_cast<const double*>(in), out, npix, mm, mm_stride);
+  else convert_luma_minmax_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(in), out, npix, mm, mm_stride);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_minmax_reset(MinMaxKeys* mm, int count, cudaStream_t stream) {
   minmax_reset_kernel<<<(count + 255) / 256, 256, 0, stream>>>(mm, count);

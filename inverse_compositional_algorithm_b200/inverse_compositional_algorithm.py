@@ -158,7 +158,7 @@ def _writeback(p, pout):
 
 def register_batch(I1, I2, transform_type, nscales=1, nu=0.5, TOL=1e-3,
                    robust_type=RobustErrorFunctionType.QUADRATIC, lambda_=0.0, nanifoutside=True,
-                   delta=10, p0=None, gray_as_rgb=True, return_images=False, plan=None):
+                   delta=10, p0=None, gray_as_rgb=True, return_images=False, plan=None, luminance=False):
     """B independent registrations in one call: ``I1``/``I2`` are ``[B, H, W, C]`` (C = 1 or 3,
     float32 / uint8 / float64); ``transform_type`` is one type or a length-B sequence (mixed
     batches).  Returns ``(p [B, 8] zero-padded, error [B], iters [B, nscales])`` and, with
@@ -170,6 +170,10 @@ def register_batch(I1, I2, transform_type, nscales=1, nu=0.5, TOL=1e-3,
         raise ValueError("I1 and I2 must be [B, H, W, C] with C in (1, 3)")
     _check_common(I1, I2, TOL)
     B, ny, nx, nz = I1.shape
+    if luminance:      # RGB in, registered on the luminance (converted on the device from the uploaded RGB bytes)
+        if nz != 3:
+            raise ValueError("luminance=True needs RGB inputs")
+        nz = 1
     types = ([_as_type(transform_type)] * B if not isinstance(transform_type, (list, tuple, np.ndarray))
              else [_as_type(t) for t in transform_type])
     if len(types) != B:
@@ -184,7 +188,7 @@ def register_batch(I1, I2, transform_type, nscales=1, nu=0.5, TOL=1e-3,
                              nanifoutside=(nanifoutside is True), gray_as_rgb=bool(gray_as_rgb) and nz == 1,
                              record_trajectory=False, write_di_iw=bool(return_images))
         plan.set_transform_types([t.value for t in types])
-        pout, err, iters, DI, Iw = plan.run_host(I1, I2, p0, want_images=return_images)
+        pout, err, iters, DI, Iw = plan.run_host(I1, I2, p0, want_images=return_images, rgb_to_luma=bool(luminance))
     if return_images:
         return pout, err, iters, DI, Iw
     return pout, err, iters

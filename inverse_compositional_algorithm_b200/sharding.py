@@ -71,10 +71,17 @@ def row_band(tiles_y: int, rank: int, nranks: int):
 
 def register_row_sharded(I1, I2, transform_type, *, nscales=5, nu=0.5, robust_type=0, robust_loop=None,
                          lambda_=0.0, tol=1e-3, max_iter=30, delta=5, nanifoutside=True,
-                         gray_as_rgb=True, p0=None, group=None, emulate_ranks=None, stats=None, poll_every=4):
+                         gray_as_rgb=True, p0=None, group=None, emulate_ranks=None, stats=None, poll_every=4,
+                         exchange="nccl"):
     """Registers one image pair with the pixels of every iteration split by rows over the ranks of
     ``group`` (``torch.distributed``, NCCL).  ``I1``/``I2``: float32 CUDA tensors ``[H, W, C]`` (the full
     images, on every rank).  Returns ``(p [8], err, iters [nscales])``, identical on all ranks.
+
+    ``exchange="nccl"`` (default) drives the loop from the host: per iteration K2 on the band, one NCCL allreduce of the
+    105 moment sums, K3.  ``exchange="peer"`` moves the exchange into the device-side loop: the ranks map one another's
+    exchange buffers (CUDA IPC over NVLink, set up once per plan through ``group``) and the solve kernel adds the moment
+    sums through them -- one CUDA-graph launch per registration, no collective call and no host round trip per
+    iteration; ``stats`` then receives ``exchange_us_mean`` (publish -> every rank's sums seen).
 
     ``emulate_ranks=W`` runs W bands one after the other on the current GPU and adds their moments
     locally -- the same kernels and band arithmetic without a process group (used by the tests).
@@ -95,6 +102,14 @@ def register_row_sharded(I1, I2, transform_type, *, nscales=5, nu=0.5, robust_ty
     rt = RobustErrorFunctionType(getattr(robust_type, "value", robust_type)).value
     if robust_loop is None:
         robust_loop = rt != 0
+    if exchange not in ("nccl", "peer"):
+        raise ValueError("exchange must be 'nccl' or 'peer'")
+    if exchange == "peer":
+        if emulate_ranks:
+            raise ValueError("the peer exchange waits on other GPUs inside a kernel: it cannot be emulated on one GPU")
+        return _register_row_sharded_peer(I1, I2, transform_type, nscales=nscales, nu=nu, rt=rt, robust_loop=robust_loop,
+                                          lambda_=lambda_, tol=tol, max_iter=max_iter, delta=delta, nanifoutside=nanifoutside,
+                                          gray_as_rgb=gray_as_rgb, p0=p0, group=group, stats=stats)
     if emulate_ranks:
         world, ranks = int(emulate_ranks), list(range(int(emulate_ranks)))
     else:
@@ -165,4 +180,52 @@ def register_row_sharded(I1, I2, transform_type, *, nscales=5, nu=0.5, robust_ty
         stats["world"] = world
         if want_time:
             stats["allreduce_ms"] = [a.elapsed_time(b) for a, b in ar_events]
+    return p[0], float(err[0]), iters[0]
+
+
+def _register_row_sharded_peer(I1, I2, transform_type, *, nscales, nu, rt, robust_loop, lambda_, tol, max_iter, delta,
+                               nanifoutside, gray_as_rgb, p0, group, stats):
+    """``register_row_sharded(..., exchange="peer")``: plan with a peer-mapped exchange buffer per rank, the whole
+    registration as one graph launch (C-ABI ``ica_plan_xchg_create / _connect / ica_plan_run_row_sharded``)."""
+    import torch
+    import torch.distributed as dist
+    from . import _native
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    H, W, Cn = (int(v) for v in I1.shape)
+    tt = int(getattr(transform_type, "value", transform_type))
+    key = ("peer", torch.cuda.current_device(), H, W, Cn, nscales, nu, tt, rt, bool(robust_loop), lambda_, tol, max_iter, delta,
+           bool(nanifoutside), bool(gray_as_rgb), rank, world)
+    pl = _ROW_PLANS.get(key)
+    if pl is None:
+        pl = _native.Plan(batch=1, height=H, width=W, channels=Cn, nscales=nscales, nu=nu, transform_type=tt, robust_type=rt,
+                          robust_loop=bool(robust_loop), lambda_=lambda_, tol=tol, max_iter=max_iter, delta=delta,
+                          nanifoutside=nanifoutside, gray_as_rgb=bool(gray_as_rgb) and Cn == 1)
+        handle = pl.xchg_create(world, rank)
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, handle, group=group)
+            pl.xchg_connect(b"".join(handles))
+            dist.barrier(group=group)          # every rank has mapped every buffer before anybody writes
+        if len(_ROW_PLANS) >= 16:
+            _ROW_PLANS.pop(next(iter(_ROW_PLANS))).close()
+        _ROW_PLANS[key] = pl
+    dev = I1.device
+    p_dev = torch.zeros((1, 8), dtype=torch.float64, device=dev)
+    if p0 is not None:
+        p0 = np.asarray(p0, dtype=np.float64)
+        p_dev[0, :p0.size] = torch.from_numpy(p0).to(dev)
+    stream = torch.cuda.current_stream()
+    pl.run_row_sharded(I1.data_ptr(), I2.data_ptr(), p_dev.data_ptr(), stream.cuda_stream)
+    stream.synchronize()
+    p, err, iters = pl.results()
+    if stats is not None:
+        st = pl.xchg_stats()
+        if st["error"]:
+            raise RuntimeError("row-sharded registration: a peer did not answer within the exchange time-out")
+        stats["iterations"] = int(iters.sum())
+        stats["launched_iterations"] = int(st["count"])
+        stats["world"] = world
+        stats["exchange_us_mean"] = st["mean_us"]
+        stats["allreduce_ms"] = [st["mean_us"] * 1e-3] * max(1, int(st["count"]))
     return p[0], float(err[0]), iters[0]

@@ -272,7 +272,7 @@ def make_pair_hash(seed: int, pair: int, height: int, width: int, channels: int,
 
 def make_batch_device(batch: int, height: int, width: int, channels: int, transform_types, *, seed: int = 0,
                       pair_offset: int = 0, device="cuda", max_shift=8.0, max_lin=0.02, noise_sigma=1.0, occlusion=0.0,
-                      margin=64, quantize=True):
+                      margin=64, quantize=True, p_gt=None):
     """Benchmark-sized batches generated on the GPU by the library's own kernels (``ica_generate_pairs_device``); torch is
     only the container of the device buffers.  Pair ``i`` of the result is pair ``pair_offset + i`` of the set ``seed``
     (the numpy mirror :func:`make_pair_hash` regenerates any of them on the CPU).
@@ -288,6 +288,8 @@ def make_batch_device(batch: int, height: int, width: int, channels: int, transf
     for i, t in enumerate(types):
         p, (ox, oy, side) = pair_ground_truth(seed, pair_offset + i, height, width, t, max_shift=max_shift,
                                               max_lin=max_lin, occlusion=occlusion)
+        if p_gt is not None:           # explicit ground truth (rows of up to 8 parameters) instead of the drawn one
+            p = np.asarray(p_gt, dtype=np.float64).reshape(batch, -1)[i][:t.nparams()]
         p_all[i, :len(p)] = p
         occ_xy[i] = (ox, oy)
     dev = torch.device(device)

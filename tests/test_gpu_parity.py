@@ -393,9 +393,12 @@ torch.cuda.set_device(rank)
 dist.init_process_group("nccl", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=rank, world_size=2)
 t = TransformType.HOMOGRAPHY
 I1, I2, _ = synthetic.make_pair(901, 384, 512, 1, t, max_shift=3.0, margin=32)
-p, err, iters = register_row_sharded(torch.from_numpy(I1).cuda(), torch.from_numpy(I2).cuda(), t, nscales=3,
-                                     robust_type=3, delta=5)
-np.savez(sys.argv[4] % rank, p=p, err=err, iters=iters)
+a, b = torch.from_numpy(I1).cuda(), torch.from_numpy(I2).cuda()
+p, err, iters = register_row_sharded(a, b, t, nscales=3, robust_type=3, delta=5)
+# the same registration with the exchange inside the device-side loop (peer memory over NVLink, no NCCL call per iteration)
+st = {}
+pp, perr, piters = register_row_sharded(a, b, t, nscales=3, robust_type=3, delta=5, exchange="peer", stats=st)
+np.savez(sys.argv[4] % rank, p=p, err=err, iters=iters, pp=pp, piters=piters, xus=st["exchange_us_mean"])
 dist.barrier(); dist.destroy_process_group()
 print("ok")
 """
@@ -428,6 +431,30 @@ def test_row_sharded_nccl_two_gpus(nat, tmp_path):
     ref_p, _, ref_it = register_batch(I1[None], I2[None], t, nscales=3, robust_type=3, delta=5)
     assert np.array_equal(r0["iters"], ref_it[0])
     assert _epe(r0["p"], ref_p[0], t.value, 512, 384) <= 1e-6
+    # peer exchange: bit-identical on both ranks and equal to the NCCL path (both add the two bands' sums in rank order)
+    assert np.array_equal(r0["pp"], r1["pp"]) and np.array_equal(r0["piters"], r1["piters"])
+    assert np.array_equal(r0["piters"], ref_it[0])
+    assert _epe(r0["pp"], ref_p[0], t.value, 512, 384) <= 1e-6
+    print("peer exchange latency (us, mean):", float(r0["xus"]), float(r1["xus"]))
+
+
+def test_row_sharded_peer_exchange_single_rank(nat):
+    """The device-side exchange path with a group of one (the rank publishes to and waits on its own buffer): the whole
+    registration is one graph launch of {K2, K3 with exchange}; result identical to the plain device-side loop."""
+    import torch
+    from inverse_compositional_algorithm_b200 import synthetic
+    from inverse_compositional_algorithm_b200.inverse_compositional_algorithm import register_batch
+    from inverse_compositional_algorithm_b200.sharding import register_row_sharded
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    t = TransformType.HOMOGRAPHY
+    I1, I2, _ = synthetic.make_pair(902, 300, 400, 1, t, max_shift=3.0, margin=32)
+    ref_p, ref_err, ref_it = register_batch(I1[None], I2[None], t, nscales=3, robust_type=3, delta=5)
+    for rep in range(2):        # the second run reuses the plan, its graph and the next range of sequence numbers
+        st = {}
+        p, err, iters = register_row_sharded(torch.from_numpy(I1).cuda(), torch.from_numpy(I2).cuda(), t, nscales=3,
+                                             robust_type=3, delta=5, exchange="peer", stats=st)
+        assert np.array_equal(iters, ref_it[0]) and np.array_equal(p, ref_p[0]) and err == ref_err[0]
+        assert st["launched_iterations"] == int(ref_it[0].sum())
 
 
 @pytest.mark.parametrize("shape,channels,ttype_name,rtype", [((93, 121), 3, "HOMOGRAPHY", 3), ((77, 101), 1, "AFFINITY", 0),
@@ -742,3 +769,52 @@ def test_hessian_b_8192_wide_gray_vs_rowblocked_oracle(nat, golden_dir):
     assert h_err <= 1e-6       # measured 1.6e-8
     assert dp_err <= HB8192_DP_RTOL
     assert epe <= 1e-5         # measured 2.1e-7 px
+
+
+# ------------------------------------------------------------------ ingest and input synthesis
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32, np.float64])
+def test_rgb_to_luminance_ingest(nat, dtype):
+    """RGB host images registered on their luminance (converted on the device from the uploaded RGB data) give bit for
+    bit what registering the luminance computed on the host gives: Y = 0.2125 R + 0.7154 G + 0.0721 B in float64,
+    rounded once to float32."""
+    from inverse_compositional_algorithm_b200 import synthetic
+    from inverse_compositional_algorithm_b200.inverse_compositional_algorithm import register_batch
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    t = TransformType.AFFINITY
+    pairs = [synthetic.make_pair(70 + i, 120, 160, 3, t, max_shift=3.0, margin=32) for i in range(2)]
+    I1 = np.round(np.stack([a for a, _, _ in pairs])).astype(dtype)
+    I2 = np.round(np.stack([b for _, b, _ in pairs])).astype(dtype)
+
+    def luma(x):
+        x = x.astype(np.float64)
+        return ((0.2125 * x[..., 0] + 0.7154 * x[..., 1]) + 0.0721 * x[..., 2]).astype(np.float32)[..., None]
+    pl, el, il = register_batch(I1, I2, t, nscales=3, robust_type=3, delta=5, luminance=True)
+    pg, eg, ig = register_batch(luma(I1), luma(I2), t, nscales=3, robust_type=3, delta=5)
+    assert np.array_equal(pl, pg) and np.array_equal(il, ig) and np.array_equal(el, eg)
+    with pytest.raises(ValueError):
+        register_batch(I1[..., :1], I2[..., :1], t, luminance=True)
+
+
+def test_device_generator_matches_numpy_mirror_and_registers(nat):
+    """The device-side pair generator (csrc/ica_generate.cu) against its numpy mirror (same counter-based noise, blur,
+    resampling): 8-bit values equal except for a handful of rounding ties; generated pairs register to their ground
+    truth; a pair's content depends on (seed, pair index) only."""
+    import torch
+    from inverse_compositional_algorithm_b200 import synthetic
+    from inverse_compositional_algorithm_b200.inverse_compositional_algorithm import register_batch_device
+    from inverse_compositional_algorithm_b200.transformation import TransformType, end_point_error
+    t = TransformType.HOMOGRAPHY
+    for (H, W, C, occ) in ((96, 128, 3, 0.2), (120, 160, 1, 0.0)):
+        I1, I2, p = synthetic.make_batch_device(4, H, W, C, t, seed=3, pair_offset=2, occlusion=occ, margin=32)
+        a1, a2, pg = synthetic.make_pair_hash(3, 3, H, W, C, t, occlusion=occ, margin=32)      # = pair 1 of the batch
+        d1 = np.abs(I1[1].cpu().numpy() - a1)
+        d2 = np.abs(I2[1].cpu().numpy() - a2)
+        assert d1.max() <= 1.0 and d2.max() <= 1.0 and (d1 > 0).mean() < 2e-3 and (d2 > 0).mean() < 2e-3
+        assert np.allclose(p[1], np.pad(pg, (0, 8 - len(pg))))
+        J1, J2, _ = synthetic.make_batch_device(2, H, W, C, t, seed=3, pair_offset=3, occlusion=occ, margin=32)
+        assert torch.equal(J1[0], I1[1]) and torch.equal(J2[0], I2[1])       # pair 3 regenerated alone
+    I1, I2, p = synthetic.make_batch_device(6, 256, 320, 3, t, seed=11, max_shift=4.0)
+    pr, err, it = register_batch_device(I1, I2, t, nscales=3, robust_type=3, delta=5)
+    pr = pr.cpu().numpy()
+    for i in range(6):
+        assert end_point_error(pr[i], p[i], t, 320, 256)[1] <= 0.05

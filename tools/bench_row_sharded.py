@@ -29,6 +29,9 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--max-lin", type=float, default=0.002, help="size of the linear part of the ground-truth motion")
     ap.add_argument("--emulate", type=int, default=0, help="emulate this many ranks on one GPU (no NCCL)")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+                    help="nccl: host-driven loop with one NCCL allreduce per iteration; peer: exchange inside the "
+                         "device-side loop through peer-mapped buffers (NVLink), one graph launch per registration")
     args = ap.parse_args()
 
     import torch
@@ -47,8 +50,10 @@ def main():
     t = TransformType.HOMOGRAPHY
     n = args.size
     # the same pair on every rank (same seed); ground truth known
-    I1, I2, p_gt = synthetic.make_batch_torch(1, n, n, 1, t, seed=5, device="cuda", max_shift=8.0,
-                                              max_lin=args.max_lin, chunk=1)
+    # ground truth: a few pixels of shift, a linear part and a perspective part that move the far corner by ~10 px each
+    lin, persp = 10.0 / n, 10.0 / (n * n)
+    p_true = [0.6 * lin, -0.4 * lin, 5.3, 0.5 * lin, -0.7 * lin, -3.7, 0.6 * persp, -0.5 * persp]
+    I1, I2, p_gt = synthetic.make_batch_device(1, n, n, 1, t, seed=5, device="cuda", p_gt=[p_true])
     I1, I2 = I1[0].contiguous(), I2[0].contiguous()
     rt = RobustErrorFunctionType[args.robust]
     times, ar, iters_all = [], [], None
@@ -60,7 +65,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         p, err, iters = register_row_sharded(I1, I2, t, nscales=args.nscales, robust_type=rt, delta=10,
-                                             emulate_ranks=args.emulate or None, stats=stats)
+                                             emulate_ranks=args.emulate or None, stats=stats, exchange=args.exchange)
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
@@ -80,10 +85,11 @@ def main():
         print(json.dumps({
             "workload": f"single {n}x{n} grayscale pair, homography, {args.robust}, {args.nscales} scales, "
                         f"row-sharded over {args.emulate or world} ranks" + (" (emulated on one GPU)" if args.emulate else ""),
-            "n_gpus": world, "ms_per_registration": float(np.median(times)), "reps": args.reps,
+            "n_gpus": world, "exchange": args.exchange, "ms_per_registration": float(np.median(times)), "reps": args.reps,
             "iterations": int(stats["iterations"]), "launched_iterations": int(stats["launched_iterations"]), "iters_per_scale(coarse->fine)": [int(v) for v in iters_all[::-1]],
             "allreduce_ms_median": float(np.median(ar)), "allreduce_ms_mean": float(ar.mean()),
             "allreduce_ms_p95": float(np.percentile(ar, 95)), "allreduce_bytes": 105 * 8,
+            "exchange_us_mean(peer mode: publish -> all ranks seen)": stats.get("exchange_us_mean"),
             "epe_vs_ground_truth_px": epe}))
     if world > 1:
         dist.barrier()
