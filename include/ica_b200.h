@@ -55,6 +55,11 @@ typedef enum {
 /* ica_plan_run_host dtype modifier: the host images are RGB [B][H][W][3] and the (one-channel) plan registers their
    luminance Y = 0.2125 R + 0.7154 G + 0.0721 B (skimage.color.rgb2gray weights), converted on the device */
 #define ICA_DTYPE_RGB_TO_LUMA 0x10
+/* IPOL-faithful options the reference carries but does not use on its default path; with both set the
+   quadratic runs reproduce the IPOL C++ console logs stored in the reference's docs/Algortihm Report.md:38-339 */
+#define ICA_FLAG_IPOL_PYRAMID 16u     /* levels by zoom.zoom_out (src/zoom.py:29-60) instead of skimage rescale */
+#define ICA_FLAG_IPOL_WARP 32u        /* warp domain of bicubic_interpolation_image (src/bicubic_interpolation.py:121-152):
+                                         valid iff the projected point lies in [delta, n-1-delta]; no clip; needs delta >= 2 */
 #define ICA_FLAG_HOST_LOOP 8u         /* drive the iteration loop from the host (polling) instead of the
                                          default CUDA-graph while node whose condition is set on the device */
 

@@ -21,6 +21,8 @@ TRAJ_STRIDE = 12
 FLAG_RECORD_TRAJECTORY = 1
 FLAG_WRITE_DI_IW = 2
 FLAG_HOST_LOOP = 8
+FLAG_IPOL_PYRAMID = 16   # zoom.zoom_out levels instead of skimage rescale
+FLAG_IPOL_WARP = 32      # warp domain of bicubic_interpolation_image instead of skimage.transform.warp's
 
 DTYPE_F32, DTYPE_U8, DTYPE_F64 = 0, 1, 2
 DTYPE_RGB_TO_LUMA = 0x10     # modifier: RGB host images, one-channel plan registers their luminance
@@ -430,10 +432,12 @@ class Plan:
 
     def __init__(self, *, batch, height, width, channels, nscales, nu, transform_type, robust_type,
                  robust_loop, lambda_, tol, max_iter, delta, nanifoutside, gray_as_rgb=False,
-                 record_trajectory=False, write_di_iw=False, blocks_per_pair=0, host_loop=False):
+                 record_trajectory=False, write_di_iw=False, blocks_per_pair=0, host_loop=False, ipol_pyramid=False,
+                 ipol_warp=False):
         require_gpu()
         flags = (FLAG_RECORD_TRAJECTORY if record_trajectory else 0) | (
-            FLAG_WRITE_DI_IW if write_di_iw else 0) | (FLAG_HOST_LOOP if host_loop else 0)
+            FLAG_WRITE_DI_IW if write_di_iw else 0) | (FLAG_HOST_LOOP if host_loop else 0) | (
+            FLAG_IPOL_PYRAMID if ipol_pyramid else 0) | (FLAG_IPOL_WARP if ipol_warp else 0)
         self.cfg = Config(batch=batch, height=height, width=width, channels=channels,
                           gray_as_rgb=1 if gray_as_rgb else 0, nscales=nscales, nu=nu,
                           transform_type=int(transform_type), robust_type=int(robust_type),

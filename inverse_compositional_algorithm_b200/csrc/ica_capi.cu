@@ -83,6 +83,7 @@ struct ica_plan {
   DeviceResample ry[ICA_MAX_SCALES], rx[ICA_MAX_SCALES];
   PairState* state = nullptr;
   MinMaxKeys* mm = nullptr;
+  MinMaxKeys* mm_open = nullptr;    // IPOL pyramid (no clip): open parent ranges
   double* partials = nullptr;
   double* traj = nullptr;
   int traj_cap = 0;
@@ -176,6 +177,10 @@ int validate_config(const ica_config* c) {
   if (!(c->tol < 0.01)) { set_error("TOL must be positive and very small (less than 0.01)"); return ICA_ERR_INVALID; }
   if (c->max_iter < 1) { set_error("max_iter must be >= 1"); return ICA_ERR_INVALID; }
   if (c->delta < 0) { set_error("delta must be >= 0"); return ICA_ERR_INVALID; }
+  if ((c->flags & ICA_FLAG_IPOL_WARP) && c->delta < 2) {
+    set_error("the IPOL warp domain needs delta >= 2 on the registration path (clamped neighbours are only in the bicubic_interpolation_image helper)");
+    return ICA_ERR_INVALID;
+  }
   return ICA_OK;
 }
 
@@ -320,6 +325,8 @@ void fill_iter_params(const ica_plan* pl, const float* /*I1*/, const float* /*I2
   P->delta = pl->cfg.delta;
   P->frame = (pl->cfg.nanifoutside != 0 && pl->cfg.delta > 0) ? 1 : 0;
   P->ch_mult = (pl->C == 1 && pl->cfg.gray_as_rgb) ? 3.0f : 1.0f;
+  P->ipol_warp = (pl->cfg.flags & ICA_FLAG_IPOL_WARP) ? 1 : 0;
+  P->ipol_nan = pl->cfg.nanifoutside != 0 ? 1 : 0;
 }
 
 // CUDA graph of the iteration loop: one conditional WHILE node whose body is {iterate, solve}; the solve
@@ -392,7 +399,7 @@ int build_pyramids(ica_plan* pl, const float* I1, const float* I2, cudaStream_t 
       if (pl->timing && pl->n_ev_pyr + 2 <= (int)pl->ev_pyr.size()) cudaEventRecord(pl->ev_pyr[pl->n_ev_pyr++], stream);
       ICA_LAUNCH_CHECK(launch_pyr_down(ina, inb, istr, Li.pitch, Li.nx, Li.ny, pl->C, pl->ry[s], pl->rx[s], pl->tmp,
                                        tmp_per_img, outa, outb, pl->pyr_stride, Lo.pitch, nset,
-                                       pl->mm + ((long long)b0 * ns + s) * 2, pl->mm + ((long long)b0 * ns + s + 1) * 2,
+                                       (pl->mm_open ? pl->mm_open : pl->mm) + ((long long)b0 * ns + s) * 2, pl->mm + ((long long)b0 * ns + s + 1) * 2,
                                        ns * 2, stream, &nl));
       if (pl->timing && pl->n_ev_pyr + 1 <= (int)pl->ev_pyr.size()) cudaEventRecord(pl->ev_pyr[pl->n_ev_pyr++], stream);
       pl->launches += nl;
@@ -440,6 +447,7 @@ int ica_plan_destroy(ica_plan* pl) {
   for (int r = 0; r < pl->x_world; ++r) if (r != pl->x_rank && pl->x_peer_ptr[r]) cudaIpcCloseMemHandle(pl->x_peer_ptr[r]);
   cudaFree(pl->xbuf); cudaFree(pl->x_peers_dev); cudaFree(pl->x_error); cudaFree(pl->x_ns); cudaFree(pl->x_seq_dev);
   if (pl->x_seq_host) cudaFreeHost(pl->x_seq_host);
+  cudaFree(pl->mm_open);
   cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->item_pair); cudaFree(pl->solve_ticket); cudaFree(pl->asm_tab); cudaFree(pl->loop_count); cudaFree(pl->kernel_ns); cudaFree(pl->hdr); cudaFree(pl->pair_ticket);
   if (pl->h_loop) cudaFreeHost(pl->h_loop);
   if (pl->h_kns) cudaFreeHost(pl->h_kns);
@@ -516,16 +524,23 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
     TRY(dev_alloc(pl, &pl->tmp, (size_t)pl->tmp_floats));
     for (int s = 0; s + 1 < pl->nscales; ++s) {
       Resample1D r;
-      build_resample_1d(pl->lv[s].ny, pl->lv[s + 1].ny, &r);
+      const bool ipol_pyr = (cfg->flags & ICA_FLAG_IPOL_PYRAMID) != 0;   // zoom.zoom_out levels instead of skimage rescale
+      if (ipol_pyr) build_zoom_out_1d(pl->lv[s].ny, cfg->nu, 0.6, &r); else build_resample_1d(pl->lv[s].ny, pl->lv[s + 1].ny, &r);
       if (r.taps > max_taps()) { set_error("resampling operator too wide (%d taps)", r.taps); ica_plan_destroy(pl); return ICA_ERR_INVALID; }
       TRY(upload_resample(pl, r, &pl->ry[s]));
-      build_resample_1d(pl->lv[s].nx, pl->lv[s + 1].nx, &r);
+      if (ipol_pyr) build_zoom_out_1d(pl->lv[s].nx, cfg->nu, 0.6, &r); else build_resample_1d(pl->lv[s].nx, pl->lv[s + 1].nx, &r);
       if (r.taps > max_taps()) { set_error("resampling operator too wide (%d taps)", r.taps); ica_plan_destroy(pl); return ICA_ERR_INVALID; }
       TRY(upload_resample(pl, r, &pl->rx[s]));
     }
   }
   TRY(dev_alloc(pl, &pl->state, (size_t)pl->B));
   TRY(dev_alloc(pl, &pl->mm, (size_t)pl->B * pl->nscales * 2));
+  if (cfg->flags & ICA_FLAG_IPOL_PYRAMID) {   // zoom_out does not clip: the pyramid kernels get an open parent range
+    TRY(dev_alloc(pl, &pl->mm_open, (size_t)pl->B * pl->nscales * 2));
+    std::vector<MinMaxKeys> open_keys((size_t)pl->B * pl->nscales * 2);
+    for (auto& k : open_keys) { k.lo = float_key(-3.4028235e38f); k.hi = float_key(3.4028235e38f); }
+    TRY_CUDA(cudaMemcpy(pl->mm_open, open_keys.data(), open_keys.size() * sizeof(MinMaxKeys), cudaMemcpyHostToDevice));
+  }
   TRY(dev_alloc(pl, &pl->partials, (size_t)pl->B * pl->max_chunks * kAccStride));
   TRY(dev_alloc(pl, &pl->chunk_start, 2 * ((size_t)pl->B + 1)));                 // double-buffered work lists
   TRY(dev_alloc(pl, &pl->item_pair, 2 * (size_t)pl->B * pl->max_chunks));
@@ -715,7 +730,7 @@ int ica_plan_shard_finish(ica_plan* pl, double* p_out, void* stream_) {
   pl->launches += 1;
   if (pl->cfg.flags & ICA_FLAG_WRITE_DI_IW) {
     ICA_LAUNCH_CHECK(launch_warp_out(pl->last_I1, pl->last_I2, pl->in_stride, pl->W, pl->H, pl->C, pl->state, pl->mm, pl->nscales,
-                                     pl->B, pl->Iw_dev, pl->DI_dev, stream));
+                                     pl->B, pl->Iw_dev, pl->DI_dev, (pl->cfg.flags & ICA_FLAG_IPOL_WARP) ? 1 : 0, pl->cfg.nanifoutside != 0, pl->cfg.delta, stream));
     pl->launches += 1;
   }
   return ICA_OK;
@@ -881,7 +896,8 @@ int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* 
   pl->launches += 1;
   if (pl->cfg.flags & ICA_FLAG_WRITE_DI_IW) {
     ICA_LAUNCH_CHECK(launch_warp_out(I1, I2, pl->in_stride, pl->W, pl->H, pl->C, pl->state, pl->mm, pl->nscales, pl->B,
-                                     pl->Iw_dev, pl->DI_dev, stream));
+                                     pl->Iw_dev, pl->DI_dev, (pl->cfg.flags & ICA_FLAG_IPOL_WARP) ? 1 : 0, pl->cfg.nanifoutside != 0,
+                                     pl->cfg.delta, stream));
     pl->launches += 1;
   }
   return ICA_OK;

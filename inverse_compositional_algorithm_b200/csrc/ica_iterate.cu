@@ -766,6 +766,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   const bool robust = P.robust_loop != 0;
   const float chm = P.ch_mult;
   const int rtype = P.robust_type;
+  const bool ipol = P.ipol_warp != 0, ipol_nan = P.ipol_nan != 0;
   // fp64 accumulators of the chunk in progress, double-buffered over consecutive chunks: [2][kConsumerWarps][K][kYPow]
   double* const accs0 = reinterpret_cast<double*>(smem + kStages * Stage<C>::kFloats);
   constexpr int kAccSet = kConsumerWarps * K * kYPow;
@@ -940,6 +941,15 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
                 iw[ch] = acc2;
               }
             }
+            // IPOL-style warp domain (bi.py:144): the projected point must lie in [delta, n - 1 - delta]; with the exact
+            // integer parts this is a test on (c, t).  Valid pixels have their 4 x 4 taps inside the image (delta >= 2).
+            bool okA = true, okB = true, inA = true, inB = true;
+            if (ipol) {
+              const int hx = nx - 1 - delta, hy = ny - 1 - delta;
+              inA = cxA >= delta && cyA >= delta && (cxA < hx || (cxA == hx && tx2.x == 0.0f)) && (cyA < hy || (cyA == hy && ty2.x == 0.0f));
+              inB = cxB >= delta && cyB >= delta && (cxB < hx || (cxB == hx && tx2.y == 0.0f)) && (cyB < hy || (cyB == hy && ty2.y == 0.0f));
+              okA = inA || !ipol_nan; okB = inB || !ipol_nan;
+            }
             // phase 2: residual, gradient of I1 (masks fold the 1/2, the frame and the image border), S, v
             float2 mgx, mgy;
             {
@@ -958,8 +968,15 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
             float2 sxx = make_float2(0.f, 0.f), sxy = sxx, syy = sxx, vx = sxx, vy = sxx, t2 = sxx;
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) {
-              const bool vA = iw[ch].x == iw[ch].x, vB = iw[ch].y == iw[ch].y;   // NaN footprint
-              const float iwA = fminf(fmaxf(iw[ch].x, fl.x), fl.y), iwB = fminf(fmaxf(iw[ch].y, fl.x), fl.y);
+              bool vA, vB;
+              float iwA, iwB;
+              if (!ipol) {
+                vA = iw[ch].x == iw[ch].x; vB = iw[ch].y == iw[ch].y;            // NaN footprint
+                iwA = fminf(fmaxf(iw[ch].x, fl.x), fl.y); iwB = fminf(fmaxf(iw[ch].y, fl.x), fl.y);   // clip (Q1)
+              } else {
+                vA = okA; vB = okB;
+                iwA = inA ? iw[ch].x : 0.0f; iwB = inB ? iw[ch].y : 0.0f;
+              }
               const float2 gx = __ffma2_rn(make_float2(cA[ch + C], cB[ch + C]), mgx, __fmul2_rn(make_float2(cA[ch - C], cB[ch - C]), nmgx));
               const float2 gy = __ffma2_rn(make_float2(cA[ch + S1W], cB[ch + S1W]), mgy, __fmul2_rn(make_float2(cA[ch - S1W], cB[ch - S1W]), nmgy));
               const float2 di = make_float2(vA ? iwA - cA[ch] : 0.0f, vB ? iwB - cB[ch] : 0.0f);   // non-finite -> 0 (io.py:72, 134)
@@ -1017,8 +1034,16 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
                 } else {
                   iwv = sample_global_slow<C>(tc->I2, lds_i4(&tc->flg).w, nx, ny, cx, cy, ch, wxs[0], wxs[1], wxs[2], wxs[3], wys[0], wys[1], wys[2], wys[3]);
                 }
-                const bool valid = iwv == iwv;             // NaN footprint
-                iwv = fminf(fmaxf(iwv, lo), hi);           // clip (only used when valid)
+                bool valid;
+                if (!ipol) {
+                  valid = iwv == iwv;                      // NaN footprint
+                  iwv = fminf(fmaxf(iwv, lo), hi);         // clip (only used when valid)
+                } else {
+                  const int hx = nx - 1 - delta, hy = ny - 1 - delta;
+                  const bool in = pok && cx >= delta && cy >= delta && (cx < hx || (cx == hx && tx == 0.0f)) && (cy < hy || (cy == hy && ty == 0.0f));
+                  valid = in || !ipol_nan;
+                  iwv = in ? iwv : 0.0f;
+                }
                 const float i1c = c1[ch];
                 const float gx = gxok ? 0.5f * (c1[ch + C] - c1[ch - C]) : 0.0f;
                 const float gy = gyok ? 0.5f * (c1[ch + S1W] - c1[ch - S1W]) : 0.0f;
@@ -1133,7 +1158,7 @@ template <int C>
 __global__ void ica_warp_out_kernel(const float* __restrict__ I1_0, const float* __restrict__ I2_0,
                                     long long in_stride, int nx, int ny, int pitch,
                                     const PairState* state, const MinMaxKeys* mm, int nscales,
-                                    float* __restrict__ Iw, float* __restrict__ DI) {
+                                    float* __restrict__ Iw, float* __restrict__ DI, int ipol, int ipol_nan, int delta) {
   const int pair = blockIdx.z;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -1159,7 +1184,13 @@ __global__ void ica_warp_out_kernel(const float* __restrict__ I1_0, const float*
 #pragma unroll
   for (int ch = 0; ch < C; ++ch) {
     float iw = pok ? sample_global<C>(I2, pitch, nx, ny, cx, cy, ch, wx, wy) : __int_as_float(0x7fc00000);
-    if (iw == iw) iw = fminf(fmaxf(iw, slo), shi);
+    if (!ipol) {
+      if (iw == iw) iw = fminf(fmaxf(iw, slo), shi);
+    } else {      // IPOL-style domain on the projected point, no clip (bi.py:144-150)
+      const int hx = nx - 1 - delta, hy = ny - 1 - delta;
+      const bool in = pok && cx >= delta && cy >= delta && (cx < hx || (cx == hx && tx == 0.0f)) && (cy < hy || (cy == hy && ty == 0.0f));
+      if (!in) iw = ipol_nan ? __int_as_float(0x7fc00000) : 0.0f;
+    }
     Iw[o + ch] = iw;
     DI[o + ch] = iw - I1[(long long)y * pitch + x * C + ch];
   }
@@ -1300,12 +1331,12 @@ cudaError_t launch_export_results(const PairState* state, int B, double* p_out, 
 
 cudaError_t launch_warp_out(const float* I1_0, const float* I2_0, long long in_stride, int nx, int ny, int channels,
                             const PairState* state, const MinMaxKeys* mm, int nscales, int B, float* Iw, float* DI,
-                            cudaStream_t stream) {
+                            int ipol_warp, int ipol_nan, int delta, cudaStream_t stream) {
   dim3 block(32, 8), grid((nx + 31) / 32, (ny + 7) / 8, B);
   if (channels == 3)
-    ica_warp_out_kernel<3><<<grid, block, 0, stream>>>(I1_0, I2_0, in_stride, nx, ny, nx * 3, state, mm, nscales, Iw, DI);
+    ica_warp_out_kernel<3><<<grid, block, 0, stream>>>(I1_0, I2_0, in_stride, nx, ny, nx * 3, state, mm, nscales, Iw, DI, ipol_warp, ipol_nan, delta);
   else
-    ica_warp_out_kernel<1><<<grid, block, 0, stream>>>(I1_0, I2_0, in_stride, nx, ny, nx, state, mm, nscales, Iw, DI);
+    ica_warp_out_kernel<1><<<grid, block, 0, stream>>>(I1_0, I2_0, in_stride, nx, ny, nx, state, mm, nscales, Iw, DI, ipol_warp, ipol_nan, delta);
   return cudaGetLastError();
 }
 

@@ -72,6 +72,9 @@ struct IterParams {
   int delta;
   int frame;              // nanifoutside && delta > 0
   float ch_mult;          // 3 for a gray image standing for its RGB replication, else 1
+  int ipol_warp;          // 1: IPOL-style warp domain (bicubic_interpolation_image, bi.py:121-152): a pixel is valid iff its
+                          //    projected point lies in [delta, n-1-delta]; no clip; 0 instead of NaN when ipol_nan == 0
+  int ipol_nan;           // IPOL warp: value outside the domain is NaN (discarded) / 0 (kept as a residual of -I1)
 };
 
 void build_assembly_table(int dh, AsmEntry* tab /* [6*72] */);
@@ -89,7 +92,7 @@ cudaError_t launch_export_results(const PairState* state, int B, double* p_out, 
                                   int nscales, cudaStream_t stream);
 cudaError_t launch_warp_out(const float* I1_0, const float* I2_0, long long in_stride, int nx, int ny, int channels,
                             const PairState* state, const MinMaxKeys* mm, int nscales, int B, float* Iw, float* DI,
-                            cudaStream_t stream);
+                            int ipol_warp, int ipol_nan, int delta, cudaStream_t stream);
 cudaError_t launch_warp_matrix(const float* img, int nx, int ny, int channels, const double* m9, const MinMaxKeys* mm,
                                float* out, cudaStream_t stream);
 cudaError_t launch_gradient(const float* img, int nx, int ny, int channels, int delta, int frame, float* Ix,

@@ -91,7 +91,7 @@ def _print_trace(traj, n, quadratic, with_scale):
 
 
 def _run_single(I1, I2, p, transform_type, nscales, nu, TOL, robust_type, robust_loop, lambda_,
-                nanifoutside, delta, verbose):
+                nanifoutside, delta, verbose, ipol_pyramid=False, ipol_warp=False):
     t = _as_type(transform_type)
     r = _as_robust(robust_type)
     n = t.nparams()
@@ -101,7 +101,8 @@ def _run_single(I1, I2, p, transform_type, nscales, nu, TOL, robust_type, robust
                          transform_type=t.value, robust_type=r.value, robust_loop=bool(robust_loop),
                          lambda_=float(lambda_), tol=float(TOL), max_iter=cts.MAX_ITER, delta=int(delta),
                          nanifoutside=(nanifoutside is True), gray_as_rgb=False,
-                         record_trajectory=bool(verbose), write_di_iw=True)
+                         record_trajectory=bool(verbose), write_di_iw=True, ipol_pyramid=bool(ipol_pyramid),
+                         ipol_warp=bool(ipol_warp))
         p0 = np.zeros(_native.MAX_PARAMS)
         p0[:n] = np.asarray(p, dtype=np.float64)[:n]
         pout, err, iters, DI, Iw = plan.run_host(_as_batch(I1), _as_batch(I2), p0[None], want_images=True)
@@ -110,20 +111,23 @@ def _run_single(I1, I2, p, transform_type, nscales, nu, TOL, robust_type, robust
     return pout[0, :n].copy(), float(err[0]), DI[0].astype(np.float64), Iw[0].astype(np.float64)
 
 
-def inverse_compositional_algorithm(I1, I2, p, transform_type, TOL, nanifoutside, delta, verbose):
+def inverse_compositional_algorithm(I1, I2, p, transform_type, TOL, nanifoutside, delta, verbose, *, ipol_warp=False):
     """Quadratic (L2) inverse compositional algorithm, one scale.
     Drop-in for ``src/inverse_compositional_algorithm.py:17-133``; ``p`` is updated in place when
-    it is a float64 array (the reference mutates it) and also returned."""
+    it is a float64 array (the reference mutates it) and also returned.
+    ``ipol_warp=True`` (keyword only, beyond the reference's signature) switches the loop's warp to the IPOL-style
+    domain of ``bicubic_interpolation_image``: the run then follows the IPOL C++ logs of the reference's
+    ``docs/Algortihm Report.md``."""
     _check_rgb(I1, I2)
     _check_common(I1, I2, TOL)
     pout, err, DI, Iw = _run_single(I1, I2, p, transform_type, 1, 0.5, TOL,
                                     RobustErrorFunctionType.QUADRATIC, False, 0.0, nanifoutside,
-                                    delta, verbose)
+                                    delta, verbose, ipol_warp=ipol_warp)
     return _writeback(p, pout), err, DI, Iw
 
 
 def robust_inverse_compositional_algorithm(I1, I2, p, transform_type, TOL, robust_type, lambda_,
-                                           nanifoutside, delta, verbose):
+                                           nanifoutside, delta, verbose, *, ipol_warp=False):
     """Robust inverse compositional algorithm, one scale.
     Drop-in for ``src/inverse_compositional_algorithm.py:135-261`` (rho' and the weighted Hessian
     are re-evaluated every iteration, also for QUADRATIC)."""
@@ -131,22 +135,26 @@ def robust_inverse_compositional_algorithm(I1, I2, p, transform_type, TOL, robus
     if len(I1.shape) != 3 or I1.shape[2] not in (1, 3):
         raise ValueError("I1 and I2 must be (H, W, 3) or (H, W, 1) images")
     pout, err, DI, Iw = _run_single(I1, I2, p, transform_type, 1, 0.5, TOL, robust_type, True,
-                                    lambda_, nanifoutside, delta, verbose)
+                                    lambda_, nanifoutside, delta, verbose, ipol_warp=ipol_warp)
     return _writeback(p, pout), err, DI, Iw
 
 
 def pyramidal_inverse_compositional_algorithm(I1, I2, p, transform_type, nscales, nu, TOL,
-                                              robust_type, lambda_, nanifoutside, delta, verbose):
+                                              robust_type, lambda_, nanifoutside, delta, verbose, *, ipol_pyramid=False,
+                                              ipol_warp=False):
     """Coarse-to-fine driver.  Drop-in for ``src/inverse_compositional_algorithm.py:264-374``:
     skimage-``rescale`` pyramid, QUADRATIC -> quadratic loop, anything else -> robust loop,
     ``zoom_in_parameters`` between scales; like the reference the input ``p`` is copied and only
-    used when ``nscales == 1`` (ica.py:327, 372)."""
+    used when ``nscales == 1`` (ica.py:327, 372).
+    Keyword-only options beyond the reference's signature (the IPOL-faithful variants the reference
+    carries as unused helpers): ``ipol_pyramid`` builds the levels with ``zoom.zoom_out`` instead of skimage ``rescale``,
+    ``ipol_warp`` uses the warp domain of ``bicubic_interpolation_image``."""
     _check_rgb(I1, I2)
     _check_common(I1, I2, TOL)
     r = _as_robust(robust_type)
     robust_loop = r != RobustErrorFunctionType.QUADRATIC
     return _run_single(I1, I2, np.copy(p), transform_type, nscales, nu, TOL, r, robust_loop, lambda_,
-                       nanifoutside, delta, verbose)
+                       nanifoutside, delta, verbose, ipol_pyramid=ipol_pyramid, ipol_warp=ipol_warp)
 
 
 def _writeback(p, pout):
@@ -158,7 +166,8 @@ def _writeback(p, pout):
 
 def register_batch(I1, I2, transform_type, nscales=1, nu=0.5, TOL=1e-3,
                    robust_type=RobustErrorFunctionType.QUADRATIC, lambda_=0.0, nanifoutside=True,
-                   delta=10, p0=None, gray_as_rgb=True, return_images=False, plan=None, luminance=False):
+                   delta=10, p0=None, gray_as_rgb=True, return_images=False, plan=None, luminance=False,
+                   ipol_pyramid=False, ipol_warp=False):
     """B independent registrations in one call: ``I1``/``I2`` are ``[B, H, W, C]`` (C = 1 or 3,
     float32 / uint8 / float64); ``transform_type`` is one type or a length-B sequence (mixed
     batches).  Returns ``(p [B, 8] zero-padded, error [B], iters [B, nscales])`` and, with
@@ -186,7 +195,8 @@ def register_batch(I1, I2, transform_type, nscales=1, nu=0.5, TOL=1e-3,
                              robust_loop=r != RobustErrorFunctionType.QUADRATIC, lambda_=float(lambda_),
                              tol=float(TOL), max_iter=cts.MAX_ITER, delta=int(delta),
                              nanifoutside=(nanifoutside is True), gray_as_rgb=bool(gray_as_rgb) and nz == 1,
-                             record_trajectory=False, write_di_iw=bool(return_images))
+                             record_trajectory=False, write_di_iw=bool(return_images), ipol_pyramid=bool(ipol_pyramid),
+                             ipol_warp=bool(ipol_warp))
         plan.set_transform_types([t.value for t in types])
         pout, err, iters, DI, Iw = plan.run_host(I1, I2, p0, want_images=return_images, rgb_to_luma=bool(luminance))
     if return_images:

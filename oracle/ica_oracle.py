@@ -367,7 +367,7 @@ def _check_inputs(I1, I2, TOL, need_rgb):
         raise ValueError("TOL must be positive and very small (less than 0.01)")
 
 
-def ica_quadratic(I1, I2, p, ttype, TOL, nanifoutside, delta, trace=None):
+def ica_quadratic(I1, I2, p, ttype, TOL, nanifoutside, delta, trace=None, warp_mode="skimage"):
     """inverse_compositional_algorithm.py:17-133.  ``p`` is updated in place.
     ``trace`` (list) receives ``(iteration, |dp|, p.copy(), nan)`` per iteration."""
     _check_inputs(I1, I2, TOL, need_rgb=True)
@@ -382,7 +382,7 @@ def ica_quadratic(I1, I2, p, ttype, TOL, nanifoutside, delta, trace=None):
     DI = np.zeros_like(I1)
     Iw = np.zeros_like(I1)
     while error > TOL and niter < MAX_ITER:
-        Iw = warp_bicubic(I2, p, ttype)
+        Iw = warp_for_loop(I2, p, ttype, warp_mode, nanifoutside, delta)
         DI = Iw - I1
         b = independent_vector(DIJ, DI)
         error, dp = parametric_solve(H_1, b)
@@ -393,7 +393,7 @@ def ica_quadratic(I1, I2, p, ttype, TOL, nanifoutside, delta, trace=None):
     return p, error, DI, Iw
 
 
-def ica_robust(I1, I2, p, ttype, TOL, rtype, lambda_, nanifoutside, delta, trace=None):
+def ica_robust(I1, I2, p, ttype, TOL, rtype, lambda_, nanifoutside, delta, trace=None, warp_mode="skimage"):
     """inverse_compositional_algorithm.py:135-261.  ``p`` is updated in place."""
     _check_inputs(I1, I2, TOL, need_rgb=False)
     I1 = np.asarray(I1, dtype=np.float64)
@@ -407,7 +407,7 @@ def ica_robust(I1, I2, p, ttype, TOL, rtype, lambda_, nanifoutside, delta, trace
     DI = np.zeros_like(I1)
     Iw = np.zeros_like(I1)
     while error > TOL and niter < MAX_ITER:
-        Iw = warp_bicubic(I2, p, ttype)
+        Iw = warp_for_loop(I2, p, ttype, warp_mode, nanifoutside, delta)
         DI = Iw - I1
         rho = robust_error_function(DI, lam, rtype)
         if lambda_ <= 0 and lam > LAMBDA_N:  # decays AFTER rho was evaluated (:235-238)
@@ -422,23 +422,40 @@ def ica_robust(I1, I2, p, ttype, TOL, rtype, lambda_, nanifoutside, delta, trace
     return p, error, DI, Iw
 
 
-def build_pyramid(I, nscales, nu):
-    """inverse_compositional_algorithm.py:331-337: cascade of skimage ``rescale`` levels."""
+def warp_for_loop(I2, p, ttype, warp_mode, nanifoutside, delta):
+    """The warp of the iteration loop: ``"skimage"`` = what the reference's drivers call
+    (bicubic_interpolation_skimage, inverse_compositional_algorithm.py:111, 227); ``"ipol"`` = the IPOL-style warp the
+    reference also carries (bicubic_interpolation_image, bicubic_interpolation.py:121-152: the domain is the projected
+    point, ``delta <= x' <= n - 1 - delta``, no clip) -- the option of SURVEY 8f-4 that reproduces the IPOL C++ console
+    logs of ``docs/Algortihm Report.md`` beyond iteration 0."""
+    if warp_mode == "ipol":
+        return bicubic_interpolation_image(I2, p, nparams(ttype), nanifoutside, delta)
+    if warp_mode != "skimage":
+        raise ValueError("warp_mode must be 'skimage' or 'ipol'")
+    return warp_bicubic(I2, p, ttype)
+
+
+def build_pyramid(I, nscales, nu, pyramid_mode="skimage"):
+    """inverse_compositional_algorithm.py:331-337: cascade of skimage ``rescale`` levels; ``pyramid_mode="ipol"``
+    builds the levels with ``zoom.zoom_out`` (zoom.py:29-60) instead, the IPOL-style pyramid."""
     levels = [np.asarray(I, dtype=np.float64)]
     for _ in range(1, nscales):
-        levels.append(sk.rescale(levels[-1], nu, order=3, mode="constant", cval=0, clip=True,
-                                 anti_aliasing=True))
+        if pyramid_mode == "ipol":
+            levels.append(zoom_out(levels[-1], nu))
+        else:
+            levels.append(sk.rescale(levels[-1], nu, order=3, mode="constant", cval=0, clip=True,
+                                     anti_aliasing=True))
     return levels
 
 
 def ica_pyramidal(I1, I2, p, ttype, nscales, nu, TOL, rtype, lambda_, nanifoutside, delta,
-                  trace=None):
+                  trace=None, warp_mode="skimage", pyramid_mode="skimage"):
     """inverse_compositional_algorithm.py:264-374.  ``trace`` receives
     ``(scale, iteration, |dp|, p.copy(), lambda)``."""
     _check_inputs(I1, I2, TOL, need_rgb=True)
     n = nparams(ttype)
-    I1s = build_pyramid(I1, nscales, nu)
-    I2s = build_pyramid(I2, nscales, nu)
+    I1s = build_pyramid(I1, nscales, nu, pyramid_mode)
+    I2s = build_pyramid(I2, nscales, nu, pyramid_mode)
     nx = np.zeros(nscales)
     ny = np.zeros(nscales)
     ny[0], nx[0] = I1s[0].shape[:2]
@@ -451,10 +468,10 @@ def ica_pyramidal(I1, I2, p, ttype, nscales, nu, TOL, rtype, lambda_, nanifoutsi
         sub = [] if trace is not None else None
         if rtype == QUADRATIC:
             ps[s], error, DI, Iw = ica_quadratic(I1s[s], I2s[s], ps[s], ttype, TOL, nanifoutside,
-                                                 delta, trace=sub)
+                                                 delta, trace=sub, warp_mode=warp_mode)
         else:
             ps[s], error, DI, Iw = ica_robust(I1s[s], I2s[s], ps[s], ttype, TOL, rtype, lambda_,
-                                              nanifoutside, delta, trace=sub)
+                                              nanifoutside, delta, trace=sub, warp_mode=warp_mode)
         if trace is not None:
             trace.extend((s,) + t for t in sub)
         if s > 0:

@@ -818,3 +818,42 @@ def test_device_generator_matches_numpy_mirror_and_registers(nat):
     pr = pr.cpu().numpy()
     for i in range(6):
         assert end_point_error(pr[i], p[i], t, 320, 256)[1] <= 0.05
+
+
+# ------------------------------------------------------------------ IPOL C++ console logs (second, independent goldens)
+@pytest.fixture(scope="module")
+def ipol_logs(golden_dir):
+    import json, os
+    with open(os.path.join(golden_dir, "ipol_cpp_logs.json")) as f:
+        return [r for r in json.load(f)["runs"] if r["robust"] == 0]
+
+
+@pytest.mark.parametrize("idx", range(6))
+def test_ipol_options_follow_the_cpp_logs(nat, rubber_whale, ipol_logs, idx):
+    """The IPOL-faithful options (``zoom_out`` pyramid, warp domain of ``bicubic_interpolation_image``) as
+    modes of the registration plan, against the console logs of the IPOL C++ implementation that the reference stores
+    in docs/Algortihm Report.md:38-339 (tests/golden/ipol_cpp_logs.json): six quadratic runs, one and three scales,
+    translation / euclidean / similarity -- every printed iteration, identical iteration counts.  (The reference's
+    default path agrees with these logs at iteration 0 only; the Charbonnier logs are not followed by the reference
+    either: its robust Hessian counts out-of-domain pixels)"""
+    from inverse_compositional_algorithm_b200 import _native
+    r = ipol_logs[idx]
+    tt = {2: orc.TRANSLATION, 3: orc.EUCLIDEAN, 4: orc.SIMILARITY}[r["nparams_code"]]
+    I1, I2 = rubber_whale[r["I1"]], rubber_whale[r["I2"]]
+    plan = _native.Plan(batch=1, height=388, width=584, channels=3, nscales=r["nscales"], nu=0.5, transform_type=tt,
+                        robust_type=0, robust_loop=False, lambda_=0.0, tol=1e-3, max_iter=30, delta=r["delta"],
+                        nanifoutside=True, record_trajectory=True, ipol_pyramid=True, ipol_warp=True)
+    plan.run_host(I1[None], I2[None])
+    traj = plan.trajectory()[0]
+    plan.close()
+    E = r["entries"]
+    n = orc.nparams(tt)
+    assert len(traj) == len(E), (len(traj), len(E))
+    derr = max(abs(row[2] - e["err"]) for row, e in zip(traj, E))
+    dp = max(np.abs(row[4:4 + n] - np.array(e["p"])).max() for row, e in zip(traj, E))
+    print("log line", r["line"], r["I1"], "scales", r["nscales"], "iterations", len(E), "max |d|Dp||", derr, "max |dp|", dp)
+    assert [int(row[0]) for row in traj] == [e["scale"] for e in E]
+    # the logs print 6 decimals; the three-scale runs differ from the C++ pyramid in the resampling kernel of zoom_out
+    # (B-spline in the reference's zoom.py, Keys in the C++ code): 3e-5 on the first iterations of the coarsest scale
+    tol = 2e-6 if r["nscales"] == 1 else 1.5e-4
+    assert derr <= tol and dp <= tol

@@ -178,3 +178,26 @@ def test_ipol_warp_matches_reference_golden():
         want = g[f"out_{i}"]
         assert np.array_equal(np.isnan(got), np.isnan(want))
         np.testing.assert_allclose(got, want, rtol=0, atol=1e-10, equal_nan=True)
+
+
+def test_oracle_ipol_modes_follow_the_cpp_logs(rubber_whale):
+    """Pins the oracle's IPOL options (``warp_mode="ipol"``, ``pyramid_mode="ipol"``: bicubic_interpolation_image's domain,
+    zoom.zoom_out levels) with an INDEPENDENT implementation: the IPOL C++ console logs the reference stores in
+    docs/Algortihm Report.md:38-339 (transcribed by oracle/make_golden_ipol_logs.py).  Single scale: every printed digit;
+    three scales: same iteration counts, 3e-5 (the C++ zoom interpolates with Keys, zoom.py with a B-spline)."""
+    import json, os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ipol_cpp_logs.json")) as f:
+        runs = [r for r in json.load(f)["runs"] if r["robust"] == 0]
+    assert len(runs) == 6
+    for r in runs[:3]:          # (the other three take a minute of CPU; the GPU suite runs all six)
+        tt = {2: orc.TRANSLATION, 3: orc.EUCLIDEAN, 4: orc.SIMILARITY}[r["nparams_code"]]
+        I1 = rubber_whale[r["I1"]].astype(np.float64)
+        I2 = rubber_whale[r["I2"]].astype(np.float64)
+        trace = []
+        orc.ica_pyramidal(I1, I2, np.zeros(orc.nparams(tt)), tt, r["nscales"], 0.5, 1e-3, orc.QUADRATIC, 0.0, True, r["delta"],
+                          trace=trace, warp_mode="ipol", pyramid_mode="ipol")
+        E = r["entries"]
+        assert len(trace) == len(E)
+        tol = 1e-6 if r["nscales"] == 1 else 1e-4
+        for t, e in zip(trace, E):
+            assert t[0] == e["scale"] and abs(t[2] - e["err"]) <= tol and np.abs(np.array(t[3]) - np.array(e["p"])).max() <= tol
