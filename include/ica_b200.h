@@ -55,6 +55,9 @@ typedef enum {
 /* ica_plan_run_host dtype modifier: the host images are RGB [B][H][W][3] and the (one-channel) plan registers their
    luminance Y = 0.2125 R + 0.7154 G + 0.0721 B (skimage.color.rgb2gray weights), converted on the device */
 #define ICA_DTYPE_RGB_TO_LUMA 0x10
+/* ica_plan_run_host dtype modifier: DI_out / Iw_out are float64 arrays (what the reference returns); the widening from the
+   device's float32 happens on the device, before the device->host copy */
+#define ICA_DTYPE_OUT_F64 0x20
 /* IPOL-faithful options the reference carries but does not use on its default path; with both set the
    quadratic runs reproduce the IPOL C++ console logs stored in the reference's docs/Algortihm Report.md:38-339 */
 #define ICA_FLAG_IPOL_PYRAMID 16u     /* levels by zoom.zoom_out (src/zoom.py:29-60) instead of skimage rescale */

@@ -26,6 +26,7 @@ FLAG_IPOL_WARP = 32      # warp domain of bicubic_interpolation_image instead of
 
 DTYPE_F32, DTYPE_U8, DTYPE_F64 = 0, 1, 2
 DTYPE_RGB_TO_LUMA = 0x10     # modifier: RGB host images, one-channel plan registers their luminance
+DTYPE_OUT_F64 = 0x20         # modifier: DI / Iw come back as float64 (widened on the device)
 
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_ALLOC = -1, -2, -3, -4
 
@@ -538,7 +539,7 @@ class Plan:
         check(lib().ica_plan_get_results(self._h, _ptr(p), _ptr(err), _ptr(iters)))
         return p, err, iters
 
-    def run_host(self, I1: np.ndarray, I2: np.ndarray, p0=None, want_images=False, rgb_to_luma=False):
+    def run_host(self, I1: np.ndarray, I2: np.ndarray, p0=None, want_images=False, rgb_to_luma=False, images_f64=False):
         """``I1``/``I2``: arrays [B][H][W][C] of dtype float32, uint8 or float64 (C-contiguous).  With ``rgb_to_luma`` the
         inputs are RGB ``[B][H][W][3]`` and the (one-channel) plan registers their luminance, computed on the device."""
         shape = (self.batch, self.height, self.width, self.channels)
@@ -566,9 +567,11 @@ class Plan:
         DI = Iw = None
         di_ptr = iw_ptr = None
         if want_images:
-            DI = np.empty(shape, dtype=np.float32)
-            Iw = np.empty(shape, dtype=np.float32)
+            DI = np.empty(shape, dtype=np.float64 if images_f64 else np.float32)
+            Iw = np.empty(shape, dtype=np.float64 if images_f64 else np.float32)
             di_ptr, iw_ptr = _ptr(DI), _ptr(Iw)
+            if images_f64:
+                code |= DTYPE_OUT_F64
         check(lib().ica_plan_run_host(self._h, _ptr(I1), _ptr(I2), code | (DTYPE_RGB_TO_LUMA if rgb_to_luma else 0),
                                       _ptr(p), _ptr(err), _ptr(iters), di_ptr, iw_ptr))
         return p, err, iters, DI, Iw

@@ -8,6 +8,7 @@
 #include <map>
 #include <mutex>
 #include <thread>
+#include <chrono>
 #include <vector>
 #include <cuda.h>
 #include "ica_common.cuh"
@@ -99,6 +100,7 @@ struct ica_plan {
   void* raw_dev = nullptr;
   size_t raw_bytes = 0;
   float *DI_dev = nullptr, *Iw_dev = nullptr;
+  double* out64_dev = nullptr;       // float64 staging of DI and Iw (host entry with ICA_DTYPE_OUT_F64), 2 x nimg doubles
   const float *last_I1 = nullptr, *last_I2 = nullptr;
   // K2 stages its tiles with tiled TMA copies: one tensor map per (pair, level, image)
   void* tmaps_dev = nullptr;                 // CUtensorMap [B][nscales][2], 128 bytes each
@@ -455,7 +457,7 @@ int ica_plan_destroy(ica_plan* pl) {
   if (pl->graph) cudaGraphDestroy(pl->graph); cudaFree(pl->dbg_time); cudaFree(pl->traj); cudaFree(pl->n_active);
   if (pl->h_n_active) cudaFreeHost(pl->h_n_active);
   cudaFree(pl->ttypes_dev); cudaFree(pl->p_dev); cudaFree(pl->err_dev); cudaFree(pl->iters_dev);
-  cudaFree(pl->in1_dev); cudaFree(pl->in2_dev); cudaFree(pl->raw_dev); cudaFree(pl->DI_dev); cudaFree(pl->Iw_dev);
+  cudaFree(pl->in1_dev); cudaFree(pl->in2_dev); cudaFree(pl->raw_dev); cudaFree(pl->DI_dev); cudaFree(pl->Iw_dev); cudaFree(pl->out64_dev);
   for (auto e : pl->ev_iter) cudaEventDestroy(e);
   for (auto e : pl->ev_pyr) cudaEventDestroy(e);
   if (pl->ev_host0) cudaEventDestroy(pl->ev_host0);
@@ -915,11 +917,16 @@ static std::mutex g_h2d_mutex[64];   // one per device: copies to different GPUs
 // cudaEventSynchronize would, while many concurrent callers (several plans per GPU, several ranks per host) give their
 // core away instead of spinning on it (blocking-sync events were measured to add ~0.4 ms to a single call).
 static int wait_event_polite(cudaEvent_t ev) {
+  // the first ~30 us are polled with yields (a lone short call sees its event at once); after that the thread sleeps
+  // 50 us between polls: with many plans in flight (8 per rank x 8 ranks on one host in the 8-GPU bench) the waiting
+  // threads leave the cores to the ones that are enqueueing work instead of storming the scheduler with yields
+  const auto t0 = std::chrono::steady_clock::now();
   for (;;) {
     const cudaError_t e = cudaEventQuery(ev);
     if (e == cudaSuccess) return ICA_OK;
     if (e != cudaErrorNotReady) { set_error("cudaEventQuery failed: %s", cudaGetErrorString(e)); return ICA_ERR_CUDA; }
-    std::this_thread::yield();
+    if (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(30)) std::this_thread::yield();
+    else std::this_thread::sleep_for(std::chrono::microseconds(50));
   }
 }
 
@@ -968,6 +975,8 @@ static int upload_pair(ica_plan* pl, const void* h1, const void* h2, int dtype_i
 int ica_plan_run_host(ica_plan* pl, const void* I1_host, const void* I2_host, int32_t dtype, double* p_inout_host,
                       double* err_out, int32_t* iters_out, float* DI_out, float* Iw_out) {
   if (!pl || !I1_host || !I2_host || !p_inout_host) { set_error("NULL argument"); return ICA_ERR_INVALID; }
+  const bool out64 = (dtype & ICA_DTYPE_OUT_F64) != 0;     // DI_out / Iw_out are float64 arrays (widened on the device)
+  dtype &= ~ICA_DTYPE_OUT_F64;
   if ((dtype & ~(0xf | ICA_DTYPE_RGB_TO_LUMA)) || (dtype & 0xf) > 2) { set_error("dtype must be 0 (f32), 1 (u8) or 2 (f64), optionally | ICA_DTYPE_RGB_TO_LUMA"); return ICA_ERR_INVALID; }
   if ((dtype & ICA_DTYPE_RGB_TO_LUMA) && pl->C != 1) { set_error("ICA_DTYPE_RGB_TO_LUMA needs a one-channel plan (the host images are RGB)"); return ICA_ERR_INVALID; }
   if ((DI_out || Iw_out) && !(pl->cfg.flags & ICA_FLAG_WRITE_DI_IW)) {
@@ -997,8 +1006,20 @@ int ica_plan_run_host(ica_plan* pl, const void* I1_host, const void* I2_host, in
   if (err_out) ICA_CUDA_CHECK(cudaMemcpyAsync(err_out, pl->err_dev, pl->B * sizeof(double), cudaMemcpyDeviceToHost, stream));
   if (iters_out) ICA_CUDA_CHECK(cudaMemcpyAsync(iters_out, pl->iters_dev, (size_t)pl->B * pl->nscales * sizeof(int),
                                                 cudaMemcpyDeviceToHost, stream));
-  if (DI_out) ICA_CUDA_CHECK(cudaMemcpyAsync(DI_out, pl->DI_dev, nimg * sizeof(float), cudaMemcpyDeviceToHost, stream));
-  if (Iw_out) ICA_CUDA_CHECK(cudaMemcpyAsync(Iw_out, pl->Iw_dev, nimg * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  if (out64 && (DI_out || Iw_out)) {
+    if (!pl->out64_dev) { if (int rc = dev_alloc(pl, &pl->out64_dev, 2 * nimg)) return rc; }
+    if (DI_out) {
+      ICA_LAUNCH_CHECK(launch_widen_f64(pl->DI_dev, pl->out64_dev, (long long)nimg, stream));
+      ICA_CUDA_CHECK(cudaMemcpyAsync(DI_out, pl->out64_dev, nimg * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    }
+    if (Iw_out) {
+      ICA_LAUNCH_CHECK(launch_widen_f64(pl->Iw_dev, pl->out64_dev + nimg, (long long)nimg, stream));
+      ICA_CUDA_CHECK(cudaMemcpyAsync(Iw_out, pl->out64_dev + nimg, nimg * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    }
+  } else {
+    if (DI_out) ICA_CUDA_CHECK(cudaMemcpyAsync(DI_out, pl->DI_dev, nimg * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    if (Iw_out) ICA_CUDA_CHECK(cudaMemcpyAsync(Iw_out, pl->Iw_dev, nimg * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  }
   ICA_CUDA_CHECK(cudaEventRecord(pl->ev_host1, stream));
   if (int rc = wait_event_polite(pl->ev_host1)) return rc;
   return ICA_OK;

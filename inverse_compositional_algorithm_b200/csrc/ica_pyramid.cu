@@ -783,6 +783,16 @@ __global__ void __launch_bounds__(256) convert_luma_minmax_kernel(const T* __res
 
 }  // namespace
 
+__global__ void widen_f32_f64_kernel(const float* __restrict__ in, double* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = (double)in[i];
+}
+// float32 -> float64 on the device (the reference returns DI / Iw as float64 arrays: the widening happens before the
+// device->host copy instead of in a host pass over the result)
+cudaError_t launch_widen_f64(const float* in, double* out, long long n, cudaStream_t stream) {
+  widen_f32_f64_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, stream>>>(in, out, n);
+  return cudaGetLastError();
+}
+
 // dtype: 0 = float32, 1 = uint8, 2 = float64 RGB input; out: float32 luminance, npix pixels per image
 cudaError_t launch_convert_luma(const void* in, int dtype, float* out, long long npix, int nimg, MinMaxKeys* mm, int mm_stride,
                                 cudaStream_t stream) {

@@ -44,6 +44,7 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
                             const MinMaxKeys* mm_parent, MinMaxKeys* mm_child, int mm_stride, cudaStream_t stream,
                             int* launches = nullptr);
 // uint8 / float64 -> float32 for nimg images of `count` elements, fused with each image's min/max keys
+cudaError_t launch_widen_f64(const float* in, double* out, long long n, cudaStream_t stream);
 // RGB host images of dtype (0 f32, 1 u8, 2 f64) -> one-channel float32 luminance + its min/max
 cudaError_t launch_convert_luma(const void* in, int dtype, float* out, long long npix, int nimg, MinMaxKeys* mm, int mm_stride,
                                 cudaStream_t stream);

@@ -105,10 +105,11 @@ def _run_single(I1, I2, p, transform_type, nscales, nu, TOL, robust_type, robust
                          ipol_warp=bool(ipol_warp))
         p0 = np.zeros(_native.MAX_PARAMS)
         p0[:n] = np.asarray(p, dtype=np.float64)[:n]
-        pout, err, iters, DI, Iw = plan.run_host(_as_batch(I1), _as_batch(I2), p0[None], want_images=True)
+        # DI / Iw come back as float64 like the reference's: widened on the device, copied straight into the result arrays
+        pout, err, iters, DI, Iw = plan.run_host(_as_batch(I1), _as_batch(I2), p0[None], want_images=True, images_f64=True)
         if verbose:
             _print_trace(plan.trajectory()[0], n, quadratic=not robust_loop, with_scale=nscales > 1)
-    return pout[0, :n].copy(), float(err[0]), DI[0].astype(np.float64), Iw[0].astype(np.float64)
+    return pout[0, :n].copy(), float(err[0]), DI[0], Iw[0]
 
 
 def inverse_compositional_algorithm(I1, I2, p, transform_type, TOL, nanifoutside, delta, verbose, *, ipol_warp=False):
