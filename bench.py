@@ -39,6 +39,7 @@ WORKLOADS = {
                H=480, W=640, C=1, transform="MIX", robust="QUADRATIC", nscales=5, occlusion=0.0),
 }
 NU, TOL, DELTA, LAMBDA = 0.5, 1e-3, 10, 0.0
+DATA_SEED = 20260              # the one synthetic data set of all arms: pair k = pair k of set DATA_SEED (synthetic.py)
 METRIC = "registrations/sec (1024^2 homography, 5-scale robust)"
 UNIT = "pairs/s"
 
@@ -105,14 +106,16 @@ def algorithmic_bytes(iters, nx, ny, C):
 def _oracle_one(args):
     """Worker: one registration with the CPU oracle port (numpy/scipy restatement of the reference)."""
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    seed, wl = args
+    pair, wl = args[:2]
     from oracle import ica_oracle as orc
     from inverse_compositional_algorithm_b200 import synthetic
     from inverse_compositional_algorithm_b200.transformation import TransformType
     from inverse_compositional_algorithm_b200.image_optimisation import RobustErrorFunctionType
-    t = TransformType[wl["transform"]] if wl["transform"] != "MIX" else TransformType.SIMILARITY
-    I1, I2, _ = synthetic.make_pair(seed, wl["H"], wl["W"], wl["C"], t, occlusion=wl["occlusion"])
-    I1, I2 = np.round(I1), np.round(I2)      # 8-bit image values, like the GPU legs
+    t = pair_type(wl, pair)
+    if len(args) > 2:          # images handed over by the caller (the GPU arm's own pair, for the parity re-check)
+        I1, I2 = args[2], args[3]
+    else:                      # pair `pair` of the data set every arm uses, regenerated on the CPU (numpy mirror of the
+        I1, I2, _ = synthetic.make_pair_hash(DATA_SEED, pair, wl["H"], wl["W"], wl["C"], t, occlusion=wl["occlusion"])   # device generator)
     if wl["C"] == 1:
         I1, I2 = np.repeat(I1, 3, 2), np.repeat(I2, 3, 2)
     t0 = time.perf_counter()
@@ -120,6 +123,14 @@ def _oracle_one(args):
     p, _, _, _ = orc.ica_pyramidal(I1, I2, np.zeros(t.nparams()), t.value, wl["nscales"], NU, TOL,
                                    RobustErrorFunctionType[wl["robust"]].value, LAMBDA, True, DELTA, trace=trace)
     return time.perf_counter() - t0, len(trace), p
+
+
+def pair_type(wl, pair):
+    """Transform type of pair `pair` of the data set (config 3 alternates similarity / affinity)."""
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    if wl["transform"] == "MIX":
+        return TransformType.SIMILARITY if pair % 2 == 0 else TransformType.AFFINITY
+    return TransformType[wl["transform"]]
 
 
 def run_reference(args, wl):
@@ -144,20 +155,22 @@ def run_reference(args, wl):
         for _ in range(max(1, min(args.warmup, 2))):       # warm the pool / imports on a tiny sample
             pool.map(_oracle_one, [(i, small) for i in range(workers)])
         t0 = time.perf_counter()
-        first = pool.map(_oracle_one, [(1000 + i, wl) for i in range(workers)])
+        first = pool.map(_oracle_one, [(i, wl) for i in range(workers)])          # pairs 0.. of the GPU arm's rank-0 batch
         t_step = time.perf_counter() - t0
         steps = max(1, min(args.steps, int(budget_s // max(t_step, 1e-3))))
         total = t_step
         for s in range(1, steps):
             t0 = time.perf_counter()
-            pool.map(_oracle_one, [(1000 + s * workers + i, wl) for i in range(workers)])
+            pool.map(_oracle_one, [(s * workers + i, wl) for i in range(workers)])
             total += time.perf_counter() - t0
     value = steps * workers / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["name"], "pairs_per_step": workers, "nu": NU, "TOL": TOL, "delta": DELTA},
+        "config": {"workload": wl["name"], "pairs_per_step": workers, "nu": NU, "TOL": TOL, "delta": DELTA,
+                   "data_set": f"synthetic set {DATA_SEED}, pairs 0..{steps * workers - 1}: the first pairs of the GPU arm's batch, "
+                               "regenerated on the CPU by the numpy mirror of the device generator"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
                          "sample": f"{workers} registrations per step, one per process "
                                    f"(single-pair latency {np.mean([r[0] for r in first]):.1f} s)"},
@@ -184,18 +197,26 @@ def run_ours(args, wl):
     torch.cuda.set_device(local)
     _native.set_device(local)
     dev = torch.device("cuda", local)
+    # one node, several ranks: give every rank its own slice of the host cores (its e2e leg runs several host threads;
+    # without this the ranks' threads migrate over all cores and fight for them)
+    affinity = None
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // world)
+        mine = cores[local * per:(local + 1) * per] or cores
+        try:
+            os.sched_setaffinity(0, mine)
+            affinity = len(mine)
+        except OSError:
+            pass
 
     B, H, W, C, ns = args.batch, wl["H"], wl["W"], wl["C"], wl["nscales"]
-    if wl["transform"] == "MIX":
-        types = [TransformType.SIMILARITY if i % 2 == 0 else TransformType.AFFINITY for i in range(B)]
-    else:
-        types = [TransformType[wl["transform"]]] * B
+    types = [pair_type(wl, rank * B + i) for i in range(B)]
     robust = RobustErrorFunctionType[wl["robust"]]
-    I1, I2, p_gt = synthetic.make_batch_torch(B, H, W, C, types, seed=1000 * rank + 1, device=dev,
-                                              occlusion=wl["occlusion"])
-    if args.input_dtype == "u8":   # 8-bit images (what the reference's notebooks read from disk); same values on both legs
-        I1 = I1.round_().clamp_(0, 255)
-        I2 = I2.round_().clamp_(0, 255)
+    # rank r registers pairs [r*B, (r+1)*B) of the data set, generated in place by the library's generator kernels
+    # (8-bit values, what the reference's notebooks read from disk, stored as float32)
+    I1, I2, p_gt = synthetic.make_batch_device(B, H, W, C, types, seed=DATA_SEED, pair_offset=rank * B, device=dev,
+                                               occlusion=wl["occlusion"], quantize=True)
     plan = _native.Plan(batch=B, height=H, width=W, channels=C, nscales=ns, nu=NU, transform_type=types[0].value,
                         robust_type=robust.value, robust_loop=robust != RobustErrorFunctionType.QUADRATIC,
                         lambda_=LAMBDA, tol=TOL, max_iter=30, delta=DELTA, nanifoutside=True, gray_as_rgb=(C == 1), blocks_per_pair=args.chunks)
@@ -294,7 +315,7 @@ def run_ours(args, wl):
     import threading
     host_dtype = torch.uint8 if args.input_dtype == "u8" else torch.float32
     code = _native.DTYPE_U8 if args.input_dtype == "u8" else _native.DTYPE_F32
-    nhalf = max(1, min(args.e2e_plans, B))
+    nhalf = max(1, min(args.e2e_plans if world == 1 else min(args.e2e_plans, 4), B))
     bounds = [(i * B // nhalf, (i + 1) * B // nhalf) for i in range(nhalf)]
     halves = []
     for lo_, hi_ in bounds:
@@ -346,6 +367,61 @@ def run_ours(args, wl):
     for hv in halves:
         hv["plan"].close()
 
+    # ---- the reference's full return tuple (p, error, DI, Iw: ica.py:261, 374) end to end: as above plus the two
+    # residual / warped images per pair copied device->host (float32, pinned).  A smaller batch (the pinned result
+    # buffers take 2 x 12.6 MB per pair); same plans-on-threads scheme.
+    full_value, full_pairs, full_d2h = None, 0, 0
+    if not args.no_e2e and not args.no_full_tuple:
+        nbf = max(1, min(B, args.full_tuple_pairs))
+        nplans = max(1, min(4, nbf))
+        fb = [(i * nbf // nplans, (i + 1) * nbf // nplans) for i in range(nplans)]
+        fulls = []
+        for lo_, hi_ in fb:
+            nb = hi_ - lo_
+            fp = _native.Plan(batch=nb, height=H, width=W, channels=C, nscales=ns, nu=NU, transform_type=types[0].value,
+                              robust_type=robust.value, robust_loop=robust != RobustErrorFunctionType.QUADRATIC,
+                              lambda_=LAMBDA, tol=TOL, max_iter=30, delta=DELTA, nanifoutside=True, gray_as_rgb=(C == 1),
+                              blocks_per_pair=args.chunks, write_di_iw=True)
+            fp.set_transform_types([t.value for t in types[lo_:hi_]])
+            h1 = torch.empty((nb, H, W, C), dtype=host_dtype).pin_memory()
+            h2 = torch.empty((nb, H, W, C), dtype=host_dtype).pin_memory()
+            h1.copy_(I1[lo_:hi_].to(host_dtype)); h2.copy_(I2[lo_:hi_].to(host_dtype))
+            fulls.append(dict(plan=fp, h1=h1, h2=h2, p=np.zeros((nb, 8)), err=np.zeros(nb), it=np.zeros((nb, ns), dtype=np.int32),
+                              di=torch.empty((nb, H, W, C), dtype=torch.float32).pin_memory(),
+                              iw=torch.empty((nb, H, W, C), dtype=torch.float32).pin_memory()))
+        torch.cuda.synchronize()
+
+        def full_worker(hv, nsteps):
+            _native.set_device(local)
+            for _ in range(nsteps):
+                hv["p"][:] = 0
+                hv["plan"].run_host_ptrs(hv["h1"].data_ptr(), hv["h2"].data_ptr(), code, hv["p"], hv["err"], hv["it"],
+                                         hv["di"].data_ptr(), hv["iw"].data_ptr())
+
+        def full_run(nsteps):
+            ths = [threading.Thread(target=full_worker, args=(hv, nsteps)) for hv in fulls]
+            for t_ in ths:
+                t_.start()
+            for t_ in ths:
+                t_.join()
+
+        full_run(1)
+        barrier()
+        t0 = time.perf_counter()
+        full_run(e2e_steps)
+        torch.cuda.synchronize()
+        full_ms = (time.perf_counter() - t0) * 1e3
+        assert np.allclose(np.concatenate([hv["p"] for hv in fulls]), p_res[:nbf], rtol=0, atol=1e-9)
+        if world > 1:
+            t = torch.tensor([full_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            full_ms = float(t.item())
+        full_value = world * nbf * e2e_steps / (full_ms * 1e-3)
+        full_pairs, full_d2h = nbf, 2 * nbf * H * W * C * 4 + nbf * (8 * 8 + 8 + ns * 4)
+        for hv in fulls:
+            hv["plan"].close()
+        del fulls
+
     # ---- accuracy vs ground truth (informative) on this rank's batch
     epe = [end_point_error(p_res[i, :types[i].nparams()], p_gt[i, :types[i].nparams()], types[i], W, H)[1]
            for i in range(min(B, 8))]
@@ -377,10 +453,14 @@ def run_ours(args, wl):
         "pixel_iterations_per_s": world * pi * 1.0 / (elapsed_ms / args.steps * 1e-3),
         "epe_vs_ground_truth_px_max": float(np.max(epe)),
         "gpu_launches": int(launches),
+        "host_cores_per_rank": affinity,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "entry": f"ica_plan_run_host, pinned {args.input_dtype} host buffers, {nhalf} sub-batch plans "
                 f"on {nhalf} host threads (copies take turns on the link and overlap the other plans' kernels), wall clock between device syncs"},
+        "e2e_full_tuple": {"value": full_value, "unit": UNIT, "pairs_per_step_per_gpu": full_pairs,
+                           "d2h_bytes_per_step": full_d2h,
+                           "what": "as e2e, plus the reference's DI and Iw (float32, pinned) copied device->host for every pair"},
         "roofline": {"bound": "hbm", "kernel": "ica_iterate_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "frac_of_nominal_8000_GBs": (achieved / 8000.0) if achieved else None, "traffic": traffic,
@@ -392,19 +472,16 @@ def run_ours(args, wl):
                      "kernel_ms_per_step_cuda_events_host_loop": tm_events["iterate_ms"]},
     }
     if world == 1 and not args.no_cpu_baseline:
-        t_cpu, n_it, p_cpu = _oracle_one((1, wl))
-        # the same pair through the CUDA path: parity at the workload's full size
-        from inverse_compositional_algorithm_b200.inverse_compositional_algorithm import register_batch
+        # pair 0 of this run's batch through the CPU oracle, on the very images the GPU registered (copied back):
+        # the timed CPU baseline and, with it, parity at the workload's full size
         tt = types[0]
-        a1, a2, _ = synthetic.make_pair(1, H, W, C, tt, occlusion=wl["occlusion"])
-        pg, _, itg = register_batch(np.round(a1)[None], np.round(a2)[None], tt, nscales=ns, nu=NU, TOL=TOL,
-                                    robust_type=robust, lambda_=LAMBDA, nanifoutside=True, delta=DELTA)
-        epe_o = end_point_error(pg[0, :tt.nparams()], p_cpu, tt, W, H)
+        t_cpu, n_it, p_cpu = _oracle_one((0, wl, I1[0].cpu().numpy(), I2[0].cpu().numpy()))
+        epe_o = end_point_error(p_res[0, :tt.nparams()], p_cpu, tt, W, H)
         line["cpu_baseline"] = {"value": 1.0 / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": f"1 registration of the workload ({n_it} iterations, {t_cpu:.1f} s), "
+                                "sample": f"1 registration of the workload (pair 0 of the batch, {n_it} iterations, {t_cpu:.1f} s), "
                                           "numpy/scipy oracle port, single process",
                                 "gpu_vs_oracle_epe_px_mean_max": [epe_o[0], epe_o[1]],
-                                "gpu_iterations_same_pair": int(itg.sum())}
+                                "gpu_iterations_same_pair": int(iters[0].sum())}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -425,6 +502,8 @@ def main():
     ap.add_argument("--e2e-plans", type=int, default=8, help="sub-batch plans (one host thread each) on the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
+    ap.add_argument("--no-full-tuple", action="store_true", help="skip the e2e leg that also returns DI and Iw")
+    ap.add_argument("--full-tuple-pairs", type=int, default=64, help="pairs per step per GPU of the e2e_full_tuple leg")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -577,10 +577,10 @@ class Plan:
         return p, err, iters, DI, Iw
 
     def run_host_ptrs(self, I1_ptr: int, I2_ptr: int, dtype_code: int, p: np.ndarray,
-                      err: np.ndarray, iters: np.ndarray):
-        """Raw host pointers (e.g. pinned torch tensors) -- used by bench.py's e2e leg."""
+                      err: np.ndarray, iters: np.ndarray, DI_ptr: int = 0, Iw_ptr: int = 0):
+        """Raw host pointers (e.g. pinned torch tensors) -- used by bench.py's e2e legs."""
         check(lib().ica_plan_run_host(self._h, _P(I1_ptr), _P(I2_ptr), int(dtype_code), _ptr(p),
-                                      _ptr(err), _ptr(iters), None, None))
+                                      _ptr(err), _ptr(iters), _P(DI_ptr) if DI_ptr else None, _P(Iw_ptr) if Iw_ptr else None))
 
     def last_host_run_ms(self) -> float:
         ms = C.c_float()

@@ -1,8 +1,10 @@
 """Synthetic image pairs with known ground-truth motion.
 
-Host-side (numpy/scipy) generator shared by the tests and by ``bench.py``: a smooth random
-texture, its centre crop as I2, and I1(x) = texture(x'(x; p_gt)) + noise, optionally with a
-square occlusion.  This is input synthesis, not part of the registration path; the reference's
+Two generators of the same kind of pair -- a smooth random texture, its centre crop as I2, and
+I1(x) = texture(x'(x; p_gt)) + noise, optionally with a square occlusion:
+* :func:`make_pair` (numpy/scipy, cubic-spline resampling): the seeded inputs of the parity tests and golden files;
+* :func:`make_batch_device` -- the library's own CUDA generator (``csrc/ica_generate.cu``, counter-based randomness) for
+  benchmark-sized batches, with :func:`make_pair_hash`, its numpy mirror, for the CPU legs.  This is input synthesis, not part of the registration path; the reference's
 counterpart is ``transformation.transform_image`` (``src/transformation.py:266-318``), which
 the notebooks use to fabricate test pairs.
 """
@@ -72,78 +74,6 @@ def make_pair(seed: int, height: int, width: int, channels: int,
         i1[y0:y0 + side, x0:x0 + side] = rng.uniform(0.0, 255.0, size=(side, side, channels))
     np.clip(i1, 0.0, 255.0, out=i1)
     return i1.astype(np.float32), i2, p_gt
-
-
-def make_batch_torch(batch: int, height: int, width: int, channels: int, transform_types, *,
-                     seed: int = 0, device="cuda", max_shift: float = 8.0, max_lin: float = 0.02,
-                     noise_sigma: float = 1.0, occlusion: float = 0.0, margin: int = 64,
-                     chunk: int = 8):
-    """Device-side variant of :func:`make_pair` for benchmark-sized batches (torch is plumbing
-    here: noise, a separable Gaussian blur and ``grid_sample``).  Returns channels-last float32
-    CUDA tensors ``I1, I2`` of shape ``[B, H, W, C]`` and the ground truth ``p_gt [B, 8]``."""
-    import torch
-    import torch.nn.functional as F
-
-    if not isinstance(transform_types, (list, tuple)):
-        transform_types = [transform_types] * batch
-    rng = np.random.default_rng(SEED0 + int(seed))
-    gen = torch.Generator(device=device)
-    gen.manual_seed(SEED0 + int(seed))
-    Ht, Wt = height + 2 * margin, width + 2 * margin
-    sigma, rad = 2.0, 8
-    k = torch.exp(-0.5 * (torch.arange(-rad, rad + 1, device=device, dtype=torch.float32) / sigma) ** 2)
-    k = k / k.sum()
-    I1 = torch.empty((batch, height, width, channels), device=device, dtype=torch.float32)
-    I2 = torch.empty_like(I1)
-    p_all = np.zeros((batch, 8))
-    yy, xx = torch.meshgrid(torch.arange(height, device=device, dtype=torch.float64),
-                            torch.arange(width, device=device, dtype=torch.float64), indexing="ij")
-    for b0 in range(0, batch, chunk):
-        nb = min(chunk, batch - b0)
-        tex = torch.randn((nb * channels, 1, Ht, Wt), device=device, generator=gen)
-        tex = F.conv2d(F.pad(tex, (rad, rad, 0, 0), mode="circular"), k.view(1, 1, 1, -1))
-        tex = F.conv2d(F.pad(tex, (0, 0, rad, rad), mode="circular"), k.view(1, 1, -1, 1))
-        tex = tex.view(nb, channels, Ht, Wt)
-        lo = tex.amin(dim=(1, 2, 3), keepdim=True)
-        hi = tex.amax(dim=(1, 2, 3), keepdim=True)
-        tex = (tex - lo) * (255.0 / (hi - lo))
-        grids = []
-        for i in range(nb):
-            t = TransformType(transform_types[b0 + i])
-            p = random_motion(rng, t, height, width, max_shift, max_lin)
-            p_all[b0 + i, :len(p)] = p
-            pt = [float(v) for v in p]
-            if t == TransformType.TRANSLATION:
-                xp, yp = xx + pt[0], yy + pt[1]
-            elif t == TransformType.EUCLIDEAN:
-                c, s = np.cos(pt[2]), np.sin(pt[2])
-                xp, yp = c * xx - s * yy + pt[0], s * xx + c * yy + pt[1]
-            elif t == TransformType.SIMILARITY:
-                xp, yp = (1 + pt[2]) * xx - pt[3] * yy + pt[0], pt[3] * xx + (1 + pt[2]) * yy + pt[1]
-            elif t == TransformType.AFFINITY:
-                xp, yp = (1 + pt[2]) * xx + pt[3] * yy + pt[0], pt[4] * xx + (1 + pt[5]) * yy + pt[1]
-            else:
-                d = pt[6] * xx + pt[7] * yy + 1
-                xp = ((1 + pt[0]) * xx + pt[1] * yy + pt[2]) / d
-                yp = (pt[3] * xx + (1 + pt[4]) * yy + pt[5]) / d
-            gx = 2.0 * (xp + margin) / (Wt - 1) - 1.0
-            gy = 2.0 * (yp + margin) / (Ht - 1) - 1.0
-            grids.append(torch.stack([gx, gy], dim=-1).to(torch.float32))
-        grid = torch.stack(grids)
-        w1 = F.grid_sample(tex, grid, mode="bicubic", padding_mode="border", align_corners=True)
-        if noise_sigma > 0:
-            w1 = w1 + noise_sigma * torch.randn(w1.shape, device=device, generator=gen)
-        if occlusion > 0:
-            side = min(int(round(np.sqrt(occlusion * height * width))), height, width)
-            for i in range(nb):
-                y0 = int(rng.integers(0, height - side + 1))
-                x0 = int(rng.integers(0, width - side + 1))
-                w1[i, :, y0:y0 + side, x0:x0 + side] = 255.0 * torch.rand(
-                    (channels, side, side), device=device, generator=gen)
-        w1 = w1.clamp_(0.0, 255.0)
-        I1[b0:b0 + nb] = w1.permute(0, 2, 3, 1)
-        I2[b0:b0 + nb] = tex[:, :, margin:margin + height, margin:margin + width].permute(0, 2, 3, 1)
-    return I1.contiguous(), I2.contiguous(), p_all
 
 
 def make_large_gray_pair(seed: int, height: int, width: int, shift=(3, -2), noise_sigma: float = 1.0):

@@ -6,7 +6,7 @@ from inverse_compositional_algorithm_b200.inverse_compositional_algorithm import
 from inverse_compositional_algorithm_b200.transformation import TransformType, end_point_error
 t = TransformType.HOMOGRAPHY
 for n, c in ((8192, 3), (4096, 3), (6000, 1)):
-    I1, I2, p_gt = synthetic.make_batch_torch(1, n, n, c, t, seed=3, device="cuda", max_lin=0.002, chunk=1)
+    I1, I2, p_gt = synthetic.make_batch_device(1, n, n, c, t, seed=3, device="cuda", max_lin=0.002)
     for rep in range(2):
         torch.cuda.synchronize(); t0 = time.perf_counter()
         p, err, iters = register_batch_device(I1, I2, t, nscales=6, robust_type=3, delta=10)

@@ -8,7 +8,7 @@ from inverse_compositional_algorithm_b200.transformation import TransformType
 t = TransformType.HOMOGRAPHY
 NB = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 NP = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-I1, I2, _ = synthetic.make_batch_torch(NB, 1024, 1024, 3, [t] * NB, seed=1, device="cuda")
+I1, I2, _ = synthetic.make_batch_device(NB, 1024, 1024, 3, [t] * NB, seed=1, device="cuda")
 h1 = I1.round().clamp(0, 255).to(torch.uint8).cpu().pin_memory()
 h2 = I2.round().clamp(0, 255).to(torch.uint8).cpu().pin_memory()
 d = torch.empty_like(h1, device="cuda")
