@@ -46,7 +46,10 @@ constexpr bool kTimeline = true;
 constexpr bool kTimeline = false;
 #endif
 constexpr int kBlocksPerSM = 2;      // 2 CTAs x 12 warps per SM at 80 registers per thread (16 warps at 64 registers measured 9 % slower)
-constexpr int kConsumerWarps = 11;   // + 1 producer warp = 12 warps: warps are allocated in groups of 4
+#ifndef ICA_CONSUMER_WARPS
+#define ICA_CONSUMER_WARPS 11
+#endif
+constexpr int kConsumerWarps = ICA_CONSUMER_WARPS;   // + 1 producer warp = 12 warps: warps are allocated in groups of 4
 constexpr int kRowsPerWarp = 1;      // rows of a tile per consumer warp
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = kConsumerThreads + 32;   // + one producer warp
