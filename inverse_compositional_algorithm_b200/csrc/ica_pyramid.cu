@@ -872,7 +872,10 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
                             int channels, const DeviceResample& ry, const DeviceResample& rx, float* tmp,
                             long long tmp_stride, float* out0a, float* out0b, long long out_stride, int out_pitch, int nset,
                             const MinMaxKeys* mm_parent, MinMaxKeys* mm_child, int mm_stride, cudaStream_t stream,
-                            int* launches) {
+                            int* launches, cudaStream_t border_stream) {
+  // everything but the fused interior kernel (border rows / columns: ~5 % of the outputs in small, latency-bound
+  // launches) can run on a second stream next to it; the caller joins the two streams after the level
+  cudaStream_t bs = border_stream ? border_stream : stream;
   const int ncols = nx_in * channels;
   const int ny_out = ry.n_out, nx_out = rx.n_out;
   int nl = 0;
@@ -900,11 +903,11 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
     const int threads = ne >= 128 ? 128 : ((ne + 31) / 32) * 32;
     dim3 grid((ne + threads - 1) / threads, (nrows + kHR - 1) / kHR, 2 * nset);
     if (channels == 3)
-      pyr_horizontal_border_kernel<3><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, r0, nrows, rs_lo, rs_hi, skip_lo,
+      pyr_horizontal_border_kernel<3><<<grid, threads, 0, bs>>>(tmp, tmp_stride, ncols, nx_out, r0, nrows, rs_lo, rs_hi, skip_lo,
                                                                      skip_hi, rx.weights_t, rx.start, rx.taps, out0a, out0b, nset,
                                                                      out_stride, out_pitch, mm_parent, mm_child, mm_stride);
     else
-      pyr_horizontal_border_kernel<1><<<grid, threads, 0, stream>>>(tmp, tmp_stride, ncols, nx_out, r0, nrows, rs_lo, rs_hi, skip_lo,
+      pyr_horizontal_border_kernel<1><<<grid, threads, 0, bs>>>(tmp, tmp_stride, ncols, nx_out, r0, nrows, rs_lo, rs_hi, skip_lo,
                                                                      skip_hi, rx.weights_t, rx.start, rx.taps, out0a, out0b, nset,
                                                                      out_stride, out_pitch, mm_parent, mm_child, mm_stride);
     ++nl;
@@ -921,13 +924,13 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
     for (int ox = hhi; ox < nx_out; ++ox) in_right = std::min(in_right, rx.start_host[ox]);
     const int l4 = std::min(ncols / 4, (in_left * channels + 3) / 4);            // strip [0, l4) in float4 columns
     const int r4 = std::max(l4, std::min(ncols / 4, (in_right * channels) / 4)); // strip [r4, ncols/4)
-    if (hlo > 0 && l4 > 0) { ICA_VF(in0a, in0b, nset, in_stride, in_pitch, ncols, 0, l4, ry.fast, vlo, ngv, tmp, tmp_stride, stream); ++nl; }
+    if (hlo > 0 && l4 > 0) { ICA_VF(in0a, in0b, nset, in_stride, in_pitch, ncols, 0, l4, ry.fast, vlo, ngv, tmp, tmp_stride, bs); ++nl; }
     if (hhi < nx_out && ncols / 4 - r4 > 0) {
-      ICA_VF(in0a, in0b, nset, in_stride, in_pitch, ncols, r4, ncols / 4 - r4, ry.fast, vlo, ngv, tmp, tmp_stride, stream); ++nl;
+      ICA_VF(in0a, in0b, nset, in_stride, in_pitch, ncols, r4, ncols / 4 - r4, ry.fast, vlo, ngv, tmp, tmp_stride, bs); ++nl;
     }
     hgeneral(vlo, vhi - vlo, 0x7fffffff, 0x7fffffff, hlo, hhi);
   } else if (ngv > 0) {
-    ICA_VF(in0a, in0b, nset, in_stride, in_pitch, ncols, 0, ncols / 4, ry.fast, vlo, ngv, tmp, tmp_stride, stream);
+    ICA_VF(in0a, in0b, nset, in_stride, in_pitch, ncols, 0, ncols / 4, ry.fast, vlo, ngv, tmp, tmp_stride, bs);
     ++nl;
   }
   // (3) border rows (all rows when nothing is uniform): general vertical pass ...
@@ -948,11 +951,11 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
     }
     if (valign && span_ok) {
       dim3 grid((ncols / 4 + 127) / 128, ngroups, 2 * nset);
-      pyr_vertical_border4_kernel<<<grid, 128, 0, stream>>>(in0a, in0b, nset, in_stride, in_pitch, ncols / 4, ny_out, vlo, vhi,
+      pyr_vertical_border4_kernel<<<grid, 128, 0, bs>>>(in0a, in0b, nset, in_stride, in_pitch, ncols / 4, ny_out, vlo, vhi,
                                                              ry.weights, ry.start, ry.taps, tmp, tmp_stride, ncols);
     } else {
       dim3 grid((ncols + 255) / 256, ngroups, 2 * nset);
-      pyr_vertical_kernel<<<grid, 256, 0, stream>>>(in0a, in0b, nset, in_stride, in_pitch, ncols, ny_out, vlo, vhi, ry.weights,
+      pyr_vertical_kernel<<<grid, 256, 0, bs>>>(in0a, in0b, nset, in_stride, in_pitch, ncols, ny_out, vlo, vhi, ry.weights,
                                                      ry.start, ry.taps, tmp, tmp_stride);
     }
     ++nl;
@@ -969,7 +972,7 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
       if (ngroups > 0) {
         glo = lo; ghi = glo + ngroups * kFR;
         ICA_TP_C(launch_hfast, tmp, tmp_stride, ncols, rx.fast, lo, ngroups, ny_out, rs_lo, rs_hi, out0a, out0b, nset, out_stride,
-                 out_pitch, mm_parent, mm_child, mm_stride, stream);
+                 out_pitch, mm_parent, mm_child, mm_stride, bs);
         ++nl;
       }
     }

@@ -42,7 +42,7 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
                             int channels, const DeviceResample& ry, const DeviceResample& rx, float* tmp,
                             long long tmp_stride, float* out0a, float* out0b, long long out_stride, int out_pitch, int nset,
                             const MinMaxKeys* mm_parent, MinMaxKeys* mm_child, int mm_stride, cudaStream_t stream,
-                            int* launches = nullptr);
+                            int* launches = nullptr, cudaStream_t border_stream = nullptr);
 // uint8 / float64 -> float32 for nimg images of `count` elements, fused with each image's min/max keys
 cudaError_t launch_widen_f64(const float* in, double* out, long long n, cudaStream_t stream);
 // RGB host images of dtype (0 f32, 1 u8, 2 f64) -> one-channel float32 luminance + its min/max
