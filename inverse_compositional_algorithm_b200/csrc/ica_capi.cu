@@ -112,8 +112,6 @@ struct ica_plan {
   long long k2_stride = 0;
   int k2_pitch = 0;
   cudaStream_t stream = nullptr;  // own stream of the host entry
-  cudaStream_t aux_stream = nullptr;     // border kernels of the pyramid run here, next to the fused interior kernel
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   size_t device_bytes = 0;
   long long launches = 0;
   int last_launches_per_iter = 2;    // 1 when the last run used the fused solve
@@ -401,15 +399,10 @@ int build_pyramids(ica_plan* pl, const float* I1, const float* I2, cudaStream_t 
       float* outb = pl->pyr2 + (long long)b0 * pl->pyr_stride + Lo.offset;
       int nl = 0;
       if (pl->timing && pl->n_ev_pyr + 2 <= (int)pl->ev_pyr.size()) cudaEventRecord(pl->ev_pyr[pl->n_ev_pyr++], stream);
-      // fork: the border kernels of this level on the auxiliary stream, the fused interior kernel on the caller's
-      ICA_CUDA_CHECK(cudaEventRecord(pl->ev_fork, stream));
-      ICA_CUDA_CHECK(cudaStreamWaitEvent(pl->aux_stream, pl->ev_fork, 0));
       ICA_LAUNCH_CHECK(launch_pyr_down(ina, inb, istr, Li.pitch, Li.nx, Li.ny, pl->C, pl->ry[s], pl->rx[s], pl->tmp,
                                        tmp_per_img, outa, outb, pl->pyr_stride, Lo.pitch, nset,
                                        (pl->mm_open ? pl->mm_open : pl->mm) + ((long long)b0 * ns + s) * 2, pl->mm + ((long long)b0 * ns + s + 1) * 2,
-                                       ns * 2, stream, &nl, pl->aux_stream));
-      ICA_CUDA_CHECK(cudaEventRecord(pl->ev_join, pl->aux_stream));
-      ICA_CUDA_CHECK(cudaStreamWaitEvent(stream, pl->ev_join, 0));
+                                       ns * 2, stream, &nl));
       if (pl->timing && pl->n_ev_pyr + 1 <= (int)pl->ev_pyr.size()) cudaEventRecord(pl->ev_pyr[pl->n_ev_pyr++], stream);
       pl->launches += nl;
     }
@@ -470,9 +463,6 @@ int ica_plan_destroy(ica_plan* pl) {
   if (pl->ev_host0) cudaEventDestroy(pl->ev_host0);
   if (pl->ev_host1) cudaEventDestroy(pl->ev_host1);
   if (pl->ev_h2d_done) cudaEventDestroy(pl->ev_h2d_done);
-  if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
-  if (pl->ev_join) cudaEventDestroy(pl->ev_join);
-  if (pl->aux_stream) cudaStreamDestroy(pl->aux_stream);
   if (pl->stream) cudaStreamDestroy(pl->stream);
   delete pl;
   return ICA_OK;
@@ -595,9 +585,6 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   pl->device_bytes += pl->tmaps_host.size();
   if (pl->nscales > 1) TRY(encode_level_maps(pl, 1, pl->nscales));   // levels >= 1 live in the plan's slabs
   TRY_CUDA(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
-  TRY_CUDA(cudaStreamCreateWithFlags(&pl->aux_stream, cudaStreamNonBlocking));
-  TRY_CUDA(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
-  TRY_CUDA(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
   TRY_CUDA(cudaEventCreate(&pl->ev_host0));
   TRY_CUDA(cudaEventCreate(&pl->ev_host1));
   TRY_CUDA(cudaEventCreateWithFlags(&pl->ev_h2d_done, cudaEventDisableTiming));

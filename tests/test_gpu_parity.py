@@ -857,3 +857,34 @@ def test_ipol_options_follow_the_cpp_logs(nat, rubber_whale, ipol_logs, idx):
     # (B-spline in the reference's zoom.py, Keys in the C++ code): 3e-5 on the first iterations of the coarsest scale
     tol = 2e-6 if r["nscales"] == 1 else 1.5e-4
     assert derr <= tol and dp <= tol
+
+
+def test_fused_solve_mode_matches_default_loop(nat, monkeypatch):
+    """The opt-in fused solve (ICA_FUSE=1: the CTA that finishes a pair's last chunk solves it inside the iterate kernel,
+    one launch per iteration, double-buffered work lists) must give what the default {iterate, solve} loop gives (same
+    iteration counts, parameters equal up to the grouping of the fp64 partial sums) -- ragged batch, graph loop and
+    host-driven loop."""
+    from inverse_compositional_algorithm_b200 import _native, synthetic
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    types = [TransformType.HOMOGRAPHY, TransformType.AFFINITY, TransformType.SIMILARITY, TransformType.HOMOGRAPHY]
+    pairs = [synthetic.make_pair(1700 + i, 150, 200, 3, t, max_shift=3.0, margin=32) for i, t in enumerate(types)]
+    I1 = np.stack([a for a, _, _ in pairs]); I2 = np.stack([b for _, b, _ in pairs])
+
+    def run(host_loop):
+        plan = _native.Plan(batch=4, height=150, width=200, channels=3, nscales=3, nu=0.5, transform_type=types[0].value,
+                            robust_type=3, robust_loop=True, lambda_=0.0, tol=1e-3, max_iter=30, delta=5, nanifoutside=True,
+                            host_loop=host_loop)
+        plan.set_transform_types([t.value for t in types])
+        out = plan.run_host(I1, I2)
+        n = plan.last_launch_count()
+        plan.close()
+        return out[0], out[1], out[2], n
+    ref = run(False)
+    monkeypatch.setenv("ICA_FUSE", "1")
+    for host_loop in (False, True):
+        got = run(host_loop)
+        # (the fused solve adds the chunk partials in 11 groups, the solve kernel in 16: last-bit differences of the fp64 sums)
+        assert np.array_equal(got[2], ref[2])
+        np.testing.assert_allclose(got[0], ref[0], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(got[1], ref[1], rtol=1e-6)
+    assert got[3] < ref[3]      # one launch per iteration instead of two
