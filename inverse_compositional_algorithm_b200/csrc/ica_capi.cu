@@ -85,6 +85,8 @@ struct ica_plan {
   PairState* state = nullptr;
   MinMaxKeys* mm = nullptr;
   MinMaxKeys* mm_open = nullptr;    // IPOL pyramid (no clip): open parent ranges
+  MinMaxKeys* gather_keys = nullptr;   // open ranges for the border kernels of a gathering level (same layout as mm)
+  int* clip_flags = nullptr;           // [2B] deferred-clip decisions
   double* partials = nullptr;
   double* traj = nullptr;
   int traj_cap = 0;
@@ -169,7 +171,7 @@ void free_resample(DeviceResample* d) {
 
 int validate_config(const ica_config* c) {
   if (!c) { set_error("config is NULL"); return ICA_ERR_INVALID; }
-  if (c->batch < 1) { set_error("batch must be >= 1"); return ICA_ERR_INVALID; }
+  if (c->batch < 1 || c->batch >= (1 << 20)) { set_error("batch must be in [1, 2^20)"); return ICA_ERR_INVALID; }
   if (c->height < 1 || c->width < 1) { set_error("image shape must be positive"); return ICA_ERR_INVALID; }
   if (c->channels != 1 && c->channels != 3) { set_error("channels must be 1 or 3"); return ICA_ERR_INVALID; }
   if (c->nscales < 1 || c->nscales > ICA_MAX_SCALES) { set_error("nscales must be in [1, %d]", ICA_MAX_SCALES); return ICA_ERR_INVALID; }
@@ -306,6 +308,7 @@ void fill_iter_params(const ica_plan* pl, const float* /*I1*/, const float* /*I2
   P->item_pair = pl->item_pair;
   P->hdr = pl->hdr;
   P->pair_ticket = pl->pair_ticket;
+  P->grid_ctas = pl->grid;
   P->fused = 0;                      // the callers that run the fused loop set it
   P->solve_ticket = pl->solve_ticket;
   P->asm_tab = pl->asm_tab;
@@ -372,14 +375,23 @@ int ensure_loop_graph(ica_plan* pl, const float* I1, const float* I2, int solve_
 // minmax of level 0 and all pyramid levels of both images
 int build_pyramids(ica_plan* pl, const float* I1, const float* I2, cudaStream_t stream) {
   const int B = pl->B, ns = pl->nscales;
-  if (!pl->mm_ready) {   // (the host entry's u8 / f64 conversion kernels have done this already)
+  // Level 0's min / max (the clip range of level 1 and of the warps at level 0): done by the host entry's
+  // conversion kernels, else gathered by the first pyramid level's own read of level 0 when that level takes the fused
+  // kernel (no separate pass over both images: -25 MB per pair), else by a separate pass.
+  bool gather0 = false;
+  if (!pl->mm_ready) {
     ICA_LAUNCH_CHECK(launch_minmax_reset(pl->mm, B * ns * 2, stream));
     pl->launches += 1;
-    const long long n0 = (long long)pl->H * pl->W * pl->C;
-    const float* src[2] = {I1, I2};
-    for (int which = 0; which < 2; ++which) {
-      ICA_LAUNCH_CHECK(launch_minmax(src[which], pl->in_stride, n0, B, pl->mm + which, ns * 2, stream));
-      pl->launches += 1;
+    gather0 = ns > 1 && pl->gather_keys && !getenv("ICA_NO_GATHER") &&
+              pyr_level_gathers(I1, I2, pl->in_stride, pl->lv[0].pitch, pl->lv[0].nx, pl->lv[0].ny, pl->C, pl->ry[0], pl->rx[0], pl->tmp,
+                                (long long)pl->lv[1].ny * pl->lv[0].nx * pl->C);
+    if (!gather0) {
+      const long long n0 = (long long)pl->H * pl->W * pl->C;
+      const float* src[2] = {I1, I2};
+      for (int which = 0; which < 2; ++which) {
+        ICA_LAUNCH_CHECK(launch_minmax(src[which], pl->in_stride, n0, B, pl->mm + which, ns * 2, stream));
+        pl->launches += 1;
+      }
     }
   }
   pl->mm_ready = false;
@@ -399,10 +411,18 @@ int build_pyramids(ica_plan* pl, const float* I1, const float* I2, cudaStream_t 
       float* outb = pl->pyr2 + (long long)b0 * pl->pyr_stride + Lo.offset;
       int nl = 0;
       if (pl->timing && pl->n_ev_pyr + 2 <= (int)pl->ev_pyr.size()) cudaEventRecord(pl->ev_pyr[pl->n_ev_pyr++], stream);
+      const bool gather = gather0 && s == 0;
       ICA_LAUNCH_CHECK(launch_pyr_down(ina, inb, istr, Li.pitch, Li.nx, Li.ny, pl->C, pl->ry[s], pl->rx[s], pl->tmp,
                                        tmp_per_img, outa, outb, pl->pyr_stride, Lo.pitch, nset,
                                        (pl->mm_open ? pl->mm_open : pl->mm) + ((long long)b0 * ns + s) * 2, pl->mm + ((long long)b0 * ns + s + 1) * 2,
-                                       ns * 2, stream, &nl));
+                                       ns * 2, stream, &nl, nullptr, gather ? pl->mm + ((long long)b0 * ns + s) * 2 : nullptr,
+                                       gather ? pl->gather_keys + ((long long)b0 * ns + s) * 2 : nullptr));
+      if (gather && !pl->mm_open) {   // deferred clip of level 1 to level 0's range (zoom_out levels are never clipped)
+        ICA_LAUNCH_CHECK(launch_clip_fixup(outa, outb, pl->pyr_stride, Lo.pitch, Lo.nx, Lo.ny, pl->C, nset,
+                                           pl->mm + ((long long)b0 * ns + s) * 2, pl->mm + ((long long)b0 * ns + s + 1) * 2, ns * 2,
+                                           pl->clip_flags + 2 * b0, stream));
+        nl += 3;
+      }
       if (pl->timing && pl->n_ev_pyr + 1 <= (int)pl->ev_pyr.size()) cudaEventRecord(pl->ev_pyr[pl->n_ev_pyr++], stream);
       pl->launches += nl;
     }
@@ -449,7 +469,7 @@ int ica_plan_destroy(ica_plan* pl) {
   for (int r = 0; r < pl->x_world; ++r) if (r != pl->x_rank && pl->x_peer_ptr[r]) cudaIpcCloseMemHandle(pl->x_peer_ptr[r]);
   cudaFree(pl->xbuf); cudaFree(pl->x_peers_dev); cudaFree(pl->x_error); cudaFree(pl->x_ns); cudaFree(pl->x_seq_dev);
   if (pl->x_seq_host) cudaFreeHost(pl->x_seq_host);
-  cudaFree(pl->mm_open);
+  cudaFree(pl->mm_open); cudaFree(pl->gather_keys); cudaFree(pl->clip_flags);
   cudaFree(pl->state); cudaFree(pl->mm); cudaFree(pl->partials); cudaFree(pl->chunk_start); cudaFree(pl->item_pair); cudaFree(pl->solve_ticket); cudaFree(pl->asm_tab); cudaFree(pl->loop_count); cudaFree(pl->kernel_ns); cudaFree(pl->hdr); cudaFree(pl->pair_ticket);
   if (pl->h_loop) cudaFreeHost(pl->h_loop);
   if (pl->h_kns) cudaFreeHost(pl->h_kns);
@@ -502,7 +522,7 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   // it is batched with
   int mc = cfg->blocks_per_pair > 0 ? cfg->blocks_per_pair : (nt0 > 16384 ? 1024 : 128);
   if (cfg->blocks_per_pair <= 0) { const char* e = getenv("ICA_CHUNKS"); if (e && atoi(e) > 0) mc = atoi(e); }   // tuning hook
-  pl->max_chunks = std::max(1, std::min(mc, nt0));
+  pl->max_chunks = std::max(1, std::min(std::min(mc, nt0), 2047));   // (work items pack the chunk index into 11 bits)
   {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -537,6 +557,13 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   }
   TRY(dev_alloc(pl, &pl->state, (size_t)pl->B));
   TRY(dev_alloc(pl, &pl->mm, (size_t)pl->B * pl->nscales * 2));
+  {
+    TRY(dev_alloc(pl, &pl->gather_keys, (size_t)pl->B * pl->nscales * 2));
+    TRY(dev_alloc(pl, &pl->clip_flags, (size_t)pl->B * 2));
+    std::vector<MinMaxKeys> open_keys((size_t)pl->B * pl->nscales * 2);
+    for (auto& k : open_keys) { k.lo = float_key(-3.4028235e38f); k.hi = float_key(3.4028235e38f); }
+    TRY_CUDA(cudaMemcpy(pl->gather_keys, open_keys.data(), open_keys.size() * sizeof(MinMaxKeys), cudaMemcpyHostToDevice));
+  }
   if (cfg->flags & ICA_FLAG_IPOL_PYRAMID) {   // zoom_out does not clip: the pyramid kernels get an open parent range
     TRY(dev_alloc(pl, &pl->mm_open, (size_t)pl->B * pl->nscales * 2));
     std::vector<MinMaxKeys> open_keys((size_t)pl->B * pl->nscales * 2);

@@ -53,6 +53,7 @@ constexpr int kConsumerWarps = ICA_CONSUMER_WARPS;   // + 1 producer warp = 12 w
 constexpr int kRowsPerWarp = 1;      // rows of a tile per consumer warp
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = kConsumerThreads + 32;   // + one producer warp
+constexpr int kItemPairBits = 20;   // a work item = pair | chunk << 20 (one read tells the producer both)
 constexpr int TW = 64;            // tile width  (2 pixels per lane: x0+lane, x0+32+lane)
 constexpr int TH = kRowsPerWarp * kConsumerWarps;   // tile height (row y0 + warp + rr * kConsumerWarps for warp, rr)
 constexpr int HALO = 4;           // the I1 patch starts at x0-4: the inner coordinate of a TMA box must be a multiple of 16 bytes
@@ -203,19 +204,22 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stages
   unsigned k = 0;   // tiles staged so far by this CTA
   SchedHdr* const hdr = P.hdr + par;
   const int* const item_pair = P.item_pair + (long long)par * P.B * P.max_chunks;
-  const int* const chunk_start = P.chunk_start + (long long)par * (P.B + 1);
+  bool first_item = !P.fused;
   const bool pdbg = kTimeline && P.dbg_time != nullptr && lane == 0;   // profiling hook: cycles spent fetching work / waiting for a free stage
   long long pd_fetch = 0, pd_empty = 0, pd_proj = 0, pd_ctl = 0, pd_issue = 0;
   for (;;) {
     // dynamic work distribution: chunks are handed out by an atomic counter (reset by the scheduler)
     const long long pf0 = pdbg ? clock64() : 0;
-    int item = 0;
-    if (lane == 0) item = atomicAdd(&hdr->counter, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
+    int item = (int)blockIdx.x;        // first item of this CTA: static (the dynamic counter starts at the grid size)
+    if (!first_item) {
+      if (lane == 0) item = atomicAdd(&hdr->counter, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
+    }
+    first_item = false;
     // (the total is re-read: with the fused solve a CTA that starts late may find the list of the NEXT iteration here)
     if (item >= __ldcg(&hdr->total)) break;
-    const int pair = __ldcg(item_pair + item);
-    const int chunk = item - __ldcg(chunk_start + pair);
+    const int packed = __ldcg(item_pair + item);
+    const int pair = packed & ((1 << kItemPairBits) - 1), chunk = packed >> kItemPairBits;
     // the pair's state was written by the solve of the previous iteration, possibly during this very launch: read
     // it from L2, never through a (per-SM, possibly stale) L1 line
     const PairState* stp = P.state + pair;
@@ -382,7 +386,7 @@ __device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal, bo
 #pragma unroll 1
     for (int src = 0; src < 32; ++src) {
       const int cb = __shfl_sync(0xffffffffu, c, src), eb = __shfl_sync(0xffffffffu, excl, src);
-      for (int i = lane; i < cb; i += 32) item_pair[eb + i] = base + (warp << 5) + src;
+      for (int i = lane; i < cb; i += 32) item_pair[eb + i] = (base + (warp << 5) + src) | (i << kItemPairBits);   // (pair, chunk)
     }
     if (lane == 0 && actmask) atomicAdd(&s_scal[1], __popc(actmask));
     if (lane == 0 && workmask) atomicAdd(&s_scal[2], __popc(workmask));
@@ -396,7 +400,10 @@ __device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal, bo
     chunk_start[B] = s_scal[0];
     *P.n_active = s_scal[1];
     SchedHdr* hn = P.hdr + np;
-    hn->total = s_scal[0]; hn->npairs = s_scal[2]; hn->counter = 0;
+    hn->total = s_scal[0]; hn->npairs = s_scal[2];
+    // CTA i takes item i first (no atomic on its critical path), then claims dynamically.  Not with the fused solve: a CTA
+    // of the previous launch that starts late may already work on this list, so there every item is claimed atomically
+    hn->counter = P.fused ? 0 : P.grid_ctas;
     hn->t0 = 0x7fffffffffffffffll; hn->t1 = 0;
     // device-side bookkeeping of the loop: iterations done, time spent in the streaming phase of the iterate kernel
     int cnt = 0;

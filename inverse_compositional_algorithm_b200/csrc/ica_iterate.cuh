@@ -41,6 +41,7 @@ struct IterParams {
   int* item_pair;         // [2][B*max_chunks] pair of each work item
   SchedHdr* hdr;          // [2] totals, work counter and time stamps of each list
   unsigned int* pair_ticket;   // [B] chunks of a pair that are done in the current iteration (fused solve)
+  int grid_ctas;          // CTAs of the iterate launch (the work counter starts there: CTA i takes item i first)
   int fused;              // 1: the CTA that finishes a pair's last chunk solves it inside the iterate kernel (no solve launch)
   const AsmEntry* asm_tab;      // [6 transform codes][72]
   const void* tmaps;            // CUtensorMap [B][nscales][2] (I1 zero-filled, I2 NaN-filled boxes), 128 bytes each

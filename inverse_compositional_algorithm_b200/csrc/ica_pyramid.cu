@@ -551,12 +551,17 @@ template <int C> struct FusedCfg {
   static constexpr int PADN = 2 * kFH * C;                 // floats between pads
   static constexpr int TASKS_PER_ROW = (OWB / kFH) * C;    // 48
 };
-template <int C, int TP>
+// GATHER (level 0 -> 1 when the caller has not computed level 0's min / max): the block also takes the min / max of the
+// input rows and float4 columns it OWNS (consecutive blocks' windows overlap; the owned parts tile the union exactly once)
+// into mm_gather -- the separate pass over level 0 disappears -- and, the parent's range being unknown until every block
+// is done, does not clip: the caller clamps the child level afterwards in the (rare) case that it leaves the range.
+template <int C, int TP, bool GATHER>
 __global__ void __launch_bounds__(128) pyr_fused_fast_kernel(
     const float* __restrict__ in0a, const float* __restrict__ in0b, int nset, long long in_stride, int in_pitch, int ncols,
     int oy_lo, int s0y, const FastW fwy, int ox_lo, int ox_hi, int s0x, const FastW fwx,
     float* __restrict__ out0a, float* __restrict__ out0b, long long out_stride, int out_pitch,
-    const MinMaxKeys* __restrict__ mm_parent, MinMaxKeys* __restrict__ mm_child, int mm_stride) {
+    const MinMaxKeys* __restrict__ mm_parent, MinMaxKeys* __restrict__ mm_child, int mm_stride,
+    MinMaxKeys* __restrict__ mm_gather) {
   constexpr int OWB = FusedCfg<C>::OWB, PADN = FusedCfg<C>::PADN, TPR = FusedCfg<C>::TASKS_PER_ROW;
   constexpr int WF = ((2 * (OWB - 1) + TP) * C + 3 + 3) / 4 * 4;   // window floats incl. alignment slack, float4 multiple
   constexpr int NW4 = WF / 4;
@@ -577,6 +582,10 @@ __global__ void __launch_bounds__(128) pyr_fused_fast_kernel(
   {
     const float* inb = (set ? in0b : in0a) + (long long)pb * in_stride;
     const bool act = t < NW4 && f0 + 4 * t < ncols;
+    constexpr int kOwnJ0 = (TP - 2) / 2, kOwnT0 = (NW4 - 2 * OWB * C / 4) / 2;     // owned rows / float4 columns of the window
+    static_assert(kOwnT0 >= 0, "a block's window is at least as wide as the stride between blocks");
+    const bool towned = GATHER && t >= kOwnT0 && t < kOwnT0 + 2 * OWB * C / 4;
+    float gmin = 3.4e38f, gmax = -3.4e38f;       // NaNs are skipped by fminf / fmaxf (nanmin / nanmax)
     float2 acc[kFRV][2];
 #pragma unroll
     for (int r = 0; r < kFRV; ++r) { acc[r][0] = make_float2(0.f, 0.f); acc[r][1] = make_float2(0.f, 0.f); }
@@ -587,6 +596,10 @@ __global__ void __launch_bounds__(128) pyr_fused_fast_kernel(
       for (int j = 0; j < TP + 2 * (kFRV - 1); ++j) {
         const float4 v = __ldg(in + (long long)j * p4);
         const float2 vlo2 = make_float2(v.x, v.y), vhi2 = make_float2(v.z, v.w);
+        if (GATHER && j >= kOwnJ0 && j < kOwnJ0 + 2 * kFRV && towned) {
+          gmin = fminf(fminf(gmin, fminf(v.x, v.y)), fminf(v.z, v.w));
+          gmax = fmaxf(fmaxf(gmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+        }
 #pragma unroll
         for (int r = 0; r < kFRV; ++r) {
           const int k = j - 2 * r;
@@ -596,6 +609,18 @@ __global__ void __launch_bounds__(128) pyr_fused_fast_kernel(
             acc[r][1] = __ffma2_rn(w2, vhi2, acc[r][1]);
           }
         }
+      }
+    }
+    if (GATHER) {      // block min / max of the owned inputs -> the parent level's keys
+      unsigned kmin = gmin <= gmax ? float_key(gmin) : 0xffffffffu, kmax = gmin <= gmax ? float_key(gmax) : 0u;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+      }
+      if ((t & 31) == 0 && kmin <= kmax) {
+        MinMaxKeys* gk = mm_gather + (long long)pb * mm_stride + set;
+        atomicMin(&gk->lo, kmin); atomicMax(&gk->hi, kmax);
       }
     }
     if (t < NW4) {
@@ -614,8 +639,11 @@ __global__ void __launch_bounds__(128) pyr_fused_fast_kernel(
   __syncthreads();
   // ---- stage 2: horizontal pass from shared memory
   float* out0 = (set ? out0b : out0a) + (long long)pb * out_stride;
-  const MinMaxKeys pk = mm_parent[(long long)pb * mm_stride + set];
-  const float lo = key_float(pk.lo), hi = key_float(pk.hi);
+  float lo = -3.4028235e38f, hi = 3.4028235e38f;
+  if (!GATHER) {
+    const MinMaxKeys pk = mm_parent[(long long)pb * mm_stride + set];
+    lo = key_float(pk.lo); hi = key_float(pk.hi);
+  }
   float vmin = 3.4e38f, vmax = -3.4e38f;
 #pragma unroll 1
   for (int q = t; q < kFRV * TPR; q += 128) {
@@ -662,6 +690,80 @@ __global__ void __launch_bounds__(128) pyr_fused_fast_kernel(
       if (kmin <= kmax) { atomicMin(&ck->lo, kmin); atomicMax(&ck->hi, kmax); }
     }
   }
+}
+
+// Min / max of the part of a level that the GATHER blocks of the fused kernel do not own: rows outside [r0, r1) in full,
+// and the floats outside [f0, f1) of the rows inside.  grid (blocks, images)
+__global__ void __launch_bounds__(256) minmax_frame_kernel(const float* __restrict__ in0a, const float* __restrict__ in0b, int nset,
+                                                            long long in_stride, int in_pitch, int ncols, int ny, int r0, int r1,
+                                                            int f0, int f1, MinMaxKeys* __restrict__ mm, int mm_stride) {
+  const int img = blockIdx.y;
+  const int set = img < nset ? 0 : 1, pb = img - set * nset;
+  const float* in = (set ? in0b : in0a) + (long long)pb * in_stride;
+  float fmin_ = 3.4e38f, fmax_ = -3.4e38f;
+  const int side = f0 + (ncols - f1);                 // floats per inside row that belong to the frame
+  for (int y = blockIdx.x; y < ny; y += gridDim.x) {
+    const float* row = in + (long long)y * in_pitch;
+    if (y < r0 || y >= r1) {
+      for (int i = threadIdx.x; i < ncols; i += blockDim.x) { const float v = __ldg(row + i); fmin_ = fminf(fmin_, v); fmax_ = fmaxf(fmax_, v); }
+    } else {
+      for (int i = threadIdx.x; i < side; i += blockDim.x) {
+        const float v = __ldg(row + (i < f0 ? i : f1 + (i - f0)));
+        fmin_ = fminf(fmin_, v); fmax_ = fmaxf(fmax_, v);
+      }
+    }
+  }
+  unsigned kmin = 0xffffffffu, kmax = 0u;
+  if (fmin_ <= fmax_) { kmin = float_key(fmin_); kmax = float_key(fmax_); }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  }
+  __shared__ unsigned smin[8], smax[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { smin[warp] = kmin; smax[warp] = kmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { kmin = min(kmin, smin[w]); kmax = max(kmax, smax[w]); }
+    MinMaxKeys* k = mm + (long long)pb * mm_stride + set;
+    if (kmin <= kmax) { atomicMin(&k->lo, kmin); atomicMax(&k->hi, kmax); }
+  }
+}
+
+// Deferred clip of a level that was built without its parent's range (GATHER): decide per image whether any value
+// left [parent min, parent max] (skimage's clip), clamp those images, then clamp their keys.
+__global__ void clip_decide_kernel(const MinMaxKeys* __restrict__ mm_parent, const MinMaxKeys* __restrict__ mm_child, int mm_stride,
+                                   int nimg, int nset, int* __restrict__ flags) {
+  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= nimg) return;
+  const int set = img < nset ? 0 : 1, pb = img - set * nset;
+  const MinMaxKeys p = mm_parent[(long long)pb * mm_stride + set], c = mm_child[(long long)pb * mm_stride + set];
+  flags[img] = (c.lo <= c.hi && (c.lo < p.lo || c.hi > p.hi)) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) clip_apply_kernel(float* __restrict__ out0a, float* __restrict__ out0b, int nset, long long out_stride,
+                                                          int out_pitch, int ncols, int ny, const MinMaxKeys* __restrict__ mm_parent,
+                                                          MinMaxKeys* __restrict__ mm_child, int mm_stride, const int* __restrict__ flags) {
+  const int img = blockIdx.y;
+  if (!flags[img]) return;
+  const int set = img < nset ? 0 : 1, pb = img - set * nset;
+  const MinMaxKeys p = mm_parent[(long long)pb * mm_stride + set];
+  const float lo = key_float(p.lo), hi = key_float(p.hi);
+  float* out = (set ? out0b : out0a) + (long long)pb * out_stride;
+  for (int y = blockIdx.x; y < ny; y += gridDim.x)
+    for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
+      float* q = out + (long long)y * out_pitch + i;
+      *q = fminf(fmaxf(*q, lo), hi);
+    }
+}
+__global__ void clip_keys_kernel(const MinMaxKeys* __restrict__ mm_parent, MinMaxKeys* __restrict__ mm_child, int mm_stride, int nimg,
+                                 int nset, const int* __restrict__ flags) {
+  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= nimg || !flags[img]) return;
+  const int set = img < nset ? 0 : 1, pb = img - set * nset;
+  const MinMaxKeys p = mm_parent[(long long)pb * mm_stride + set];
+  MinMaxKeys* c = mm_child + (long long)pb * mm_stride + set;
+  c->lo = max(c->lo, p.lo); c->hi = min(c->hi, p.hi);      // keys are order-preserving: the range of the clamped values
 }
 
 __global__ void minmax_reset_kernel(MinMaxKeys* mm, int count) {
@@ -856,14 +958,57 @@ template <int C, int TP>
 static void launch_fused(const float* in0a, const float* in0b, int nset, long long in_stride, int in_pitch, int ncols,
                          const FastRows& fy, int vlo, int ngv, const FastRows& fx, int hlo, int hhi,
                          float* out0a, float* out0b, long long out_stride, int out_pitch,
-                         const MinMaxKeys* mm_parent, MinMaxKeys* mm_child, int mm_stride, cudaStream_t stream) {
+                         const MinMaxKeys* mm_parent, MinMaxKeys* mm_child, int mm_stride, cudaStream_t stream,
+                         MinMaxKeys* mm_gather, int* own /* r0, r1, f0, f1 of the gathered region */) {
   FastW fwy, fwx;
   for (int k = 0; k < kFastTapsMax; ++k) { fwy.w[k] = fy.w[k]; fwx.w[k] = fx.w[k]; }
   constexpr int OWB = FusedCfg<C>::OWB;
   dim3 grid((hhi - hlo + OWB - 1) / OWB, ngv, 2 * nset);
-  pyr_fused_fast_kernel<C, TP><<<grid, 128, 0, stream>>>(in0a, in0b, nset, in_stride, in_pitch, ncols, vlo, fy.s0, fwy, hlo, hhi,
-                                                          fx.s0, fwx, out0a, out0b, out_stride, out_pitch, mm_parent, mm_child,
-                                                          mm_stride);
+  if (mm_gather) {
+    pyr_fused_fast_kernel<C, TP, true><<<grid, 128, 0, stream>>>(in0a, in0b, nset, in_stride, in_pitch, ncols, vlo, fy.s0, fwy, hlo, hhi,
+                                                                  fx.s0, fwx, out0a, out0b, out_stride, out_pitch, mm_parent, mm_child,
+                                                                  mm_stride, mm_gather);
+    // the region the blocks own (same arithmetic as the kernel): rows and floats, clamped to the image
+    constexpr int WF = ((2 * (OWB - 1) + TP) * C + 3 + 3) / 4 * 4, NW4 = WF / 4;
+    constexpr int kOwnJ0 = (TP - 2) / 2, kOwnT0 = (NW4 - 2 * OWB * C / 4) / 2;
+    const int f00 = ((2 * hlo + fx.s0) * C) & ~3;
+    own[0] = 2 * vlo + fy.s0 + kOwnJ0;
+    own[1] = own[0] + 2 * kFRV * ngv;
+    own[2] = std::min(ncols, f00 + 4 * kOwnT0);
+    own[3] = std::min(ncols, f00 + 4 * kOwnT0 + 2 * OWB * C * (int)grid.x);
+  } else {
+    pyr_fused_fast_kernel<C, TP, false><<<grid, 128, 0, stream>>>(in0a, in0b, nset, in_stride, in_pitch, ncols, vlo, fy.s0, fwy, hlo, hhi,
+                                                                   fx.s0, fwx, out0a, out0b, out_stride, out_pitch, mm_parent, mm_child,
+                                                                   mm_stride, nullptr);
+  }
+}
+
+// True when launch_pyr_down would take the fused interior kernel for this level, i.e. when it can gather the parent's
+// min / max itself (same conditions as in launch_pyr_down).
+bool pyr_level_gathers(const float* in0a, const float* in0b, long long in_stride, int in_pitch, int nx_in, int ny_in, int channels,
+                       const DeviceResample& ry, const DeviceResample& rx, const float* tmp, long long tmp_stride) {
+  const int ncols = nx_in * channels;
+  const bool valign = (ncols % 4 == 0) && (in_pitch % 4 == 0) && (in_stride % 4 == 0) && (tmp_stride % 4 == 0) &&
+                      ((reinterpret_cast<unsigned long long>(in0a) | reinterpret_cast<unsigned long long>(in0b) |
+                        reinterpret_cast<unsigned long long>(tmp)) & 15ull) == 0;
+  const int tmax = std::max(ry.fast.taps, rx.fast.taps);
+  const int TP = tmax <= 32 ? 32 : kFastTapsMax;
+  int vlo = 0, ngv = 0, fhl = 0, fhn = 0;
+  if (valign && ry.fast.hi - ry.fast.lo >= kFRV) fast_groups(ry.fast, ny_in, TP, kFRV, &vlo, &ngv);
+  if (ngv > 0 && rx.fast.hi - rx.fast.lo >= kFH) fast_groups(rx.fast, nx_in, TP, kFH, &fhl, &fhn);
+  return ngv > 0 && fhn > 0;
+}
+
+// Deferred clip after a gathering level: clamp the child images whose values left the parent's range, and their keys.
+cudaError_t launch_clip_fixup(float* out0a, float* out0b, long long out_stride, int out_pitch, int nx_out, int ny_out, int channels,
+                              int nset, const MinMaxKeys* mm_parent, MinMaxKeys* mm_child, int mm_stride, int* flags,
+                              cudaStream_t stream) {
+  const int nimg = 2 * nset;
+  clip_decide_kernel<<<(nimg + 127) / 128, 128, 0, stream>>>(mm_parent, mm_child, mm_stride, nimg, nset, flags);
+  clip_apply_kernel<<<dim3(std::min(ny_out, 32), nimg), 256, 0, stream>>>(out0a, out0b, nset, out_stride, out_pitch, nx_out * channels,
+                                                                           ny_out, mm_parent, mm_child, mm_stride, flags);
+  clip_keys_kernel<<<(nimg + 127) / 128, 128, 0, stream>>>(mm_parent, mm_child, mm_stride, nimg, nset, flags);
+  return cudaGetLastError();
 }
 
 // One level for `nset` pairs: both image sets (a = I1, b = I2) in the same launches.  mm_parent / mm_child
@@ -872,7 +1017,7 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
                             int channels, const DeviceResample& ry, const DeviceResample& rx, float* tmp,
                             long long tmp_stride, float* out0a, float* out0b, long long out_stride, int out_pitch, int nset,
                             const MinMaxKeys* mm_parent, MinMaxKeys* mm_child, int mm_stride, cudaStream_t stream,
-                            int* launches, cudaStream_t border_stream) {
+                            int* launches, cudaStream_t border_stream, MinMaxKeys* mm_gather, const MinMaxKeys* mm_open) {
   // everything but the fused interior kernel (border rows / columns: ~5 % of the outputs in small, latency-bound
   // launches) can run on a second stream next to it; the caller joins the two streams after the level
   cudaStream_t bs = border_stream ? border_stream : stream;
@@ -894,6 +1039,11 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
   int fhl = 0, fhn = 0;
   if (ngv > 0 && rx.fast.hi - rx.fast.lo >= kFH) fast_groups(rx.fast, nx_in, TP, kFH, &fhl, &fhn);
   const bool fused = ngv > 0 && fhn > 0;
+  // gather mode (see pyr_level_gathers): the parent's min / max is produced by this level's own first read; nothing is
+  // clipped here (the border kernels get an open range), the caller clamps afterwards if a value left the range
+  if (mm_gather && (!fused || !mm_open)) return cudaErrorInvalidValue;
+  if (mm_gather) mm_parent = mm_open;
+  int own[4] = {0, 0, 0, 0};
 #define ICA_TP_C(fn, ...) do { if (channels == 3) { if (TP == 32) fn<3, 32>(__VA_ARGS__); else fn<3, kFastTapsMax>(__VA_ARGS__); } \
                                else { if (TP == 32) fn<1, 32>(__VA_ARGS__); else fn<1, kFastTapsMax>(__VA_ARGS__); } } while (0)
 #define ICA_VF(...) do { if (TP == 32) launch_vfast<32>(__VA_ARGS__); else launch_vfast<kFastTapsMax>(__VA_ARGS__); } while (0)
@@ -916,8 +1066,13 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
     hlo = fhl; hhi = hlo + fhn * kFH;
     // (1) interior x interior: both passes in one kernel, no intermediate image
     ICA_TP_C(launch_fused, in0a, in0b, nset, in_stride, in_pitch, ncols, ry.fast, vlo, ngv, rx.fast, hlo, hhi, out0a, out0b,
-             out_stride, out_pitch, mm_parent, mm_child, mm_stride, stream);
+             out_stride, out_pitch, mm_parent, mm_child, mm_stride, stream, mm_gather, own);
     ++nl;
+    if (mm_gather) {   // the frame of the parent level that no block owns
+      minmax_frame_kernel<<<dim3(std::min(ny_in, 64), 2 * nset), 256, 0, bs>>>(in0a, in0b, nset, in_stride, in_pitch, ncols, ny_in, own[0],
+                                                                                own[1], own[2], own[3], mm_gather, mm_stride);
+      ++nl;
+    }
     // (2) interior rows x border columns: vertical fast pass on the two column strips the border outputs read
     int in_left = 0, in_right = nx_in;
     for (int ox = 0; ox < hlo; ++ox) in_left = std::max(in_left, rx.start_host[ox] + rx.taps);

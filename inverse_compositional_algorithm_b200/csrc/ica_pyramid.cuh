@@ -42,7 +42,15 @@ cudaError_t launch_pyr_down(const float* in0a, const float* in0b, long long in_s
                             int channels, const DeviceResample& ry, const DeviceResample& rx, float* tmp,
                             long long tmp_stride, float* out0a, float* out0b, long long out_stride, int out_pitch, int nset,
                             const MinMaxKeys* mm_parent, MinMaxKeys* mm_child, int mm_stride, cudaStream_t stream,
-                            int* launches = nullptr, cudaStream_t border_stream = nullptr);
+                            int* launches = nullptr, cudaStream_t border_stream = nullptr, MinMaxKeys* mm_gather = nullptr,
+                            const MinMaxKeys* mm_open = nullptr);
+// gather mode of launch_pyr_down (mm_gather != nullptr): the level's first read also produces the PARENT's min / max
+// (no separate pass over the parent), nothing is clipped, and launch_clip_fixup clamps afterwards where needed
+bool pyr_level_gathers(const float* in0a, const float* in0b, long long in_stride, int in_pitch, int nx_in, int ny_in, int channels,
+                       const DeviceResample& ry, const DeviceResample& rx, const float* tmp, long long tmp_stride);
+cudaError_t launch_clip_fixup(float* out0a, float* out0b, long long out_stride, int out_pitch, int nx_out, int ny_out, int channels,
+                              int nset, const MinMaxKeys* mm_parent, MinMaxKeys* mm_child, int mm_stride, int* flags,
+                              cudaStream_t stream);
 // uint8 / float64 -> float32 for nimg images of `count` elements, fused with each image's min/max keys
 cudaError_t launch_widen_f64(const float* in, double* out, long long n, cudaStream_t stream);
 // RGB host images of dtype (0 f32, 1 u8, 2 f64) -> one-channel float32 luminance + its min/max
