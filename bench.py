@@ -494,7 +494,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=256, help="image pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=512, help="image pairs per step per GPU")
     ap.add_argument("--input-dtype", default="u8", choices=["u8", "f32"],
                     help="dtype of the host images on the e2e leg (values are identical on the device-resident leg)")
     ap.add_argument("--chunks", type=int, default=0, help="partial-sum slots per pair (0 = library default: 256, or 1024 for very large images)")

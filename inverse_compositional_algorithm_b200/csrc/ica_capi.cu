@@ -888,12 +888,12 @@ int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* 
   IterParams P;
   fill_iter_params(pl, I1, I2, &P);
   const int max_launches = pl->nscales * pl->cfg.max_iter;
-  ICA_LAUNCH_CHECK(launch_schedule(P, stream));   // work list of the first iteration
-  pl->launches += 1;
   // timing mode 2 brackets every iterate launch with CUDA events: keep the solve in its own launch there
   const bool fused = pl->fused && pl->timing < 2;
-  P.fused = fused ? 1 : 0;
+  P.fused = fused ? 1 : 0;            // (before the first schedule: the work counter's start value depends on it)
   pl->last_launches_per_iter = fused ? 1 : 2;
+  ICA_LAUNCH_CHECK(launch_schedule(P, stream));   // work list of the first iteration
+  pl->launches += 1;
   if (pl->use_graph && pl->timing < 2) {
     // device-side loop: CUDA-graph while node, condition set by the solve kernel
     if (int rc = ensure_loop_graph(pl, I1, I2)) return rc;

@@ -407,7 +407,7 @@ __device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal, bo
     hn->t0 = 0x7fffffffffffffffll; hn->t1 = 0;
     // device-side bookkeeping of the loop: iterations done, time spent in the streaming phase of the iterate kernel
     int cnt = 0;
-    if (first) { P.kernel_ns[0] = 0; P.kernel_ns[1] = 0; }
+    if (first) { P.kernel_ns[0] = 0; P.kernel_ns[1] = 0; P.loop_count[1] = 0; }
     else {
       cnt = cnt_old + 1;
       const SchedHdr* ho = P.hdr + (cnt_old & 1);
@@ -755,6 +755,12 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   // which of the two work lists this launch consumes: one thread decides for the CTA (with the fused solve the counter
   // can advance while a late CTA of the same launch starts; such a CTA simply works on the next iteration's list)
   if (tid == 0) {
+    // safety net of the device-side loop: whatever happens to the scheduling, the graph's while node ends after
+    // max_launches (+ slack) launches of this kernel
+    if (blockIdx.x == 0 && P.cond_handle) {
+      const int n = atomicAdd(P.loop_count + 1, 1);
+      if (n > P.max_launches + 8) cudaGraphSetConditional(P.cond_handle, 0u);
+    }
     s_par = __ldcg(P.loop_count) & 1;
     for (int i = 0; i < kStages; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], kConsumerWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
