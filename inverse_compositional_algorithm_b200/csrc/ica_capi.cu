@@ -311,6 +311,7 @@ void fill_iter_params(const ica_plan* pl, const float* /*I1*/, const float* /*I2
   P->grid_ctas = pl->grid;
   P->fused = 0;                      // the callers that run the fused loop set it
   P->solve_ticket = pl->solve_ticket;
+  P->sched_dirty = pl->loop_count + 2;
   P->asm_tab = pl->asm_tab;
   P->cond_handle = 0;
   P->loop_count = pl->loop_count;
@@ -578,8 +579,8 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   TRY(dev_alloc(pl, &pl->pair_ticket, (size_t)pl->B));
   TRY_CUDA(cudaMemset(pl->pair_ticket, 0, (size_t)pl->B * sizeof(unsigned int)));
   TRY(dev_alloc(pl, &pl->solve_ticket, 1));
-  TRY(dev_alloc(pl, &pl->loop_count, 2));
-  TRY_CUDA(cudaMemset(pl->loop_count, 0, 2 * sizeof(int)));
+  TRY(dev_alloc(pl, &pl->loop_count, 4));      // iterations, iterate launches (safety net), work-list dirty flag
+  TRY_CUDA(cudaMemset(pl->loop_count, 0, 4 * sizeof(int)));
   TRY(dev_alloc(pl, &pl->kernel_ns, 2));
   TRY_CUDA(cudaMemset(pl->kernel_ns, 0, 2 * sizeof(long long)));
   TRY_CUDA(cudaMallocHost((void**)&pl->h_loop, 2 * sizeof(int)));

@@ -203,7 +203,7 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stages
   constexpr int S1W = Stage<C>::S1W, S2W = Stage<C>::S2W, kStages = Stage<C>::kStages;
   unsigned k = 0;   // tiles staged so far by this CTA
   SchedHdr* const hdr = P.hdr + par;
-  const int* const item_pair = P.item_pair + (long long)par * P.B * P.max_chunks;
+  const int* const item_pair = P.item_pair + (long long)__ldcg(&hdr->list) * P.B * P.max_chunks;
   bool first_item = !P.fused;
   const bool pdbg = kTimeline && P.dbg_time != nullptr && lane == 0;   // profiling hook: cycles spent fetching work / waiting for a free stage
   long long pd_fetch = 0, pd_empty = 0, pd_proj = 0, pd_ctl = 0, pd_issue = 0;
@@ -352,6 +352,25 @@ __device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal, bo
   const int B = P.B;
   const int cnt_old = first ? -1 : __ldcg(P.loop_count);
   const int np = (cnt_old + 1) & 1;
+  // No pair changed scale or finished in this iteration: the next work list is the current one.  Re-announce it under the
+  // next header instead of rebuilding it (not with the fused solve, whose late CTAs need the two lists to alternate).
+  if (!first && !P.fused && __ldcg(P.sched_dirty) == 0) {
+    if (tid == 0) {
+      const SchedHdr* ho = P.hdr + (cnt_old & 1);
+      SchedHdr* hn = P.hdr + np;
+      hn->total = ho->total; hn->npairs = ho->npairs; hn->list = ho->list; hn->counter = P.grid_ctas;
+      hn->t0 = 0x7fffffffffffffffll; hn->t1 = 0;
+      const long long t0 = __ldcg(&ho->t0), t1 = __ldcg(&ho->t1);
+      if (t1 > t0 && t1 > 0) { P.kernel_ns[0] += t1 - t0; P.kernel_ns[1] += 1; }
+      const int cnt = cnt_old + 1;
+      *P.solve_ticket = 0;
+      __threadfence();
+      *P.loop_count = cnt;
+      // (the number of unfinished pairs did not change either; a rank of the row-sharded mode may own no work item yet go on)
+      if (P.cond_handle) cudaGraphSetConditional(P.cond_handle, (__ldcg(P.n_active) > 0 && cnt < P.max_launches) ? 1u : 0u);
+    }
+    return;
+  }
   int* const chunk_start = P.chunk_start + (long long)np * (B + 1);
   int* const item_pair = P.item_pair + (long long)np * B * P.max_chunks;
   if (tid == 0) { s_scal[0] = 0; s_scal[1] = 0; s_scal[2] = 0; }   // carry, active pairs, pairs with work
@@ -400,7 +419,8 @@ __device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal, bo
     chunk_start[B] = s_scal[0];
     *P.n_active = s_scal[1];
     SchedHdr* hn = P.hdr + np;
-    hn->total = s_scal[0]; hn->npairs = s_scal[2];
+    hn->total = s_scal[0]; hn->npairs = s_scal[2]; hn->list = np;
+    *P.sched_dirty = 0;
     // CTA i takes item i first (no atomic on its critical path), then claims dynamically.  Not with the fused solve: a CTA
     // of the previous launch that starts late may already work on this list, so there every item is claimed atomically
     hn->counter = P.fused ? 0 : P.grid_ctas;
@@ -666,6 +686,7 @@ __device__ bool solve_pair(const IterParams& P, int pair, int tid, double* s_par
           if (err > P.tol && itn < P.max_iter) {
             st.iter = itn;
           } else {  // this scale is done (ica.py:109, 225)
+            *P.sched_dirty = 1;     // the pair changes level or leaves: the next work list differs
             st.iters_per_scale[s] = itn;
             if (s > 0) {
               double q[ICA_MAX_PARAMS];

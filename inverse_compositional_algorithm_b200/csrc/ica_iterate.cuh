@@ -14,7 +14,7 @@ struct SchedHdr {
   int total;              // work items of the list
   int npairs;             // pairs that own at least one item
   int counter;            // next unclaimed item (dynamic work distribution)
-  int pad_;
+  int list;               // which of the two list buffers holds the items (a list that did not change is reused)
   long long t0, t1;       // %globaltimer: first CTA start / last chunk done of the launch that consumed the list
 };
 
@@ -51,6 +51,7 @@ struct IterParams {
   long long* kernel_ns;         // [2] accumulated time of the streaming phase of the iterate kernel (ns: first CTA start ->
                                 //     last chunk partial written) and number of launches of this run
   unsigned int* solve_ticket;   // pairs solved in the current iteration (the last one schedules the next)
+  int* sched_dirty;             // set when a pair changed scale or finished in this iteration: the work list must be rebuilt
   int shard_rank, shard_n;      // row-sharded mode: this rank's band of tile rows (0, 1 = whole image)
   int solve_mode;               // 0: sum partials + solve; 1: sum partials -> ext_moments only; 2: solve from ext_moments;
                                 // 3: sum partials, exchange them with the other ranks through peer memory, solve

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarises an ncu launch list (gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum; --csv) into
 profiles/: per-kernel time shares of one bench step and the DRAM traffic of ica_iterate_kernel against its
-algorithmic bytes.   usage: make_profiles.py gpurun_out/r1_launches_final.csv"""
+algorithmic bytes.   usage: make_profiles.py <launches.csv> [round prefix, default r1] [bench JSON line of the same command]"""
 import collections
 import csv
 import json
@@ -10,6 +10,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src = sys.argv[1]
+RND = sys.argv[2] if len(sys.argv) > 2 else "r1"
+BENCH = sys.argv[3] if len(sys.argv) > 3 else None
 rows = list(csv.reader(open(src)))
 hdr = None
 launches = collections.OrderedDict()
@@ -45,14 +47,17 @@ summary = {"source": os.path.basename(src),
                       "--clock-control none python bench.py --steps 1 --warmup 1 --batch 32 --streams 1 --no-cpu-baseline --no-e2e",
            "step": "second step of the run (the timed one), 32 pairs, single stream; per-launch times under ncu are cold-cache and serialised",
            "total_us": round(tot, 1), "kernels": agg}
-json.dump(summary, open(os.path.join(ROOT, "profiles", "r1_step_shares.json"), "w"), indent=1)
+json.dump(summary, open(os.path.join(ROOT, "profiles", RND + "_step_shares.json"), "w"), indent=1)
 it = [launches[i] for i in step if "ica_iterate_kernel" in launches[i]["name"]]
 traffic = sum(L.get("dram__bytes_read.sum", 0.0) + L.get("dram__bytes_write.sum", 0.0) for L in it)
-out = {"kernel": "ica_iterate_kernel<3,4>", "source": "profiles/" + os.path.basename(src) + " (see r1_step_shares.json for the command)",
+out = {"kernel": "ica_iterate_kernel<3,4>", "source": "profiles/" + os.path.basename(src) + " (see " + RND + "_step_shares.json for the command)",
        "launches_per_step": len(it), "traffic_bytes_per_step": traffic, "traffic_bytes_per_launch": traffic / max(1, len(it)),
        "pairs_per_step": 32,
-       # algorithmic bytes of the same step (bench.py prints them: Sum_s iterations_s * N_s * 24 B over the 32 pairs of seed 1)
+       # algorithmic bytes of the same step (bench.py prints them: Sum_s iterations_s * N_s * 24 B over the 32 pairs of the step)
        "algorithmic_bytes_per_step_at_capture": 2887778304.0}
+if BENCH:
+    line = [l for l in open(BENCH) if l.startswith("{")][-1]
+    out["algorithmic_bytes_per_step_at_capture"] = json.loads(line)["roofline"]["algorithmic_bytes_per_step"]
 out["traffic_over_algorithmic"] = out["traffic_bytes_per_step"] / out["algorithmic_bytes_per_step_at_capture"]
 json.dump(out, open(os.path.join(ROOT, "profiles", "iterate_dram_bytes.json"), "w"), indent=1)
 print(json.dumps(summary, indent=1))
