@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "libica_b200.so")
-SOURCES = ["ica_iterate.cu", "ica_pyramid.cu", "ica_capi.cu", "ica_helpers.cu", "ica_generate.cu"]
+SOURCES = ["ica_iterate.cu", "ica_march.cu", "ica_pyramid.cu", "ica_capi.cu", "ica_helpers.cu", "ica_generate.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

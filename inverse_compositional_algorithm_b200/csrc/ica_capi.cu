@@ -44,6 +44,8 @@ struct ica_plan {
   int B, H, W, C, nscales, dh;
   int device = 0;                    // the CUDA device the plan's buffers, stream and graph live on
   int max_chunks = 0, grid = 0;
+  int march = 0;                     // 1: column-march K2 (ica_march.cu, opt-in: ICA_K2=march); 0: the tile kernel
+  int chunk_m = 2;                   // march kernel: preferred tiles per consumer warp and chunk (ICA_CHUNK_M)
   int shard_rank = 0, shard_n = 1;   // row-sharded mode (ica_plan_set_row_shard)
   int* chunk_start = nullptr;
   int* item_pair = nullptr;
@@ -246,7 +248,7 @@ int encode_image_map(void* out128, const float* base, int nx, int ny, int C, int
 // maps of levels [s_lo, s_hi) of every pair into the host copy
 int encode_level_maps(ica_plan* pl, int s_lo, int s_hi) {
   int w1, h1, w2, h2;
-  iterate_stage_boxes(pl->C, &w1, &h1, &w2, &h2);
+  if (pl->march) march_stage_boxes(pl->C, &w1, &h1, &w2, &h2); else iterate_stage_boxes(pl->C, &w1, &h1, &w2, &h2);
   for (int b = 0; b < pl->B; ++b)
     for (int s = s_lo; s < s_hi; ++s) {
       const LevelDesc& L = pl->lv[s];
@@ -255,7 +257,8 @@ int encode_level_maps(ica_plan* pl, int s_lo, int s_hi) {
       const int pitch = s == 0 ? pl->k2_pitch : L.pitch;
       unsigned char* rec = pl->tmaps_host.data() + ((size_t)(b * pl->nscales + s) * 2) * 128;
       if (int rc = encode_image_map(rec, i1, L.nx, L.ny, pl->C, pitch, w1, h1, false)) return rc;
-      if (int rc = encode_image_map(rec + 128, i2, L.nx, L.ny, pl->C, pitch, w2, h2, true)) return rc;
+      // (the march kernel evaluates the NaN footprint analytically: its zero-padded weights must never meet a NaN)
+      if (int rc = encode_image_map(rec + 128, i2, L.nx, L.ny, pl->C, pitch, w2, h2, !pl->march)) return rc;
     }
   return ICA_OK;
 }
@@ -286,6 +289,11 @@ int prepare_level0(ica_plan* pl, const float* I1, const float* I2, cudaStream_t 
     pl->tm_I1 = pl->k2_I1; pl->tm_I2 = pl->k2_I2;
   }
   return ICA_OK;
+}
+
+// K2 of this plan: the tile kernel (default) or the column-march kernel (ICA_K2=march)
+cudaError_t launch_k2(const ica_plan* pl, const IterParams& P, cudaStream_t stream) {
+  return pl->march ? launch_march(P, pl->C, pl->dh, pl->grid, stream) : launch_iterate(P, pl->C, pl->dh, pl->grid, stream);
 }
 
 // kernel parameters of the current run (prepare_level0 first)
@@ -323,6 +331,8 @@ void fill_iter_params(const ica_plan* pl, const float* /*I1*/, const float* /*I2
   P->x_error = pl->x_error; P->x_ns = pl->x_ns;
   P->B = pl->B;
   P->max_chunks = pl->max_chunks;
+  P->chunk_unit = pl->march ? march_chunk_unit() : 0;
+  P->chunk_m = pl->chunk_m;
   P->robust_type = pl->cfg.robust_type;
   P->robust_loop = pl->cfg.robust_loop;
   P->lambda_cfg = pl->cfg.lambda_;
@@ -360,7 +370,7 @@ int ensure_loop_graph(ica_plan* pl, const float* I1, const float* I2, int solve_
   P.fused = solve_mode == 0 ? pl->fused : 0;
   P.solve_mode = solve_mode;
   ICA_CUDA_CHECK(cudaStreamBeginCaptureToGraph(pl->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
-  cudaError_t e1 = launch_iterate(P, pl->C, pl->dh, pl->grid, pl->stream);
+  cudaError_t e1 = launch_k2(pl, P, pl->stream);
   cudaError_t e2 = P.fused ? cudaSuccess : launch_solve(P, pl->dh, pl->stream);   // fused: the iterate kernel solves
   cudaGraph_t captured = nullptr;
   cudaError_t e3 = cudaStreamEndCapture(pl->stream, &captured);
@@ -500,7 +510,15 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   pl->B = cfg->batch; pl->H = cfg->height; pl->W = cfg->width; pl->C = cfg->channels; pl->nscales = cfg->nscales;
   pl->ttypes.assign(pl->B, cfg->transform_type);
   pl->dh = moment_degree_of(cfg->transform_type);
-  const int TWv = iterate_tile_w(), THv = iterate_tile_h();
+  {   // which K2: ICA_K2=march selects the column-march kernel (ica_march.cu).  Measured on B200 (round 2,
+      // profiles/README.md) it needs a third of the shared-memory loads but 1.5x the instructions of the tile kernel and
+      // runs at 0.12 instead of 0.24 of the HBM roofline: it stays opt-in.
+    const char* e = getenv("ICA_K2");
+    pl->march = (e && (e[0] == 'm' || e[0] == 'M')) ? 1 : 0;
+    const char* m = getenv("ICA_CHUNK_M");
+    if (m && atoi(m) > 0) pl->chunk_m = atoi(m);
+  }
+  const int TWv = pl->march ? march_tile_w() : iterate_tile_w(), THv = pl->march ? march_tile_h() : iterate_tile_h();
   // level shapes (zoom.zoom_size, src/zoom.py:8-22; skimage uses the same rounding)
   long long off = 0;
   int nx = pl->W, ny = pl->H;
@@ -529,7 +547,7 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
     cudaGetDevice(&dev);
     pl->device = dev;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    pl->grid = iterate_blocks_per_sm() * sms;   // persistent kernel: every CTA resident
+    pl->grid = (pl->march ? 1 : iterate_blocks_per_sm()) * sms;   // persistent kernel: every CTA resident
   }
   int rc = ICA_OK;
 #define TRY(expr) do { if ((rc = (expr)) != ICA_OK) { ica_plan_destroy(pl); return rc; } } while (0)
@@ -591,7 +609,7 @@ int ica_plan_create(const ica_config* cfg, ica_plan** plan_out) {
   // iteration) is available but off by default: measured on B200 (round 2, profiles/README.md) it is SLOWER than the
   // separate 512-thread solve launch -- 28.5 vs 26.9 ms per 256-pair step, 2.39 vs 2.12 ms for a single pair -- the
   // solve is a latency chain that runs worse at the iterate kernel's 80 registers, and it stalls a streaming CTA.
-  pl->fused = getenv("ICA_FUSE") ? 1 : 0;
+  pl->fused = (getenv("ICA_FUSE") && !pl->march) ? 1 : 0;
   TRY(dev_alloc(pl, &pl->asm_tab, (size_t)6 * 72));
   TRY(upload_assembly(pl));
   TRY_CUDA(cudaMemset(pl->solve_ticket, 0, sizeof(unsigned int)));
@@ -730,7 +748,7 @@ int ica_plan_shard_partial(ica_plan* pl, double* moments, void* stream_) {
   IterParams P;
   fill_iter_params(pl, pl->last_I1, pl->last_I2, &P);
   P.solve_mode = 1; P.ext_moments = moments;
-  ICA_LAUNCH_CHECK(launch_iterate(P, pl->C, pl->dh, pl->grid, stream));
+  ICA_LAUNCH_CHECK(launch_k2(pl, P, stream));
   ICA_LAUNCH_CHECK(launch_solve(P, pl->dh, stream));
   pl->launches += 2;
   return ICA_OK;
@@ -862,7 +880,7 @@ int ica_plan_run_row_sharded(ica_plan* pl, const float* I1, const float* I2, dou
     // host-driven variant (profilers): every rank launches the full count; finished iterations are empty
     P.solve_mode = 3;
     for (int it = 0; it < max_launches; ++it) {
-      ICA_LAUNCH_CHECK(launch_iterate(P, pl->C, pl->dh, pl->grid, stream));
+      ICA_LAUNCH_CHECK(launch_k2(pl, P, stream));
       ICA_LAUNCH_CHECK(launch_solve(P, pl->dh, stream));
     }
   }
@@ -907,7 +925,7 @@ int ica_plan_run_device(ica_plan* pl, const float* I1, const float* I2, double* 
     for (int it = 0; it < max_launches && !done; ++it) {
       const bool timed = pl->timing >= 2 && pl->n_ev_iter + 2 <= (int)pl->ev_iter.size();
       if (timed) cudaEventRecord(pl->ev_iter[pl->n_ev_iter++], stream);
-      ICA_LAUNCH_CHECK(launch_iterate(P, pl->C, pl->dh, pl->grid, stream));
+      ICA_LAUNCH_CHECK(launch_k2(pl, P, stream));
       if (timed) cudaEventRecord(pl->ev_iter[pl->n_ev_iter++], stream);
       // per-pair solve / compose; its last block publishes the next work list and the number of unfinished pairs
       if (!fused) ICA_LAUNCH_CHECK(launch_solve(P, pl->dh, stream));
@@ -1370,7 +1388,7 @@ int ica_hessian_b_host(const float* I1, const float* I2, int32_t height, int32_t
     fill_iter_params(pl, pl->in1_dev, pl->in2_dev, &P);
     P.dbg_Hb = d_dbg;
     if (e == cudaSuccess) e = launch_schedule(P, 0);
-    if (e == cudaSuccess) e = launch_iterate(P, channels, pl->dh, pl->grid, 0);
+    if (e == cudaSuccess) e = launch_k2(pl, P, 0);
     if (e == cudaSuccess) e = launch_solve(P, pl->dh, 0);
     double hb[72];
     if (e == cudaSuccess) e = cudaMemcpy(hb, d_dbg, sizeof(hb), cudaMemcpyDeviceToHost);

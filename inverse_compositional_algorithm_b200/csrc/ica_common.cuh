@@ -48,6 +48,34 @@ __host__ __device__ inline int band_tiles(const LevelDesc& L, int rank, int n, i
   return (ty1 - ty0) * L.tiles_x;
 }
 
+// Chunks (= partial slots, work items) of a level with `ntiles` tiles.  unit == 0 (tile kernel, ica_iterate.cu):
+// min(ntiles, max_chunks) chunks of nearly equal size.  unit > 0 (march kernel, ica_march.cu): chunks of unit * m tiles
+// (one or `mpref` tiles per consumer warp; more when max_chunks would be exceeded), the last one shorter.  Neither
+// depends on what else is in the batch.
+__host__ __device__ inline int chunk_tiles(int ntiles, int max_chunks, int unit, int mpref) {
+  int m = ntiles >= 8 * unit ? (mpref > 1 ? mpref : 1) : 1;
+  const int need = (ntiles + unit * max_chunks - 1) / (unit * max_chunks);
+  if (need > m) m = need;
+  return unit * m;
+}
+__host__ __device__ inline int chunk_count(int ntiles, int max_chunks, int unit, int mpref) {
+  if (unit <= 0) return ntiles < max_chunks ? ntiles : max_chunks;
+  if (ntiles <= 0) return 0;
+  const int tpc = chunk_tiles(ntiles, max_chunks, unit, mpref);
+  return (ntiles + tpc - 1) / tpc;
+}
+// tiles [*b, *e) of chunk `chunk` (relative to the first tile of the rank's band)
+__host__ __device__ inline void chunk_range(int chunk, int ntiles, int nch, int max_chunks, int unit, int mpref, int* b, int* e) {
+  if (unit <= 0) {
+    *b = (int)((long long)chunk * ntiles / nch);
+    *e = (int)((long long)(chunk + 1) * ntiles / nch);
+  } else {
+    const int tpc = chunk_tiles(ntiles, max_chunks, unit, mpref);
+    *b = chunk * tpc;
+    *e = *b + tpc < ntiles ? *b + tpc : ntiles;
+  }
+}
+
 // Device-side state of one image pair (one "registration").
 struct PairState {
   double p[ICA_MAX_PARAMS];       // current parameters at `scale`

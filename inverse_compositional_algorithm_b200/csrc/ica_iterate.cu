@@ -381,7 +381,7 @@ __device__ void schedule_block(const IterParams& P, int* s_warp, int* s_scal, bo
     bool act = false;   // a rank whose band is empty at a coarse level still counts the pair as unfinished
     if (b < B) {
       const int s = __ldcg(&P.state[b].scale);
-      if (s >= 0) { int tf; const int nt = band_tiles(P.lv[s], P.shard_rank, P.shard_n, &tf); c = nt < P.max_chunks ? nt : P.max_chunks; }
+      if (s >= 0) { int tf; const int nt = band_tiles(P.lv[s], P.shard_rank, P.shard_n, &tf); c = chunk_count(nt, P.max_chunks, P.chunk_unit, P.chunk_m); }
       act = s >= 0;
     }
     const unsigned actmask = __ballot_sync(0xffffffffu, act);
@@ -531,7 +531,7 @@ __device__ bool solve_pair(const IterParams& P, int pair, int tid, double* s_par
     const int nx = L.nx, ny = L.ny;
     int t_first;
     const int ntiles = band_tiles(L, P.shard_rank, P.shard_n, &t_first);
-    const int nch = ntiles < P.max_chunks ? ntiles : P.max_chunks;
+    const int nch = chunk_count(ntiles, P.max_chunks, P.chunk_unit, P.chunk_m);
     const bool need_h = P.robust_loop || st.iter == 0;
     const int ttype = st.ttype;
     const int n = nparams_of(ttype);

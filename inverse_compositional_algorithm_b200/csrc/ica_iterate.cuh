@@ -65,6 +65,8 @@ struct IterParams {
   long long* x_ns;                   // [2] accumulated exchange time (publish -> all peers seen), exchanges
   int B;
   int max_chunks;         // partial slots per pair
+  int chunk_unit;         // 0: tile kernel (ica_iterate.cu); > 0: march kernel, consumer warps per CTA (ica_common.cuh: chunk_count)
+  int chunk_m;            // march kernel: preferred tiles per consumer warp and chunk
   int traj_cap;
   int robust_type;
   int robust_loop;        // 1: rho' and H every iteration; 0: quadratic loop (H at iter 0 of a scale)
@@ -88,6 +90,12 @@ void iterate_stage_boxes(int channels, int* w1, int* h1, int* w2, int* h2);
 cudaError_t launch_schedule(const IterParams& P, cudaStream_t stream);
 cudaError_t launch_solve(const IterParams& P, int dh, cudaStream_t stream);
 cudaError_t launch_iterate(const IterParams& P, int channels, int dh, int grid, cudaStream_t stream);
+// second-generation K2 (ica_march.cu): same contract as launch_iterate, own tile shape and TMA boxes
+int march_tile_w();
+int march_tile_h();
+int march_chunk_unit();
+void march_stage_boxes(int channels, int* w1, int* h1, int* w2, int* h2);
+cudaError_t launch_march(const IterParams& P, int channels, int dh, int grid, cudaStream_t stream);
 cudaError_t launch_init_state(PairState* state, const double* p_in, const int* ttypes, int B, int nscales,
                               double lambda_cfg, int* n_active, unsigned int* pair_ticket, cudaStream_t stream);
 cudaError_t launch_export_results(const PairState* state, int B, double* p_out, double* err_out, int* iters_out,

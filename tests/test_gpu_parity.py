@@ -888,3 +888,41 @@ def test_fused_solve_mode_matches_default_loop(nat, monkeypatch):
         np.testing.assert_allclose(got[0], ref[0], rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(got[1], ref[1], rtol=1e-6)
     assert got[3] < ref[3]      # one launch per iteration instead of two
+
+
+@pytest.mark.gpu
+def test_march_kernel_matches_tile_kernel(nat, monkeypatch):
+    """The opt-in column-march K2 (ICA_K2=march, csrc/ica_march.cu: register-resident 5 x 5 bicubic window, one new window
+    row per pixel, zero-padded Keys weights, analytic NaN footprint) must register like the default tile kernel: identical
+    iteration counts and parameters within fp32 rounding of the moment sums -- RGB and gray, all moment degrees, a ragged
+    batch, a shape that is not a multiple of the 32 x 16 tile, and a rotation beyond the window's slack (global path)."""
+    from inverse_compositional_algorithm_b200 import _native, synthetic
+    from inverse_compositional_algorithm_b200.transformation import TransformType
+    cases = [
+        (3, 150, 203, [TransformType.HOMOGRAPHY, TransformType.AFFINITY, TransformType.TRANSLATION, TransformType.HOMOGRAPHY], 3, 3.0),
+        (1, 131, 97, [TransformType.SIMILARITY, TransformType.EUCLIDEAN, TransformType.HOMOGRAPHY], 3, 2.0),
+        (3, 96, 160, [TransformType.EUCLIDEAN], 0, 2.0),
+    ]
+    for C, H, W, types, rt, shift in cases:
+        pairs = [synthetic.make_pair(2300 + i, H, W, C, t, max_shift=shift, margin=24) for i, t in enumerate(types)]
+        if len(types) == 1:      # one strongly rotated pair (7 degrees): most pixels leave the register window
+            pairs = [synthetic.make_pair(2400, H, W, C, types[0], margin=24, p_gt=np.array([1.5, -2.0, 0.12]))]
+        I1 = np.stack([a for a, _, _ in pairs]); I2 = np.stack([b for _, b, _ in pairs])
+
+        def run():
+            plan = _native.Plan(batch=len(types), height=H, width=W, channels=C, nscales=3, nu=0.5,
+                                transform_type=types[0].value, robust_type=rt, robust_loop=rt != 0, lambda_=0.0, tol=1e-3,
+                                max_iter=30, delta=5, nanifoutside=True)
+            plan.set_transform_types([t.value for t in types])
+            out = plan.run_host(I1, I2)
+            plan.close()
+            return out[0], out[1], out[2]
+        monkeypatch.delenv("ICA_K2", raising=False)
+        ref = run()
+        monkeypatch.setenv("ICA_K2", "march")
+        got = run()
+        monkeypatch.delenv("ICA_K2", raising=False)
+        assert np.array_equal(got[2], ref[2]), (C, H, W)
+        for b, t in enumerate(types):
+            n = t.nparams()
+            assert _epe(got[0][b, :n], ref[0][b, :n], t.value, W, H) <= 1e-4, (C, H, W, b)
