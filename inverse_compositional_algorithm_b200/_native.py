@@ -120,9 +120,14 @@ def lib():
         if _lib is not None:
             return _lib
         path = _build.LIB_PATH
+        override = os.environ.get("ICA_LIB_PATH")      # tuning hook: a library variant built elsewhere (tools/build_variant.sh)
+        if override:
+            if not os.path.exists(override):
+                raise RuntimeError(f"ICA_LIB_PATH={override} does not exist")
+            path = override
         # rebuild when missing, or when a source is newer than the library and a compiler is at hand (on a box
         # without nvcc the shipped library is used as it is)
-        if not os.path.exists(path) or (_build.is_stale() and _build.have_nvcc()):
+        if not override and (not os.path.exists(path) or (_build.is_stale() and _build.have_nvcc())):
             try:
                 path = _build.build()
             except Exception as exc:  # noqa: BLE001

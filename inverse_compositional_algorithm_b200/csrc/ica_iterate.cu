@@ -45,7 +45,10 @@ constexpr bool kTimeline = true;
 #else
 constexpr bool kTimeline = false;
 #endif
-constexpr int kBlocksPerSM = 2;      // 2 CTAs x 12 warps per SM at 80 registers per thread (16 warps at 64 registers measured 9 % slower)
+#ifndef ICA_BLOCKS_PER_SM
+#define ICA_BLOCKS_PER_SM 2
+#endif
+constexpr int kBlocksPerSM = ICA_BLOCKS_PER_SM;      // 2 CTAs x 12 warps per SM at 80 registers per thread (16 warps at 64 registers measured 9 % slower)
 #ifndef ICA_CONSUMER_WARPS
 #define ICA_CONSUMER_WARPS 11
 #endif
@@ -872,7 +875,8 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
         const int4 geo = lds_i4(&tc->geo);             // x0, y0, nx, ny
         const int y = geo.y + ly;
         if (vrow >= 0 && vrow != y) flush_row();
-        if (y < geo.w) {
+        // rows of the discarded frame (ica.py:85-93) have no gradient: they add exact zeros to every moment -- skip them
+        if (y < geo.w && (!frame || (y >= delta && y < geo.w - delta))) {
           vrow = y;
           const int nx = geo.z, ny = geo.w;
           const bool need_hr = lds_i4(&tc->flg).x != 0;
