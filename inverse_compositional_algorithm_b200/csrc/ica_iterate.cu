@@ -64,6 +64,9 @@ constexpr int S1ROWS = TH + 2;
 #ifndef ICA_BH
 #define ICA_BH 24
 #endif
+#ifndef ICA_S2W_RGB
+#define ICA_S2W_RGB 256           // (tuning hook: 224 = 74 pixels measured no faster)
+#endif
 #ifndef ICA_STAGES_RGB
 #define ICA_STAGES_RGB 2
 #endif
@@ -78,7 +81,7 @@ template <int DH> struct RowVals { static constexpr int K = 3 * (DH + 1) + 2 * (
 // S1ROWS rows).  A box is at most 256 elements wide, its rows are multiples of 16 bytes, and S2W == 0 (mod 32
 // banks), so lanes of a warp that sit on different window rows never collide.
 template <int C> struct Stage {
-  static constexpr int S2W = C == 3 ? 256 : 96;            // floats per window row
+  static constexpr int S2W = C == 3 ? ICA_S2W_RGB : 96;    // floats per window row
   static constexpr int BWPX = S2W / C;                     // window width in pixels (85 RGB, 96 gray)
   static constexpr int S1W = (TW + 2 * HALO) * C;          // 216 (RGB) / 72 (gray) floats per patch row
   static constexpr int kFloats = (BH_MAX * S2W + S1ROWS * S1W + 31) / 32 * 32;   // I2 window, then I1 patch; 128-byte multiple
