@@ -252,6 +252,9 @@ constexpr int kFR = 8;        // outputs per thread along the filtered axis in t
 constexpr int kFRV = 8;       // output rows per thread in the uniform vertical kernel (each input row is read (TP+14)/16 times)
 
 struct FastW { float w[kFastTapsMax]; };
+// the same weights paired for packed fp32 arithmetic on two neighbouring outputs of a 2:1 level: wp[j] = (w[j], w[j-2]),
+// zero outside [0, taps) -- an input sample j contributes to output i with weight w[j - 2 i]
+struct FastW2 { float2 wp[kFastTapsMax + 2]; };
 
 // logical index of the general kernels -> output index, skipping the range [lo, hi) the fast kernel covers
 __device__ __forceinline__ int skip_range(int i, int lo, int hi) { return i < lo ? i : i + (hi - lo); }
@@ -558,7 +561,7 @@ template <int C> struct FusedCfg {
 template <int C, int TP, bool GATHER>
 __global__ void __launch_bounds__(128) pyr_fused_fast_kernel(
     const float* __restrict__ in0a, const float* __restrict__ in0b, int nset, long long in_stride, int in_pitch, int ncols,
-    int oy_lo, int s0y, const FastW fwy, int ox_lo, int ox_hi, int s0x, const FastW fwx,
+    int oy_lo, int s0y, const FastW fwy, int ox_lo, int ox_hi, int s0x, const FastW2 fwx,
     float* __restrict__ out0a, float* __restrict__ out0b, long long out_stride, int out_pitch,
     const MinMaxKeys* __restrict__ mm_parent, MinMaxKeys* __restrict__ mm_child, int mm_stride,
     MinMaxKeys* __restrict__ mm_gather) {
@@ -652,18 +655,18 @@ __global__ void __launch_bounds__(128) pyr_fused_fast_kernel(
     const int ox = ox0 + og * kFH;
     if (ox >= ox_hi) continue;                       // partial last strip (ox_hi - ox_lo is a multiple of kFH)
     const float* src = &stmp[r][(PADN + 1) * og + c];
-    float acc[kFH];
-#pragma unroll
-    for (int i = 0; i < kFH; ++i) acc[i] = 0.f;
+    // outputs (0, 1) and (2, 3) as two packed accumulators: per input sample two FFMA2 with the paired weights instead
+    // of up to four FFMA (element by element the same fmaf sequence: the terms outside a band carry weight zero)
+    static_assert(kFH == 4, "two packed accumulator pairs");
+    float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < TP + 2 * (kFH - 1); ++j) {
       const float v = src[C * j + j / (2 * kFH)];
-#pragma unroll
-      for (int i = 0; i < kFH; ++i) {
-        const int k = j - 2 * i;
-        if (k >= 0 && k < TP) acc[i] = fmaf(fwx.w[k], v, acc[i]);
-      }
+      const float2 v2 = make_float2(v, v);
+      if (j < TP + 2) a01 = __ffma2_rn(fwx.wp[j], v2, a01);
+      if (j >= 4) a23 = __ffma2_rn(fwx.wp[j - 4], v2, a23);
     }
+    const float acc[kFH] = {a01.x, a01.y, a23.x, a23.y};
     float* o = out0 + (long long)(oy + r) * out_pitch + ox * C + c;
 #pragma unroll
     for (int i = 0; i < kFH; ++i) {
@@ -960,8 +963,11 @@ static void launch_fused(const float* in0a, const float* in0b, int nset, long lo
                          float* out0a, float* out0b, long long out_stride, int out_pitch,
                          const MinMaxKeys* mm_parent, MinMaxKeys* mm_child, int mm_stride, cudaStream_t stream,
                          MinMaxKeys* mm_gather, int* own /* r0, r1, f0, f1 of the gathered region */) {
-  FastW fwy, fwx;
-  for (int k = 0; k < kFastTapsMax; ++k) { fwy.w[k] = fy.w[k]; fwx.w[k] = fx.w[k]; }
+  FastW fwy;
+  FastW2 fwx;
+  for (int k = 0; k < kFastTapsMax; ++k) fwy.w[k] = fy.w[k];
+  for (int j = 0; j < kFastTapsMax + 2; ++j)
+    fwx.wp[j] = make_float2(j < TP ? fx.w[j] : 0.f, (j >= 2 && j - 2 < TP) ? fx.w[j - 2] : 0.f);
   constexpr int OWB = FusedCfg<C>::OWB;
   dim3 grid((hhi - hlo + OWB - 1) / OWB, ngv, 2 * nset);
   if (mm_gather) {
