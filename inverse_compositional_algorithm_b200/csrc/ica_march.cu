@@ -59,7 +59,7 @@ constexpr int kItemPairBitsM = 20;
 #define MSTAT_ADD(slot, val) do { if (P.dbg_time && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(P.dbg_time) + blockIdx.x * 16 + (slot), (unsigned long long)(val)); } while (0)
 #define MSTAT_CLK() clock64()
 #else
-#define MSTAT_ADD(slot, val) do { } while (0)
+#define MSTAT_ADD(slot, val) do { (void)(val); } while (0)
 #define MSTAT_CLK() 0ll
 #endif
 
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(kMThreads, 1) ica_march_kernel(const __grid_co
       }
       try_issue();
       const MTile* const cur = &tiles[cs];
-      const int x0 = cur->x0, y0 = cur->y0, nrows = cur->nrows, ng = cur->ng, nst = cur->nst;
+      const int x0 = cur->x0, y0 = cur->y0, nrows = cur->nrows, nst = cur->nst;
       const unsigned q0 = cur->q0;
       const bool tfits = cur->fits != 0;
       MSTAT_ADD(0, 1); if (!tfits) MSTAT_ADD(1, 1);

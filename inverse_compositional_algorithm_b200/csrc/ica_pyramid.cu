@@ -249,7 +249,10 @@ namespace {
 constexpr int kVR = 4;        // output rows per thread in the vertical pass
 constexpr int kMaxTaps = 128;
 constexpr int kFR = 8;        // outputs per thread along the filtered axis in the uniform (fast) horizontal kernel
-constexpr int kFRV = 8;       // output rows per thread in the uniform vertical kernel (each input row is read (TP+14)/16 times)
+#ifndef ICA_KFRV
+#define ICA_KFRV 8
+#endif
+constexpr int kFRV = ICA_KFRV;       // output rows per thread in the uniform vertical kernel (each input row is read (TP+14)/16 times)
 
 struct FastW { float w[kFastTapsMax]; };
 // the same weights paired for packed fp32 arithmetic on two neighbouring outputs of a 2:1 level: wp[j] = (w[j], w[j-2]),
