@@ -64,6 +64,9 @@ constexpr int S1ROWS = TH + 2;
 #ifndef ICA_BH
 #define ICA_BH 24
 #endif
+#ifndef ICA_PRODUCER_SLEEP
+#define ICA_PRODUCER_SLEEP 200     // ns between the producer's polls of an `empty` barrier (tuning hook)
+#endif
 #ifndef ICA_S2W_RGB
 #define ICA_S2W_RGB 256           // (tuning hook: 224 = 74 pixels measured no faster)
 #endif
@@ -135,7 +138,7 @@ __device__ __forceinline__ void mbar_wait_backoff(unsigned long long* bar, unsig
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     if (done) break;
-    __nanosleep(200);
+    __nanosleep(ICA_PRODUCER_SLEEP);
   }
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, unsigned long long* bar) {
