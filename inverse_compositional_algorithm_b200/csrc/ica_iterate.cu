@@ -761,7 +761,11 @@ __global__ void __launch_bounds__(kSolveThreads) ica_solve_kernel(const __grid_c
 }
 
 // ============================================================ the kernel
-template <int C, int DH>
+// MODE 1 / 2 / 3 = the common configurations as compile-time constants (1: robust loop with the Lorentzian rho', 2:
+// quadratic loop, 3: robust loop with Geman-McClure; all with the discarded frame and skimage's warp domain): their
+// per-pixel code has no mode branches, which is worth 4-5 % of the kernel time.  MODE 0 reads the modes from the
+// parameters.
+template <int C, int DH, int MODE>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(const __grid_constant__ IterParams P) {
   constexpr int K = RowVals<DH>::K;
   constexpr int HW = DH + 1;        // x-powers kept for the Hessian moments
@@ -808,11 +812,11 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
 
   // ------------------------------------------------------------------ consumers
   const int delta = P.delta;
-  const bool frame = P.frame != 0;
-  const bool robust = P.robust_loop != 0;
-  const float chm = P.ch_mult;
-  const int rtype = P.robust_type;
-  const bool ipol = P.ipol_warp != 0, ipol_nan = P.ipol_nan != 0;
+  const bool frame = MODE != 0 ? true : P.frame != 0;
+  const bool robust = (MODE == 1 || MODE == 3) ? true : (MODE == 2 ? false : P.robust_loop != 0);
+  const float chm = C == 3 ? 1.0f : P.ch_mult;      // (only a gray image can stand for its RGB replication)
+  const int rtype = MODE == 1 ? (int)LORENTZIAN : (MODE == 2 ? (int)QUADRATIC : (MODE == 3 ? (int)GERMAN_MCCLURE : P.robust_type));
+  const bool ipol = MODE != 0 ? false : P.ipol_warp != 0, ipol_nan = MODE != 0 ? false : P.ipol_nan != 0;
   // fp64 accumulators of the chunk in progress, double-buffered over consecutive chunks: [2][kConsumerWarps][K][kYPow]
   double* const accs0 = reinterpret_cast<double*>(smem + kStages * Stage<C>::kFloats);
   constexpr int kAccSet = kConsumerWarps * K * kYPow;
@@ -885,7 +889,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
         if (y < geo.w && (!frame || (y >= delta && y < geo.w - delta))) {
           vrow = y;
           const int nx = geo.z, ny = geo.w;
-          const bool need_hr = lds_i4(&tc->flg).x != 0;
+          const bool need_hr = (MODE == 1 || MODE == 3) ? true : lds_i4(&tc->flg).x != 0;
           // moments of one pixel: v[] += (rho' S, rho' v) * x^a.  Consecutive powers share a packed FFMA2 (the weight
           // is its broadcast operand): element by element the same fmaf as the scalar form.
           auto add_moments = [&](float scl, float sxx, float sxy, float syy, float vx, float vy, float xf) {
@@ -943,6 +947,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
             const float tmax = fmaxf(fmaxf(tx2.x, tx2.y), fmaxf(ty2.x, ty2.y));
             if (tmin < kTie || tmax > 1.0f - kTie) {
               // (rare) a coordinate next to an integer: the exact fp64 evaluation decides the tap set
+              // (kept inline: as an out-of-line call its by-reference results live in local memory, measured 3 % slower)
               WarpCoef coef;
               coef.d00 = q0.x; coef.m01 = q0.z; coef.m02 = q1.x; coef.m10 = q1.z; coef.d11 = q2.x; coef.m12 = q2.z; coef.m20 = q3.x; coef.m21 = q3.z;
               float a, b;
@@ -1285,8 +1290,8 @@ __global__ void ica_gradient_kernel(const float* __restrict__ img, int nx, int n
   }
 }
 
-template <int C, int DH>
-cudaError_t launch_iterate_t(const IterParams& P, int grid, cudaStream_t stream) {
+template <int C, int DH, int MODE>
+cudaError_t launch_iterate_m(const IterParams& P, int grid, cudaStream_t stream) {
   constexpr size_t smem = Stage<C>::kStages * (size_t)Stage<C>::kFloats * sizeof(float) +
                           2 * (size_t)kConsumerWarps * RowVals<DH>::K * kYPow * sizeof(double);
   // the attribute belongs to the (device, function) pair: configure once per device
@@ -1295,12 +1300,22 @@ cudaError_t launch_iterate_t(const IterParams& P, int grid, cudaStream_t stream)
   cudaGetDevice(&dev);
   const unsigned long long bit = 1ull << (dev & 63);
   if (!(configured.load(std::memory_order_acquire) & bit)) {
-    cudaError_t e = cudaFuncSetAttribute(ica_iterate_kernel<C, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ica_iterate_kernel<C, DH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured.fetch_or(bit, std::memory_order_release);
   }
-  ica_iterate_kernel<C, DH><<<grid, kThreads, smem, stream>>>(P);
+  ica_iterate_kernel<C, DH, MODE><<<grid, kThreads, smem, stream>>>(P);
   return cudaGetLastError();
+}
+
+template <int C, int DH>
+cudaError_t launch_iterate_t(const IterParams& P, int grid, cudaStream_t stream) {
+  if (P.frame && !P.ipol_warp) {
+    if (P.robust_loop && P.robust_type == LORENTZIAN) return launch_iterate_m<C, DH, 1>(P, grid, stream);
+    if (P.robust_loop && P.robust_type == GERMAN_MCCLURE) return launch_iterate_m<C, DH, 3>(P, grid, stream);
+    if (!P.robust_loop) return launch_iterate_m<C, DH, 2>(P, grid, stream);
+  }
+  return launch_iterate_m<C, DH, 0>(P, grid, stream);
 }
 
 }  // namespace
