@@ -56,6 +56,7 @@ constexpr int kConsumerWarps = ICA_CONSUMER_WARPS;   // + 1 producer warp = 12 w
 constexpr int kRowsPerWarp = 1;      // rows of a tile per consumer warp
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = kConsumerThreads + 32;   // + one producer warp
+constexpr int kChunkRing = 8;       // chunk records in flight per CTA (> the deepest pipeline + 2)
 constexpr int kItemPairBits = 20;   // a work item = pair | chunk << 20 (one read tells the producer both)
 constexpr int TW = 64;            // tile width  (2 pixels per lane: x0+lane, x0+32+lane)
 constexpr int TH = kRowsPerWarp * kConsumerWarps;   // tile height (row y0 + warp + rr * kConsumerWarps for warp, rr)
@@ -208,9 +209,10 @@ __device__ __noinline__ float sample_global_slow(const float* __restrict__ img, 
 template <int C>
 __device__ __forceinline__ void producer_loop(const IterParams& P, float* stages, int stage_floats,
                                               unsigned long long* full, unsigned long long* empty, TileCtl* tctl,
-                                              double* pm64, int par, int lane) {
+                                              double* pm64, int4* cinfo, int par, int lane) {
   constexpr int S1W = Stage<C>::S1W, S2W = Stage<C>::S2W, kStages = Stage<C>::kStages;
   unsigned k = 0;   // tiles staged so far by this CTA
+  unsigned cseq = 0;   // chunks started so far by this CTA
   SchedHdr* const hdr = P.hdr + par;
   const int* const item_pair = P.item_pair + (long long)__ldcg(&hdr->list) * P.B * P.max_chunks;
   bool first_item = !P.fused;
@@ -262,6 +264,10 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stages
     const int nch = ntiles < P.max_chunks ? ntiles : P.max_chunks;
     const int t_begin = t_first + (int)((long long)chunk * ntiles / nch);
     const int t_end = t_first + (int)((long long)(chunk + 1) * ntiles / nch);
+    // what the consumers need at the chunk's epilogue, in a ring that outlives the stages (the producer is at most
+    // kStages tiles, hence chunks, ahead): published by the `full` barrier of the chunk's first tile
+    if (lane == 0) cinfo[cseq & (kChunkRing - 1)] = make_int4(pair, chunk, nch, 0);
+    ++cseq;
 
     if (kTimeline && P.dbg_time && k == 0 && lane == 0) P.dbg_time[blockIdx.x * 16 + 9] = gtime();
     if (pdbg) pd_fetch += clock64() - pf0;
@@ -774,12 +780,14 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   constexpr int S2W = Stage<C>::S2W;
   constexpr int NENT = K * kYPow;
   constexpr int kStages = Stage<C>::kStages;
+  static_assert(kChunkRing >= kStages + 2 && (kChunkRing & (kChunkRing - 1)) == 0, "chunk records outlive the stages");
 
   extern __shared__ __align__(128) float smem[];
   float* const stages = smem;                      // kStages x Stage<C>::kFloats
   __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages];
   __shared__ TileCtl tctl[kStages];
   __shared__ double s_pm64[9];
+  __shared__ int4 s_cinfo[kChunkRing];
   __shared__ __align__(8) SolveShared s_solve;     // fused solve / scheduling (the CTA that finishes a pair's last chunk)
   __shared__ int s_par, s_last;
 
@@ -806,7 +814,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
   if (tid == 0) atomicMin(&hdr->t0, gtime());
 
   if (warp == kConsumerWarps) {
-    producer_loop<C>(P, stages, Stage<C>::kFloats, s_full, s_empty, tctl, s_pm64, par, lane);
+    producer_loop<C>(P, stages, Stage<C>::kFloats, s_full, s_empty, tctl, s_pm64, s_cinfo, par, lane);
     return;
   }
 
@@ -862,7 +870,6 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
 #pragma unroll
       for (int b = 0; b < kYPow; ++b) myacc[b] = 0.0;
     }
-    int pair = 0, chunk = 0, nch = 1;
     bool last;
     bool stop = false;
     do {
@@ -1006,12 +1013,18 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
             float2 mgx, mgy;
             {
               const int4 msk = lds_i4(&tc->msk);   // gxlo, gxspan, fxlo, fxspan
-              const bool yin = !frame || (y >= delta && y < ny - delta);
-              const bool gyrow = yin && y >= 1 && y <= ny - 2;
-              mgx = make_float2((yin && (unsigned)(xA - msk.x) < (unsigned)msk.y) ? 0.5f : 0.0f,
-                                (yin && (unsigned)(xB - msk.x) < (unsigned)msk.y) ? 0.5f : 0.0f);
-              mgy = make_float2((gyrow && (unsigned)(xA - msk.z) < (unsigned)msk.w) ? 0.5f : 0.0f,
-                                (gyrow && (unsigned)(xB - msk.z) < (unsigned)msk.w) ? 0.5f : 0.0f);
+              // (rows of the frame never get here: see the row test above)
+              mgx = make_float2((unsigned)(xA - msk.x) < (unsigned)msk.y ? 0.5f : 0.0f,
+                                (unsigned)(xB - msk.x) < (unsigned)msk.y ? 0.5f : 0.0f);
+              if (MODE != 0) {
+                // with a frame (delta >= 1) every remaining row has a central y-difference, and the columns with an
+                // x-gradient are exactly the columns inside the frame: one mask serves both gradients
+                mgy = mgx;
+              } else {
+                const bool gyrow = y >= 1 && y <= ny - 2;
+                mgy = make_float2((gyrow && (unsigned)(xA - msk.z) < (unsigned)msk.w) ? 0.5f : 0.0f,
+                                  (gyrow && (unsigned)(xB - msk.z) < (unsigned)msk.w) ? 0.5f : 0.0f);
+              }
             }
             const float2 nmgx = make_float2(-mgx.x, -mgx.y), nmgy = make_float2(-mgy.x, -mgy.y);
             const float* cA = s1 + (ly + 1) * S1W + (lane + HALO) * C;
@@ -1110,13 +1123,14 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
           }
         }
       }
-      if (last) { pair = tc->pair; chunk = tc->chunk; nch = tc->nch; }   // (before the stage and its TileCtl are released)
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sidx]);   // this warp is done with the stage (and its TileCtl)
       ++k;
     } while (!last);
     if (stop) break;
     if (vrow >= 0) flush_row();   // the chunk's last row segment
+    const int4 ci = s_cinfo[nitems & (kChunkRing - 1)];     // pair, chunk, chunks of the pair (written by the producer)
+    const int pair = ci.x, chunk = ci.y, nch = ci.z;
     ++nitems;
     ICA_STAMP(2);
     const long long e0 = dbg ? clock64() : 0;
