@@ -935,14 +935,19 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
             const float fy = (float)y, fxa = (float)xA;
             const float2 fy2 = make_float2(fy, fy), nfy2 = make_float2(-fy, -fy);
             const float2 fx2 = make_float2(fxa, fxa + 32.0f), nfx2 = make_float2(-fxa, -(fxa + 32.0f));
-            const float2 zm1 = __ffma2_rn(make_float2(q3.x, q3.y), fx2, __fmul2_rn(make_float2(q3.z, q3.w), fy2));
             float2 nx_ = __ffma2_rn(make_float2(q0.x, q0.y), fx2, __ffma2_rn(make_float2(q0.z, q0.w), fy2, make_float2(q1.x, q1.y)));
             float2 ny_ = __ffma2_rn(make_float2(q1.z, q1.w), fx2, __ffma2_rn(make_float2(q2.x, q2.y), fy2, make_float2(q2.z, q2.w)));
-            nx_ = __ffma2_rn(nfx2, zm1, nx_);
-            ny_ = __ffma2_rn(nfy2, zm1, ny_);
-            const float zA = 1.0f + zm1.x, zB = 1.0f + zm1.y;
-            const float2 rz = make_float2(fast_rcp(zA), fast_rcp(zB));
-            const float2 dx2 = __fmul2_rn(nx_, rz), dy2 = __fmul2_rn(ny_, rz);
+            float2 dx2 = nx_, dy2 = ny_;
+            if (DH == 4) {
+              // (only a batch with a homography has moment degree 4: for the affine family the bottom row of the matrix is
+              // (0, 0, 1), z is exactly 1 and the perspective terms below are exact no-ops, so they are not issued)
+              const float2 zm1 = __ffma2_rn(make_float2(q3.x, q3.y), fx2, __fmul2_rn(make_float2(q3.z, q3.w), fy2));
+              nx_ = __ffma2_rn(nfx2, zm1, nx_);
+              ny_ = __ffma2_rn(nfy2, zm1, ny_);
+              const float zA = 1.0f + zm1.x, zB = 1.0f + zm1.y;
+              const float2 rz = make_float2(fast_rcp(zA), fast_rcp(zB));
+              dx2 = __fmul2_rn(nx_, rz); dy2 = __fmul2_rn(ny_, rz);
+            }
             const float flxA = floorf(dx2.x), flxB = floorf(dx2.y), flyA = floorf(dy2.x), flyB = floorf(dy2.y);
             tx2 = make_float2(dx2.x - flxA, dx2.y - flxB);
             ty2 = make_float2(dy2.x - flyA, dy2.y - flyB);
