@@ -99,7 +99,7 @@ template <int C> struct Stage {
 // kernel: nothing tile-constant is kept in registers across the tap loads).  The warp coefficients are stored
 // duplicated, (c, c): they are operands of packed fp32 arithmetic on the lane's two pixels.
 struct __align__(16) TileCtl {
-  float2 c2[8];           // d00, m01, m02, m10, d11, m12, m20, m21 of WarpCoef, each as (c, c)
+  float c8[8];            // d00, m01, m02, m10, d11, m12, m20, m21 of WarpCoef (broadcast operands of the packed arithmetic)
   int4 geo;               // x0, y0, nx, ny
   int4 win;               // bx0, by0, bw - 3, bh - 3: the staged I2 window as corner + unsigned limits (0, 0: no window)
   int4 msk;               // gxlo, gxspan: columns with an in-frame x-gradient; fxlo, fxspan: columns inside the frame
@@ -305,10 +305,8 @@ __device__ __forceinline__ void producer_loop(const IterParams& P, float* stages
       if (tile < t_begin + kStages) {   // first use of this stage's control block by the chunk: per-chunk constants
         if (lane < 9) tc.m64[lane] = pm64[lane];
         if (lane == 0) {
-          tc.c2[0] = make_float2(coef.d00, coef.d00); tc.c2[1] = make_float2(coef.m01, coef.m01);
-          tc.c2[2] = make_float2(coef.m02, coef.m02); tc.c2[3] = make_float2(coef.m10, coef.m10);
-          tc.c2[4] = make_float2(coef.d11, coef.d11); tc.c2[5] = make_float2(coef.m12, coef.m12);
-          tc.c2[6] = make_float2(coef.m20, coef.m20); tc.c2[7] = make_float2(coef.m21, coef.m21);
+          tc.c8[0] = coef.d00; tc.c8[1] = coef.m01; tc.c8[2] = coef.m02; tc.c8[3] = coef.m10;
+          tc.c8[4] = coef.d11; tc.c8[5] = coef.m12; tc.c8[6] = coef.m20; tc.c8[7] = coef.m21;
           tc.fl = make_float4(lo, hi, lambda2, 0.0f);
           // columns inside the discarded frame (ica.py:85-93) and, of those, the ones with a central x-difference
           const int fxlo = P.frame ? P.delta : 0;
@@ -931,17 +929,19 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
           int cxA, cyA, cxB, cyB;
           float2 tx2, ty2;
           {
-            const float4 q0 = lds_f4(&tc->c2[0]), q1 = lds_f4(&tc->c2[2]), q2 = lds_f4(&tc->c2[4]), q3 = lds_f4(&tc->c2[6]);
+            const float4 qa = lds_f4(&tc->c8[0]), qb = lds_f4(&tc->c8[4]);   // d00, m01, m02, m10 / d11, m12, m20, m21
+            const float2 c_d00 = make_float2(qa.x, qa.x), c_m01 = make_float2(qa.y, qa.y), c_m02 = make_float2(qa.z, qa.z);
+            const float2 c_m10 = make_float2(qa.w, qa.w), c_d11 = make_float2(qb.x, qb.x), c_m12 = make_float2(qb.y, qb.y);
             const float fy = (float)y, fxa = (float)xA;
             const float2 fy2 = make_float2(fy, fy), nfy2 = make_float2(-fy, -fy);
             const float2 fx2 = make_float2(fxa, fxa + 32.0f), nfx2 = make_float2(-fxa, -(fxa + 32.0f));
-            float2 nx_ = __ffma2_rn(make_float2(q0.x, q0.y), fx2, __ffma2_rn(make_float2(q0.z, q0.w), fy2, make_float2(q1.x, q1.y)));
-            float2 ny_ = __ffma2_rn(make_float2(q1.z, q1.w), fx2, __ffma2_rn(make_float2(q2.x, q2.y), fy2, make_float2(q2.z, q2.w)));
+            float2 nx_ = __ffma2_rn(c_d00, fx2, __ffma2_rn(c_m01, fy2, c_m02));
+            float2 ny_ = __ffma2_rn(c_m10, fx2, __ffma2_rn(c_d11, fy2, c_m12));
             float2 dx2 = nx_, dy2 = ny_;
             if (DH == 4) {
               // (only a batch with a homography has moment degree 4: for the affine family the bottom row of the matrix is
               // (0, 0, 1), z is exactly 1 and the perspective terms below are exact no-ops, so they are not issued)
-              const float2 zm1 = __ffma2_rn(make_float2(q3.x, q3.y), fx2, __fmul2_rn(make_float2(q3.z, q3.w), fy2));
+              const float2 zm1 = __ffma2_rn(make_float2(qb.z, qb.z), fx2, __fmul2_rn(make_float2(qb.w, qb.w), fy2));
               nx_ = __ffma2_rn(nfx2, zm1, nx_);
               ny_ = __ffma2_rn(nfy2, zm1, ny_);
               const float zA = 1.0f + zm1.x, zB = 1.0f + zm1.y;
@@ -961,7 +961,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
               // (rare) a coordinate next to an integer: the exact fp64 evaluation decides the tap set
               // (kept inline: as an out-of-line call its by-reference results live in local memory, measured 3 % slower)
               WarpCoef coef;
-              coef.d00 = q0.x; coef.m01 = q0.z; coef.m02 = q1.x; coef.m10 = q1.z; coef.d11 = q2.x; coef.m12 = q2.z; coef.m20 = q3.x; coef.m21 = q3.z;
+              coef.d00 = qa.x; coef.m01 = qa.y; coef.m02 = qa.z; coef.m10 = qa.w; coef.d11 = qb.x; coef.m12 = qb.y; coef.m20 = qb.z; coef.m21 = qb.w;
               float a, b;
               project_px(coef, tc->m64, xA, y, cxA, cyA, a, b); tx2.x = a; ty2.x = b;
               project_px(coef, tc->m64, xB, y, cxB, cyB, a, b); tx2.y = a; ty2.y = b;
@@ -1066,8 +1066,8 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) ica_iterate_kernel(con
             const int4 win = lds_i4(&tc->win);
             const float4 fl = lds_f4(&tc->fl);
             WarpCoef coef;
-            coef.d00 = tc->c2[0].x; coef.m01 = tc->c2[1].x; coef.m02 = tc->c2[2].x; coef.m10 = tc->c2[3].x;
-            coef.d11 = tc->c2[4].x; coef.m12 = tc->c2[5].x; coef.m20 = tc->c2[6].x; coef.m21 = tc->c2[7].x;
+            coef.d00 = tc->c8[0]; coef.m01 = tc->c8[1]; coef.m02 = tc->c8[2]; coef.m10 = tc->c8[3];
+            coef.d11 = tc->c8[4]; coef.m12 = tc->c8[5]; coef.m20 = tc->c8[6]; coef.m21 = tc->c8[7];
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
               const int x = half ? xB : xA;
